@@ -232,7 +232,7 @@ class Parser:
         if self.accept("op", "+"):
             return self.unary()
         if self.accept("op", "^"):
-            return ("not", self.unary())  # resolved by the enclosing conversion
+            return ~self.unary() & ((1 << 64) - 1)  # every ^x in the tables is a uint64
         if self.accept("op", "&"):
             return self.unary()
         return self.primary()
