@@ -1,0 +1,145 @@
+/*
+ * simdjson_b200.h -- C ABI of the B200-native simdjson parse engine.
+ *
+ * This is the drop-in boundary for the ONE hot path of minio/simdjson-go that this
+ * library replaces.  The reference has no FFI of its own
+ * (pure Go + Go assembly); the seam is
+ *
+ *     (*internalParsedJson).parseMessage(msg []byte, ndjson bool) error
+ *                                                     parse_json_amd64.go:52
+ *
+ * Everything above it (Parse / ParseND / ParseNDStream, simdjson_amd64.go:66,82,116)
+ * and everything that reads its result (Iter / Object / Array / Serializer) stays host
+ * code and only sees the output triple { Message, Tape []uint64, Strings.B []byte },
+ * which is bit-exact with the reference.  INTEGRATION.md shows the cgo binding.
+ *
+ * Plain pointers and sizes only: no CUDA or torch types appear in any signature.
+ * All functions are thread-safe on distinct contexts; one context serialises its calls.
+ */
+#ifndef SIMDJSON_B200_H
+#define SIMDJSON_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* flags (parse_json_amd64.go:58-62 ndjson; options.go:13 WithCopyStrings) */
+#define SJ_FLAG_NDJSON 1u
+#define SJ_FLAG_COPY_STRINGS 2u
+
+/* return codes.  Only nil / non-nil matters to the reference's callers; the two parse
+ * errors keep the reference's precedence (stage 1 wins, parse_json_amd64.go:123-126). */
+#define SJ_OK 0
+#define SJ_ERR_STAGE1 1     /* "Failed to find all structural indices for stage 1"  parse_json_amd64.go:93,104 */
+#define SJ_ERR_STAGE2 2     /* "Bad parsing while executing stage 2"                parse_json_amd64.go:81,112 */
+#define SJ_ERR_NO_DEVICE 3  /* "Host CPU does not meet target specs" analogue       simdjson_amd64.go:43 */
+#define SJ_ERR_CAPACITY 4   /* caller buffer too small; *_len hold the required sizes */
+#define SJ_ERR_TOO_LARGE 5  /* message longer than SJ_MAX_MESSAGE bytes per call */
+#define SJ_ERR_ARGUMENT 6
+/* negative values: -(1000 + cudaError_t) */
+
+#define SJ_MAX_MESSAGE 0x7fffff00ull /* positions are uint32, string lengths keep one flag bit */
+
+typedef struct sj_ctx sj_ctx;
+
+/* simdjson_amd64.go:37 SupportedCPU(): 1 when an sm_100 device is usable */
+int sj_supported(void);
+int sj_device_count(void);
+const char* sj_error_string(int rc);
+
+/* One context = one CUDA stream + reusable device scratch (the analogue of the reused
+ * *ParsedJson internals, simdjson_amd64.go:46-51).  device < 0 selects the current device. */
+int sj_ctx_create(int device, sj_ctx** out);
+void sj_ctx_destroy(sj_ctx* ctx);
+
+/* pinned host memory for callers that want full PCIe speed (optional) */
+void* sj_host_alloc(size_t bytes);
+void sj_host_free(void* p);
+
+/* Safe output sizes for a message of `len` bytes (SURVEY.md 8b "ownership"). */
+void sj_bounds(size_t len, size_t* tape_cap, size_t* strings_cap);
+
+/*
+ * parseMessage replacement (parse_json_amd64.go:52-127), HOST buffers.
+ *   msg/len      raw message; trimmed like bytes.TrimSpace; *msg_off / *msg_len give the
+ *                trimmed window = ParsedJson.Message (string offsets are relative to it)
+ *   tape         receives ParsedJson.Tape   (tape_cap entries available)
+ *   strings      receives ParsedJson.Strings.B (strings_cap bytes available)
+ * Returns SJ_OK, SJ_ERR_STAGE1, SJ_ERR_STAGE2, SJ_ERR_CAPACITY, ... (see above).
+ */
+int sj_parse(sj_ctx* ctx, const uint8_t* msg, size_t len, uint32_t flags, uint64_t* tape, size_t tape_cap,
+             size_t* tape_len, uint8_t* strings, size_t strings_cap, size_t* strings_len, size_t* msg_off,
+             size_t* msg_len);
+
+/*
+ * Same parse with everything resident in device memory (inputs already in HBM, outputs
+ * left in HBM): the building block for batch pipelines and what bench.py's `value` times.
+ *   d_msg        device pointer, 16-byte aligned, readable up to round_up(len,16); NOT
+ *                trimmed by this call (callers pass the trimmed window)
+ *   d_tape / d_strings   device output buffers
+ */
+int sj_parse_device(sj_ctx* ctx, const uint8_t* d_msg, size_t len, uint32_t flags, uint64_t* d_tape, size_t tape_cap,
+                    size_t* tape_len, uint8_t* d_strings, size_t strings_cap, size_t* strings_len);
+
+/*
+ * Stage 1 + flatten only (findStructuralIndices, stage1_find_marks_amd64.go:41):
+ * writes the concatenated uint32 index deltas the reference would hand to stage 2
+ * (flatten_bits_amd64.s:26-60: delta to the previous structural, first = position+1).
+ * HOST buffers; msg is used as given (no trimming).  *n is exact even on SJ_ERR_CAPACITY.
+ * Returns SJ_OK or SJ_ERR_STAGE1 (indices are still written), ...
+ */
+int sj_find_structural_indices(sj_ctx* ctx, const uint8_t* msg, size_t len, int ndjson, uint32_t* deltas,
+                               size_t cap, size_t* n);
+
+/* Device-resident stage 1: positions (deltas = 0) or deltas (deltas = 1) into d_out. */
+typedef struct {
+    uint64_t n_idx;
+    uint32_t error;          /* control character inside a string */
+    uint32_t ends_in_string;
+    uint32_t last_pos;
+    uint32_t overflow;
+} sj_stage1_info;
+int sj_stage1_device(sj_ctx* ctx, const uint8_t* d_msg, size_t len, int ndjson, int deltas, uint32_t* d_out,
+                     size_t cap, sj_stage1_info* info);
+/* asynchronous launch of the same kernel on the context's stream (no result read-back);
+ * used by bench.py to time the kernel alone with CUDA events */
+int sj_stage1_launch(sj_ctx* ctx, const uint8_t* d_msg, size_t len, int ndjson, int deltas, uint32_t* d_out,
+                     size_t cap);
+/* CUDA-event timing helpers on the context's stream (bench only) */
+int sj_ctx_sync(sj_ctx* ctx);
+int sj_event_record(sj_ctx* ctx, int which /*0 = start, 1 = stop*/);
+int sj_event_elapsed_ms(sj_ctx* ctx, float* ms);
+int sj_kernel_launches(sj_ctx* ctx, uint64_t* count); /* kernels launched by this context so far */
+
+/* ---- unit-test hooks: the reference's per-routine Go stubs replayed on the device code ----
+ * find_subroutines_amd64.go:26-231.  For block i: in = blocks + 64*i and
+ * carry_in[4*i..] = { prev_iter_ends_odd_backslash, prev_iter_inside_quote (0 / ~0),
+ * prev_iter_ends_pseudo_pred, ndjson }.  out[12*i..] = { odd_ends, quote_mask, quote_bits,
+ * error_mask, whitespace, structurals(raw), structurals_finalized (incl. newlines if
+ * ndjson), raw newline mask (before & ~quote_mask), carry_out odd_backslash, carry_out inside_quote, carry_out
+ * pseudo_pred, any-control-character flag }.  Host buffers. */
+int sj_test_block_masks(sj_ctx* ctx, const uint8_t* blocks, size_t nblocks, const uint64_t* carry_in, uint64_t* out);
+/* finalize_structurals on caller-provided masks: in[5*i..] = {structurals, whitespace,
+ * quote_mask, quote_bits, prev_pseudo}; out[2*i..] = {structurals, prev_pseudo'} */
+int sj_test_finalize(sj_ctx* ctx, const uint64_t* in, size_t n, uint64_t* out);
+/* flatten_bits_incremental over a sequence of 64-bit masks (flatten_bits_amd64.s:26),
+ * carried = 0 and position = ^0 initially */
+int sj_test_flatten_bits(sj_ctx* ctx, const uint64_t* masks, size_t nmasks, uint32_t* deltas, size_t cap, size_t* n);
+/* parse_string_validate_only + parse_string (parse_string_amd64.go:33,48) for a batch:
+ * string i = buf[offs[i] .. offs[i+1]) starting AT its opening quote; max_size[i] is
+ * maxStringSize.  ok[i], src_len[i], dst_len[i]; unescaped bytes are written at
+ * dst + offs[i].  Host buffers. */
+int sj_test_parse_strings(sj_ctx* ctx, const uint8_t* buf, const uint64_t* offs, size_t n, const uint64_t* max_size,
+                          uint8_t* ok, uint64_t* src_len, uint64_t* dst_len, uint8_t* dst);
+/* parseNumber (parse_number.go:65) for a batch: number i = buf[offs[i] .. offs[i+1]);
+ * tag[i] = tape tag word (tag << 56 | flags, 0 on failure), val[i] = raw value */
+int sj_test_parse_numbers(sj_ctx* ctx, const uint8_t* buf, const uint64_t* offs, size_t n, uint64_t* tag,
+                          uint64_t* val);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

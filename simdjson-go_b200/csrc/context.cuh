@@ -1,0 +1,55 @@
+// context.cuh -- per-context CUDA stream, events and grow-only device scratch.
+#pragma once
+#include <cstdint>
+#include <cstdlib>
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    // grow-only; contents are not preserved
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + (bytes >> 3) + 4096;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            e = cudaMalloc(&p, bytes);  // retry without slack
+            want = bytes;
+        }
+        if (e != cudaSuccess) return -(1000 + (int)e);
+        cap = want;
+        return 0;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T* as() const {
+        return reinterpret_cast<T*>(p);
+    }
+};
+
+struct sj_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    uint64_t launches = 0;
+    // stage 1
+    DevBuf msg;      // device copy of the (trimmed) message, padded
+    DevBuf idx;      // structural positions (uint32)
+    DevBuf desc;     // look-back descriptors (3 x nslabs x u64)
+    DevBuf result;   // Stage1Result + Stage2Result
+    void* host_result = nullptr;  // pinned mirror
+    // stage 2
+    DevBuf s2a, s2b, s2c, s2d, s2e, s2f, s2g;
+    DevBuf tape, strings;  // device outputs for the host-buffer API
+    DevBuf test_in, test_out, test_aux;
+};

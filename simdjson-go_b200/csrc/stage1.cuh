@@ -1,0 +1,612 @@
+// stage1.cuh -- K1 `stage1_flatten`: structural-index discovery + flatten_bits as ONE
+// sm_100a kernel (the reference also fuses them: find_structural_bits_amd64.s:56-115).
+//
+// Replaces, per 64-byte block:
+//   find_odd_backslash_sequences     find_odd_backslash_sequences_amd64.s:24-61
+//   find_quote_mask_and_bits         find_quote_mask_and_bits_amd64.s:49-84   (CLMUL -> shift/xor prefix + warp ballot parity)
+//   find_whitespace_and_structurals  find_whitespace_and_structurals_amd64.s:62-103 (VPSHUFB LUTs -> SWAR compares)
+//   finalize_structurals             finalize_structurals_amd64.s:19-36
+//   find_newline_delimiters          find_newline_delimiters_amd64.s:16-28    (NDJSON)
+//   flatten_bits_incremental         flatten_bits_amd64.s:26-60               (serial tzcnt -> popcount + warp scan compaction)
+// and the driver loop of stage1_find_marks_amd64.go:41-148.
+//
+// Shape: persistent grid (1 CTA per SM), S1_WARPS warps per CTA, each warp owns one
+// 8 KiB slab at a time (round-robin over the message).  A slab is staged HBM -> shared
+// memory by one 1-D TMA bulk copy per warp into a per-warp double buffer (the next slab
+// streams in while the current one is processed); lane L of the warp owns the 64-byte
+// block L of each of the slab's four 2 KiB steps and reads it with four conflict-free
+// 16-byte LDS.  Carries across blocks use ballots inside a warp; carries across slabs use
+// two decoupled look-back chains (in-string parity, then structural count / last
+// position); the odd-backslash and pseudo-predecessor carries are recovered from the 32
+// bytes in front of the slab.
+#pragma once
+#include "common.cuh"
+
+namespace sj {
+
+constexpr int S1_WARPS = 12;
+constexpr int S1_THREADS = S1_WARPS * 32;
+constexpr int S1_STEPS = 4;
+constexpr int S1_STEP_BYTES = 32 * 64;
+constexpr int S1_SLAB_BYTES = S1_STEPS * S1_STEP_BYTES;  // 8 KiB per look-back
+constexpr int S1_BUFS = 2;
+constexpr size_t S1_SMEM_BYTES = (size_t)S1_WARPS * S1_BUFS * S1_SLAB_BYTES + S1_WARPS * S1_BUFS * 8 + 128;
+
+struct Stage1Result {
+    uint32_t n_idx;           // total structurals found
+    uint32_t error;           // != 0: control character (< 0x20) inside a string
+    uint32_t ends_in_string;  // message ends inside an unterminated string
+    uint32_t last_pos;        // position of the last structural (valid if n_idx > 0)
+    uint32_t overflow;        // index buffer too small (n_idx is still exact)
+    uint32_t ticket;          // next unclaimed slab (dynamic assignment keeps the look-back deadlock-free
+                              // even when not every CTA of the grid is resident)
+    uint32_t pad[2];
+};
+
+// ---------------------------------------------------------------------------------
+// byte classification: SWAR on 32-bit words, flags land in bit 7 of each byte
+// ---------------------------------------------------------------------------------
+struct WordFlags {
+    uint32_t bs, qt, st, sp;
+};
+
+__device__ __forceinline__ WordFlags classify_word(uint32_t v, uint32_t& ctacc) {
+    const uint32_t L7 = 0x7f7f7f7fu, H = 0x80808080u;
+    uint32_t v7 = v & L7;
+    // (x ^ C) + 0x7f: bit 7 set iff (byte & 0x7f) != C.  Bytes >= 0x80 are removed by "| v".
+    uint32_t tbs = (v7 ^ 0x5c5c5c5cu) + L7;
+    uint32_t tqt = (v7 ^ 0x22222222u) + L7;
+    uint32_t tcm = (v7 ^ 0x2c2c2c2cu) + L7;
+    uint32_t tcl = (v7 ^ 0x3a3a3a3au) + L7;
+    uint32_t tsp = (v7 ^ 0x20202020u) + L7;
+    // { } [ ] in one test: (b + 1) & 0xDD == 0x5C  <=>  b in {5b,5d,7b,7d}
+    uint32_t tbr = (((v7 + 0x01010101u) & 0x5d5d5d5du) ^ 0x5c5c5c5cu) + L7;
+    uint32_t tct = v7 + 0x60606060u;  // bit 7 set iff (byte & 0x7f) >= 0x20
+    WordFlags f;
+    f.bs = ~(tbs | v) & H;
+    f.qt = ~(tqt | v) & H;
+    f.st = ~((tbr & tcm & tcl) | v) & H;
+    f.sp = ~(tsp | v) & H;
+    ctacc |= ~(tct | v);
+    return f;
+}
+
+struct WordFlagsSlow {
+    uint32_t ct, wsc, nl;
+};
+
+__device__ __forceinline__ WordFlagsSlow classify_word_slow(uint32_t v) {
+    const uint32_t L7 = 0x7f7f7f7fu, H = 0x80808080u;
+    uint32_t v7 = v & L7;
+    uint32_t tct = v7 + 0x60606060u;
+    uint32_t ge9 = v7 + 0x77777777u;  // >= 0x09
+    uint32_t geb = v7 + 0x75757575u;  // >= 0x0b
+    uint32_t tcr = (v7 ^ 0x0d0d0d0du) + L7;
+    uint32_t tnl = (v7 ^ 0x0a0a0a0au) + L7;
+    WordFlagsSlow f;
+    f.ct = ~(tct | v) & H;
+    f.wsc = ((ge9 & ~geb) | ~tcr) & ~v & H;
+    f.nl = ~(tnl | v) & H;
+    return f;
+}
+
+// gather the four bit-7 flags of a word into the next nibble of an accumulator
+// (words are fed most-significant first): acc = acc << 4 | flags
+__device__ __forceinline__ uint32_t gather4(uint32_t flags, uint32_t acc) {
+    return __funnelshift_l(flags * 0x00204081u, acc, 4);
+}
+
+__device__ __forceinline__ uint64_t mk64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+
+// rotate a 64-bit mask left by 16*r bits (r = 0..3): undoes the bank-conflict-free
+// chunk rotation used when a lane reads its 64 bytes from shared memory
+__device__ __forceinline__ uint64_t rotl16x(uint64_t m, uint32_t r) {
+    uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
+    if (r & 2) {
+        uint32_t t = lo;
+        lo = hi;
+        hi = t;
+    }
+    uint32_t s = (r & 1) * 16;
+    uint32_t nlo = __funnelshift_l(hi, lo, s);
+    uint32_t nhi = __funnelshift_l(lo, hi, s);
+    return mk64(nlo, nhi);
+}
+
+struct BlockMasks {
+    uint64_t bs, qt, st, sp;
+    uint32_t anyct;
+};
+
+// w[16]: the block's 16 words in slot order
+__device__ __forceinline__ BlockMasks classify_block(const uint32_t (&w)[16]) {
+    uint32_t bs_lo = 0, bs_hi = 0, qt_lo = 0, qt_hi = 0, st_lo = 0, st_hi = 0, sp_lo = 0, sp_hi = 0, ct = 0;
+#pragma unroll
+    for (int k = 7; k >= 0; k--) {
+        WordFlags f = classify_word(w[k], ct);
+        bs_lo = gather4(f.bs, bs_lo);
+        qt_lo = gather4(f.qt, qt_lo);
+        st_lo = gather4(f.st, st_lo);
+        sp_lo = gather4(f.sp, sp_lo);
+    }
+#pragma unroll
+    for (int k = 15; k >= 8; k--) {
+        WordFlags f = classify_word(w[k], ct);
+        bs_hi = gather4(f.bs, bs_hi);
+        qt_hi = gather4(f.qt, qt_hi);
+        st_hi = gather4(f.st, st_hi);
+        sp_hi = gather4(f.sp, sp_hi);
+    }
+    BlockMasks m;
+    m.bs = mk64(bs_lo, bs_hi);
+    m.qt = mk64(qt_lo, qt_hi);
+    m.st = mk64(st_lo, st_hi);
+    m.sp = mk64(sp_lo, sp_hi);
+    m.anyct = ct & 0x80808080u;
+    return m;
+}
+
+struct SlowMasks {
+    uint64_t ct, wsc, nl;
+};
+
+__device__ __forceinline__ SlowMasks classify_block_slow(const uint32_t (&w)[16]) {
+    uint32_t a_lo = 0, a_hi = 0, b_lo = 0, b_hi = 0, c_lo = 0, c_hi = 0;
+#pragma unroll
+    for (int k = 7; k >= 0; k--) {
+        WordFlagsSlow f = classify_word_slow(w[k]);
+        a_lo = gather4(f.ct, a_lo);
+        b_lo = gather4(f.wsc, b_lo);
+        c_lo = gather4(f.nl, c_lo);
+    }
+#pragma unroll
+    for (int k = 15; k >= 8; k--) {
+        WordFlagsSlow f = classify_word_slow(w[k]);
+        a_hi = gather4(f.ct, a_hi);
+        b_hi = gather4(f.wsc, b_hi);
+        c_hi = gather4(f.nl, c_hi);
+    }
+    SlowMasks m;
+    m.ct = mk64(a_lo, a_hi);
+    m.wsc = mk64(b_lo, b_hi);
+    m.nl = mk64(c_lo, c_hi);
+    return m;
+}
+
+// ---------------------------------------------------------------------------------
+// 64-bit mask algebra (same formulas as the reference's scalar tail of each routine)
+// ---------------------------------------------------------------------------------
+// find_odd_backslash_sequences_amd64.s:27-58 ; prev in {0,1}
+__device__ __forceinline__ uint64_t odd_backslash_ends(uint64_t bs, uint32_t prev, uint32_t* carry_out) {
+    const uint64_t even_bits = 0x5555555555555555ull, odd_bits = 0xAAAAAAAAAAAAAAAAull;
+    uint64_t p = prev;
+    uint64_t starts = bs & ~(bs << 1);
+    uint64_t even_starts = starts & (even_bits ^ p);
+    uint64_t odd_starts = starts & (odd_bits ^ p);
+    uint64_t even_carries = bs + even_starts;
+    uint64_t odd_carries = bs + odd_starts;
+    if (carry_out) *carry_out = odd_carries < bs;
+    odd_carries |= p;
+    return (even_carries & ~bs & odd_bits) | (odd_carries & ~bs & even_bits);
+}
+
+// find_quote_mask_and_bits_amd64.s:66: carry-less multiply by all-ones == prefix XOR
+__device__ __forceinline__ uint64_t prefix_xor64(uint64_t x) {
+    uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+    lo ^= lo << 1;
+    hi ^= hi << 1;
+    lo ^= lo << 2;
+    hi ^= hi << 2;
+    lo ^= lo << 4;
+    hi ^= hi << 4;
+    lo ^= lo << 8;
+    hi ^= hi << 8;
+    lo ^= lo << 16;
+    hi ^= hi << 16;
+    hi ^= (uint32_t)((int32_t)lo >> 31);  // parity of the low half carries into the high half
+    return mk64(lo, hi);
+}
+
+// finalize_structurals_amd64.s:19-36 ; pp_in in {0,1}; *pp_out = pseudo_pred >> 63
+__device__ __forceinline__ uint64_t finalize_structurals(uint64_t st, uint64_t ws, uint64_t qm, uint64_t qb,
+                                                         uint32_t pp_in, uint32_t* pp_out) {
+    uint64_t s = (st & ~qm) | qb;
+    uint64_t pred = s | ws;
+    uint64_t shifted = (pred << 1) | pp_in;
+    *pp_out = (uint32_t)(pred >> 63);
+    uint64_t pseudo = shifted & ~ws & ~qm;
+    s |= pseudo;
+    s &= ~(qb & ~qm);
+    return s;
+}
+
+// ---------------------------------------------------------------------------------
+// flatten: one warp emits the structurals of one 2 KiB step (lane L holds the 64-bit
+// mask of block L).  Positions are written in order at out[base + ...]; in delta mode
+// each entry is the distance from the previous structural (reference format,
+// flatten_bits_amd64.s:26-60: first delta of the message = position + 1).
+// `prev_last` is the position of the last structural before this step (0xffffffff = none).
+// Returns the number of structurals in the step; updates prev_last.
+// ---------------------------------------------------------------------------------
+template <bool DELTAS>
+__device__ __forceinline__ uint32_t flatten_step(uint64_t S, uint32_t blockpos, uint32_t* __restrict__ out,
+                                                 uint64_t base, uint64_t cap, uint32_t& prev_last, uint32_t& overflow) {
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t lo = (uint32_t)S, hi = (uint32_t)(S >> 32);
+    uint32_t c = __popc(lo) + __popc(hi);
+    // warp inclusive scan of counts
+    uint32_t inc = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(FULL, inc, d);
+        if (lane >= d) inc += t;
+    }
+    uint32_t total = __shfl_sync(FULL, inc, 31);
+    uint64_t off = base + (inc - c);
+    // last structural of this lane and of the nearest non-empty lane below
+    uint32_t own_last = blockpos + (hi ? 63 - __clz(hi) : 31 - __clz(lo | 1));
+    uint32_t ne = __ballot_sync(FULL, c != 0);
+    uint32_t below = ne & lanemask_lt();
+    uint32_t src = below ? 31 - __clz(below) : 0;
+    uint32_t got = __shfl_sync(FULL, own_last, src);
+    uint32_t prev = below ? got : prev_last;
+    uint32_t top = ne ? 31 - __clz(ne) : 0;
+    uint32_t newlast = __shfl_sync(FULL, own_last, top);
+    if (ne) prev_last = newlast;
+    if (base + total > cap) {  // warp-uniform
+        overflow = 1;
+        return total;
+    }
+    uint32_t pos0 = blockpos;
+    while (lo) {
+        uint32_t b = __ffs(lo) - 1;
+        lo &= lo - 1;
+        uint32_t p = pos0 + b;
+        out[off++] = DELTAS ? p - prev : p;
+        prev = p;
+    }
+    pos0 += 32;
+    while (hi) {
+        uint32_t b = __ffs(hi) - 1;
+        hi &= hi - 1;
+        uint32_t p = pos0 + b;
+        out[off++] = DELTAS ? p - prev : p;
+        prev = p;
+    }
+    return total;
+}
+
+// ---------------------------------------------------------------------------------
+// look-back chains.  Descriptor word = value << 2 | status (0 empty, 1 aggregate of the
+// slab alone, 2 inclusive prefix).  One warp inspects 32 predecessors per round.
+// ---------------------------------------------------------------------------------
+constexpr uint64_t ST_AGG = 1, ST_INC = 2;
+
+__device__ __forceinline__ uint32_t lookback_parity(const uint64_t* desc, int slab) {
+    const int lane = threadIdx.x & 31;
+    uint32_t par = 0;
+    for (int j = slab - 1;; j -= 32) {
+        int idx = j - lane;
+        uint64_t d;
+        do {
+            d = idx >= 0 ? ld_relaxed_u64(desc + idx) : ST_INC;
+        } while (__any_sync(FULL, (d & 3) == 0));
+        uint32_t incl = __ballot_sync(FULL, (d & 3) == ST_INC);
+        uint32_t bits = __ballot_sync(FULL, (d >> 2) & 1);
+        if (incl) {
+            int f = __ffs(incl) - 1;
+            uint32_t m = f == 31 ? FULL : ((2u << f) - 1);
+            return par ^ (__popc(bits & m) & 1);
+        }
+        par ^= __popc(bits) & 1;
+    }
+}
+
+// count chain (desc_c) and last-structural-position chain (desc_p, value = pos + 1, 0 = none).
+// The two words of a slab are separate relaxed stores, so each chain trusts only the
+// status bits of its own word.
+__device__ __forceinline__ void lookback_count(const uint64_t* desc_c, const uint64_t* desc_p, int slab,
+                                               uint64_t& count, uint32_t& last_plus1) {
+    const int lane = threadIdx.x & 31;
+    uint64_t total = 0;
+    uint32_t last = 0;
+    bool cdone = false, pdone = false;
+    for (int j = slab - 1; !(cdone && pdone); j -= 32) {
+        int idx = j - lane;
+        uint64_t c, p;
+        do {
+            c = idx >= 0 ? ld_relaxed_u64(desc_c + idx) : ST_INC;
+            p = idx >= 0 ? ld_relaxed_u64(desc_p + idx) : ST_INC;
+        } while (__any_sync(FULL, (c & 3) == 0 || (p & 3) == 0));
+        if (!cdone) {
+            uint32_t incl = __ballot_sync(FULL, (c & 3) == ST_INC);
+            int f = incl ? __ffs(incl) - 1 : 31;
+            uint64_t v = lane <= f ? (c >> 2) : 0;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+            total += v;
+            cdone = incl != 0;
+        }
+        if (!pdone) {
+            uint32_t incl = __ballot_sync(FULL, (p & 3) == ST_INC);
+            int f = incl ? __ffs(incl) - 1 : 31;
+            uint32_t m = f == 31 ? FULL : ((2u << f) - 1);
+            uint32_t pv = (uint32_t)(p >> 2);
+            uint32_t nz = __ballot_sync(FULL, pv != 0) & m;
+            uint32_t cand = __shfl_sync(FULL, pv, nz ? __ffs(nz) - 1 : 0);
+            if (nz) last = cand;
+            pdone = nz != 0 || incl != 0;
+        }
+    }
+    count = total;
+    last_plus1 = last;
+}
+
+// ---------------------------------------------------------------------------------
+// carries recovered from the bytes in front of a slab: length of the run of backslashes
+// that ends just before `end` (warp-cooperative, 32 bytes per round; one round in practice)
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t backslash_run_before(const uint8_t* __restrict__ msg, uint64_t end) {
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t run = 0;
+    for (uint64_t off = 0;; off += 32) {
+        uint64_t back = off + lane + 1;  // lane L looks at byte end-1-off-L
+        uint32_t c = back <= end ? msg[end - back] : 0x20;
+        uint32_t B = __ballot_sync(FULL, c == '\\');
+        uint32_t n = B == FULL ? 32 : __ffs(~B) - 1;
+        run += n;
+        if (n < 32) return run;
+    }
+}
+
+struct Stage1Params {
+    const uint8_t* msg;  // 16-byte aligned, readable up to round_up(len, 16)
+    uint64_t len;
+    uint32_t* out;       // positions (or deltas)
+    uint64_t out_cap;
+    uint64_t* desc_par;  // [nslabs] zeroed
+    uint64_t* desc_cnt;  // [nslabs] zeroed
+    uint64_t* desc_pos;  // [nslabs] zeroed
+    Stage1Result* result;
+    int nslabs;
+};
+
+__device__ __forceinline__ void load_block_words(const uint8_t* buf, uint32_t lane, uint32_t (&w)[16]) {
+    // lane's 64 bytes live at buf + 64*lane; read the four 16-byte chunks in the rotated
+    // order (j + lane/2) & 3 so that every quarter-warp touches all 32 banks once
+    const uint4* base = reinterpret_cast<const uint4*>(buf + 64 * lane);
+    const uint32_t r = (lane >> 1) & 3;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        uint4 q = base[(j + r) & 3];
+        w[4 * j + 0] = q.x;
+        w[4 * j + 1] = q.y;
+        w[4 * j + 2] = q.z;
+        w[4 * j + 3] = q.w;
+    }
+}
+
+// bytes at or beyond `len` read as 0x20 (find_structural_bits_amd64.s:134-155)
+__device__ __forceinline__ void mask_tail(uint32_t (&w)[16], uint32_t lane, uint64_t blockpos, uint64_t len) {
+    if (blockpos + 64 <= len) return;
+    const uint32_t r = (lane >> 1) & 3;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        uint32_t chunk = ((k >> 2) + r) & 3;
+        uint64_t wpos = blockpos + chunk * 16 + (k & 3) * 4;
+        uint32_t v = w[k];
+        if (wpos >= len) {
+            v = 0x20202020u;
+        } else if (wpos + 4 > len) {
+            uint32_t keep = (uint32_t)(len - wpos);  // 1..3 valid bytes
+            uint32_t m = (1u << (8 * keep)) - 1;
+            v = (v & m) | (0x20202020u & ~m);
+        }
+        w[k] = v;
+    }
+}
+
+template <bool NDJSON, bool DELTAS>
+__global__ void __launch_bounds__(S1_THREADS, 1) stage1_flatten_kernel(const Stage1Params p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t* wbuf = smem + (size_t)warp * S1_BUFS * S1_SLAB_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S1_WARPS * S1_BUFS * S1_SLAB_BYTES) + warp * S1_BUFS;
+    const uint64_t len16 = (p.len + 15) & ~15ull;
+
+    if (lane == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+
+    auto issue = [&](int slab, int b) {
+        if (lane == 0 && slab < p.nslabs) {
+            uint64_t start = (uint64_t)slab * S1_SLAB_BYTES;
+            uint32_t bytes = (uint32_t)min((uint64_t)S1_SLAB_BYTES, len16 - start);
+            mbar_expect_tx(&bars[b], bytes);
+            tma_load_1d(wbuf + (size_t)b * S1_SLAB_BYTES, p.msg + start, bytes, &bars[b]);
+        }
+    };
+
+    auto ticket = [&]() -> int {
+        int t = 0;
+        if (lane == 0) t = (int)atomicAdd(&p.result->ticket, 1u);
+        return __shfl_sync(FULL, t, 0);
+    };
+
+    int slab = ticket();
+    uint32_t phasebits = 0;
+    int b = 0;
+    issue(slab, 0);
+
+    while (slab < p.nslabs) {
+        const int next_slab = ticket();
+        issue(next_slab, b ^ 1);  // next slab streams in while this one is processed
+        const uint64_t slab_start = (uint64_t)slab * S1_SLAB_BYTES;
+        const uint8_t* buf = wbuf + (size_t)b * S1_SLAB_BYTES;
+
+        // carries that depend only on raw bytes in front of the slab
+        uint32_t bs_carry = 0, prevc = 0x20, prevc_esc = 0;
+        if (slab > 0) {
+            bs_carry = backslash_run_before(p.msg, slab_start) & 1;
+            prevc = p.msg[slab_start - 1];
+            if (prevc == '"') prevc_esc = backslash_run_before(p.msg, slab_start - 1) & 1;  // warp-uniform
+        }
+
+        mbar_wait(&bars[b], (phasebits >> b) & 1);
+        phasebits ^= 1u << b;
+
+        // ---------------- phase A: classify, escape analysis, slab quote parity ----------------
+        uint64_t qb[S1_STEPS], st[S1_STEPS], sp[S1_STEPS];
+        uint32_t ctmask = 0;  // bit s: step s has a control character somewhere in the warp
+        uint32_t slab_par = 0;
+#pragma unroll
+        for (int s = 0; s < S1_STEPS; s++) {
+            uint32_t w[16];
+            load_block_words(buf + s * S1_STEP_BYTES, lane, w);
+            const uint64_t blockpos = slab_start + (uint64_t)s * S1_STEP_BYTES + 64 * lane;
+            mask_tail(w, lane, blockpos, p.len);
+            BlockMasks m = classify_block(w);
+            const uint32_t r = (lane >> 1) & 3;
+            uint64_t bs = rotl16x(m.bs, r), qt = rotl16x(m.qt, r);
+            st[s] = rotl16x(m.st, r);
+            sp[s] = rotl16x(m.sp, r);
+            if (__any_sync(FULL, m.anyct != 0)) ctmask |= 1u << s;
+
+            // odd-backslash carry into each lane's block (warp-uniform fast path: no backslashes at all)
+            uint64_t odd_ends = 0;
+            if (__any_sync(FULL, bs != 0) || bs_carry) {
+                uint32_t allbs = bs == ~0ull;
+                uint32_t trail_odd = (bs == ~0ull) ? 0 : (__clzll(~bs) & 1);
+                uint32_t A = __ballot_sync(FULL, allbs);
+                uint32_t F = __ballot_sync(FULL, trail_odd);
+                uint32_t below = ~A & lanemask_lt();
+                uint32_t cin = below ? (F >> (31 - __clz(below))) & 1 : bs_carry;
+                uint32_t nonpass = ~A;
+                bs_carry = nonpass ? (F >> (31 - __clz(nonpass))) & 1 : bs_carry;
+                odd_ends = odd_backslash_ends(bs, cin, nullptr);
+            }
+            qb[s] = qt & ~odd_ends;
+            uint32_t P = __ballot_sync(FULL, (__popcll(qb[s]) & 1) != 0);
+            slab_par ^= __popc(P) & 1;
+        }
+
+        // ---------------- chain 1: in-string parity at slab entry ----------------
+        uint32_t par_in = 0;
+        if (slab == 0) {
+            if (lane == 0) st_relaxed_u64(p.desc_par + slab, ((uint64_t)slab_par << 2) | ST_INC);
+        } else {
+            if (lane == 0) st_relaxed_u64(p.desc_par + slab, ((uint64_t)slab_par << 2) | ST_AGG);
+            par_in = lookback_parity(p.desc_par, slab);
+            if (lane == 0) st_relaxed_u64(p.desc_par + slab, ((uint64_t)(slab_par ^ par_in) << 2) | ST_INC);
+        }
+
+        // pseudo-structural predecessor carry into the slab (finalize_structurals_amd64.s:24-27;
+        // initial value 1: stage1_find_marks_amd64.go:54)
+        uint32_t pp_carry = 1;
+        if (slab > 0) {
+            uint32_t is_q = prevc == '"' && !prevc_esc;
+            uint32_t is_ws = prevc == 0x20 || prevc == 0x09 || prevc == 0x0a || prevc == 0x0d;
+            uint32_t is_st = prevc == '{' || prevc == '}' || prevc == '[' || prevc == ']' || prevc == ':' || prevc == ',';
+            // prevc not a quote: its quote_mask bit equals the in-string state after it (= par_in)
+            pp_carry = is_q | is_ws | (is_st & (par_in ^ 1));
+        }
+
+        // ---------------- phase B: quote mask, finalize, counts ----------------
+        uint64_t S[S1_STEPS];
+        uint32_t err = 0;
+        uint32_t par = par_in;
+        uint32_t slab_count = 0;
+#pragma unroll
+        for (int s = 0; s < S1_STEPS; s++) {
+            uint32_t P = __ballot_sync(FULL, (__popcll(qb[s]) & 1) != 0);
+            uint32_t lane_in = par ^ (__popc(P & lanemask_lt()) & 1);
+            par ^= __popc(P) & 1;
+            uint64_t qm = prefix_xor64(qb[s]) ^ (lane_in ? ~0ull : 0ull);
+            uint64_t ws = sp[s];
+            uint64_t nl = 0;
+            if (ctmask & (1u << s)) {  // warp-uniform slow path: tab / LF / CR / other control characters present
+                uint32_t w[16];
+                load_block_words(buf + s * S1_STEP_BYTES, lane, w);
+                const uint64_t blockpos = slab_start + (uint64_t)s * S1_STEP_BYTES + 64 * lane;
+                mask_tail(w, lane, blockpos, p.len);
+                SlowMasks sm = classify_block_slow(w);
+                const uint32_t r = (lane >> 1) & 3;
+                ws |= rotl16x(sm.wsc, r);
+                if (rotl16x(sm.ct, r) & qm) err = 1;  // find_quote_mask_and_bits_amd64.s:69-80
+                if (NDJSON) nl = rotl16x(sm.nl, r) & ~qm;  // find_newline_delimiters_amd64.s:17-27
+            }
+            // pseudo_pred bit of the previous block: previous lane, or the carry for lane 0
+            uint64_t s0 = (st[s] & ~qm) | qb[s];
+            uint32_t my_pp = (uint32_t)((s0 | ws) >> 63);
+            uint32_t up = __shfl_up_sync(FULL, my_pp, 1);
+            uint32_t pp_in = lane == 0 ? pp_carry : up;
+            pp_carry = __shfl_sync(FULL, my_pp, 31);
+            uint32_t dummy;
+            uint64_t fin = finalize_structurals(st[s], ws, qm, qb[s], pp_in, &dummy);
+            if (NDJSON) fin |= nl;
+            S[s] = fin;
+            slab_count += __popcll(fin);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) slab_count += __shfl_xor_sync(FULL, slab_count, d);
+        if (__any_sync(FULL, err)) {
+            if (lane == 0) atomicOr(&p.result->error, 1u);
+        }
+
+        // last structural of the slab (pos + 1, 0 = none)
+        uint32_t own_last1 = 0;
+#pragma unroll
+        for (int s = S1_STEPS - 1; s >= 0; s--) {
+            if (own_last1 == 0 && S[s] != 0)
+                own_last1 = (uint32_t)(slab_start + (uint64_t)s * S1_STEP_BYTES + 64 * lane + 63 - __clzll(S[s])) + 1;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) own_last1 = max(own_last1, __shfl_xor_sync(FULL, own_last1, d));
+
+        // ---------------- chain 2: output offset and previous structural ----------------
+        uint64_t base = 0;
+        uint32_t prev_last1 = 0;
+        if (slab == 0) {
+            if (lane == 0) {
+                st_relaxed_u64(p.desc_pos + slab, ((uint64_t)own_last1 << 2) | ST_INC);
+                st_relaxed_u64(p.desc_cnt + slab, ((uint64_t)slab_count << 2) | ST_INC);
+            }
+        } else {
+            if (lane == 0) {
+                st_relaxed_u64(p.desc_pos + slab, ((uint64_t)own_last1 << 2) | ST_AGG);
+                st_relaxed_u64(p.desc_cnt + slab, ((uint64_t)slab_count << 2) | ST_AGG);
+            }
+            lookback_count(p.desc_cnt, p.desc_pos, slab, base, prev_last1);
+            if (lane == 0) {
+                uint32_t inc_last1 = own_last1 ? own_last1 : prev_last1;
+                st_relaxed_u64(p.desc_pos + slab, ((uint64_t)inc_last1 << 2) | ST_INC);
+                st_relaxed_u64(p.desc_cnt + slab, ((base + slab_count) << 2) | ST_INC);
+            }
+        }
+
+        // ---------------- flatten ----------------
+        uint32_t prev_last = prev_last1 - 1;  // 0xffffffff when there is none (first delta = pos + 1)
+        uint32_t overflow = 0;
+        uint64_t off = base;
+#pragma unroll
+        for (int s = 0; s < S1_STEPS; s++) {
+            uint32_t blockpos = (uint32_t)(slab_start + (uint64_t)s * S1_STEP_BYTES + 64 * lane);
+            off += flatten_step<DELTAS>(S[s], blockpos, p.out, off, p.out_cap, prev_last, overflow);
+        }
+        if (overflow && lane == 0) atomicOr(&p.result->overflow, 1u);
+
+        if (slab == p.nslabs - 1 && lane == 0) {
+            p.result->n_idx = (uint32_t)(base + slab_count);
+            p.result->ends_in_string = par;
+            p.result->last_pos = (own_last1 ? own_last1 : prev_last1) - 1;
+        }
+        __syncwarp();  // every lane is done with buf before the next TMA may overwrite it
+        slab = next_slab;
+        b ^= 1;
+    }
+}
+
+}  // namespace sj

@@ -1,0 +1,95 @@
+"""ctypes binding of the C ABI declared in include/simdjson_b200.h.
+
+The shared library is built in-tree by __graft_entry__.build() (nvcc, sm_100a) as
+simdjson-go_b200/libsimdjson_b200.so.  There is no CPU fallback: loading fails loudly if
+the library is missing, and every call fails with SJ_ERR_NO_DEVICE without a B200.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libsimdjson_b200.so")
+
+FLAG_NDJSON = 1
+FLAG_COPY_STRINGS = 2
+OK, ERR_STAGE1, ERR_STAGE2, ERR_NO_DEVICE, ERR_CAPACITY, ERR_TOO_LARGE, ERR_ARGUMENT = range(7)
+
+# every symbol include/simdjson_b200.h declares
+EXPORTS = [
+    "sj_supported", "sj_device_count", "sj_error_string", "sj_ctx_create", "sj_ctx_destroy", "sj_host_alloc",
+    "sj_host_free", "sj_bounds", "sj_parse", "sj_parse_device", "sj_find_structural_indices", "sj_stage1_device",
+    "sj_stage1_launch", "sj_ctx_sync", "sj_event_record", "sj_event_elapsed_ms", "sj_kernel_launches",
+    "sj_test_block_masks", "sj_test_finalize", "sj_test_flatten_bits", "sj_test_parse_strings",
+    "sj_test_parse_numbers",
+]
+
+
+class Stage1Info(C.Structure):
+    _fields_ = [("n_idx", C.c_uint64), ("error", C.c_uint32), ("ends_in_string", C.c_uint32),
+                ("last_pos", C.c_uint32), ("overflow", C.c_uint32)]
+
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("simdjson_b200: %s is missing -- run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(nvcc, sm_100a); there is no CPU fallback" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, sz, u32, u64, i32 = C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint64, C.c_int
+    szp = C.POINTER(C.c_size_t)
+    L.sj_supported.restype = i32
+    L.sj_device_count.restype = i32
+    L.sj_error_string.restype = C.c_char_p
+    L.sj_error_string.argtypes = [i32]
+    L.sj_ctx_create.restype = i32
+    L.sj_ctx_create.argtypes = [i32, C.POINTER(vp)]
+    L.sj_ctx_destroy.restype = None
+    L.sj_ctx_destroy.argtypes = [vp]
+    L.sj_host_alloc.restype = vp
+    L.sj_host_alloc.argtypes = [sz]
+    L.sj_host_free.restype = None
+    L.sj_host_free.argtypes = [vp]
+    L.sj_bounds.restype = None
+    L.sj_bounds.argtypes = [sz, szp, szp]
+    L.sj_parse.restype = i32
+    L.sj_parse.argtypes = [vp, vp, sz, u32, vp, sz, szp, vp, sz, szp, szp, szp]
+    L.sj_parse_device.restype = i32
+    L.sj_parse_device.argtypes = [vp, vp, sz, u32, vp, sz, szp, vp, sz, szp]
+    L.sj_find_structural_indices.restype = i32
+    L.sj_find_structural_indices.argtypes = [vp, vp, sz, i32, vp, sz, szp]
+    L.sj_stage1_device.restype = i32
+    L.sj_stage1_device.argtypes = [vp, vp, sz, i32, i32, vp, sz, C.POINTER(Stage1Info)]
+    L.sj_stage1_launch.restype = i32
+    L.sj_stage1_launch.argtypes = [vp, vp, sz, i32, i32, vp, sz]
+    L.sj_ctx_sync.restype = i32
+    L.sj_ctx_sync.argtypes = [vp]
+    L.sj_event_record.restype = i32
+    L.sj_event_record.argtypes = [vp, i32]
+    L.sj_event_elapsed_ms.restype = i32
+    L.sj_event_elapsed_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.sj_kernel_launches.restype = i32
+    L.sj_kernel_launches.argtypes = [vp, C.POINTER(u64)]
+    L.sj_test_block_masks.restype = i32
+    L.sj_test_block_masks.argtypes = [vp, vp, sz, vp, vp]
+    L.sj_test_finalize.restype = i32
+    L.sj_test_finalize.argtypes = [vp, vp, sz, vp]
+    L.sj_test_flatten_bits.restype = i32
+    L.sj_test_flatten_bits.argtypes = [vp, vp, sz, vp, sz, szp]
+    L.sj_test_parse_strings.restype = i32
+    L.sj_test_parse_strings.argtypes = [vp, vp, vp, sz, vp, vp, vp, vp, vp]
+    L.sj_test_parse_numbers.restype = i32
+    L.sj_test_parse_numbers.argtypes = [vp, vp, vp, sz, vp, vp]
+    _lib = L
+    return L
+
+
+class SjError(RuntimeError):
+    def __init__(self, rc):
+        self.rc = rc
+        msg = load().sj_error_string(rc)
+        super().__init__("simdjson_b200: rc=%d (%s)" % (rc, msg.decode() if msg else "?"))

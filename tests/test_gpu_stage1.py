@@ -1,0 +1,195 @@
+"""GPU parity tests for stage 1 + flatten (kernel K1) through the C ABI.
+
+The CUDA path is compared with the CPU oracle bit for bit, and replays the same
+reference goldens (G1..G10) the oracle is pinned on.
+"""
+import numpy as np
+import pytest
+
+from tests.util import SMALL_FILES, TAPE_FILES, golden, load_fixture, unhex
+
+pytestmark = pytest.mark.gpu
+M64 = (1 << 64) - 1
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import simdjson_b200 as sj
+    assert sj.SupportedCPU(), "no sm_100 device (the CUDA path has no fallback)"
+    c = sj.Context(0)
+    yield c
+    c.close()
+
+
+# ---- reference goldens through the device code ---------------------------------------
+def test_g1_finalize_structurals(ctx):
+    for i, tc in enumerate(golden("G1_finalize_structurals")):
+        got = ctx.finalize_structurals(tc["structurals"], tc["whitespace"], tc["quote_mask"], tc["quote_bits"], 0)
+        assert got == (tc["expected_strls"], tc["expected_pseudo"]), i
+
+
+def test_g2_newline_delimiters(ctx):
+    g = golden("G2_newline_delimiters")
+    nd = unhex(g["input"])
+    for k, off in enumerate(range(0, len(nd) - 64, 64)):
+        assert ctx.find_newline_delimiters(nd[off:off + 64], 0) == g["want"][k]
+    q = bytearray(unhex(g["quoted_case"]["input"]))
+    for p in g["quoted_case"]["newline_at"]:
+        q[p] = 0x0A
+    qm, _, _, _ = ctx.find_quote_mask_and_bits(bytes(q), 0, 0)
+    assert ctx.find_newline_delimiters(bytes(q), qm) == g["quoted_case"]["want"]
+    # and fused: the ndjson structural mask contains exactly the unquoted newline
+    assert ctx._one(bytes(q), prev_pseudo=1, ndjson=1)[6] & (1 << 50)
+    assert not ctx._one(bytes(q), prev_pseudo=1, ndjson=1)[6] & (1 << 10)
+
+
+def test_g3_odd_backslash(ctx):
+    for i, tc in enumerate(golden("G3_odd_backslash")):
+        got = ctx.find_odd_backslash_sequences(unhex(tc["input"]), tc["prev_ends_odd"])
+        assert got == (tc["expected"], tc["ends_odd_backslash"]), i
+    for i in range(1, 129):
+        t = b" " * (i - 1) + b'\\"' + b" " * (62 + 64)
+        lo, c = ctx.find_odd_backslash_sequences(t[:64], 0)
+        hi, c = ctx.find_odd_backslash_sequences(t[64:128], c)
+        assert (lo, hi) == ((1 << i, 0) if i < 64 else (0, (1 << (i - 64)) & M64)), i
+
+
+def test_g4_quote_mask_and_bits(ctx):
+    g = golden("G4_quote_mask")
+    for i, tc in enumerate(g["cases"]):
+        # odd_ends in the table is 0 or 1: bit 0 set <=> the block before ended in an odd run
+        got = ctx.find_quote_mask_and_bits(unhex(tc["input"]), tc["odd_ends"], 0)
+        assert got == (tc["expected"], tc["quote_bits"], tc["piiq"], tc["error_mask"]), i
+    for i, tc in enumerate(g["piiq_cases"]):
+        assert ctx.find_quote_mask_and_bits(unhex(tc["input"]), 0, tc["piiq_in"])[2] == tc["piiq_out"], i
+
+
+def test_g5_whitespace_and_structurals(ctx):
+    for i, tc in enumerate(golden("G5_whitespace_structurals")):
+        assert ctx.find_whitespace_and_structurals(unhex(tc["input"])[:64]) == (tc["ws"], tc["structurals"]), i
+
+
+def test_g9_flatten_bits(ctx):
+    for i, tc in enumerate(golden("G9_flatten_bits")):
+        assert ctx.flatten_bits(tc["masks"])[0] == tc["expected"], i
+
+
+def test_g10_demo_json_positions(ctx):
+    g = golden("G10_stage1_marks")
+    ok, deltas = ctx.find_structural_indices(unhex(g["demo_json"]))
+    assert ok
+    assert (np.cumsum(deltas.astype(np.int64)) - 1).tolist() == g["positions"]
+
+
+def test_g7_tail_padding(ctx):
+    msg = unhex(golden("G7_tail_padding")["msg"])
+    for l in range(len(msg), 0, -1):
+        ok, deltas = ctx.find_structural_indices(msg[:l])
+        assert len(deltas) == l and int(deltas.astype(np.int64).sum()) - 1 == l - 1  # (':' last => not ok, by design)
+
+
+def test_g8_twitter_count(ctx):
+    g = golden("G8_twitter_loop")
+    msg = load_fixture("twitter")
+    ok, deltas = ctx.find_structural_indices(msg)
+    assert ok and len(deltas) == g["count"]
+    pos = len(msg) - 1
+    for j, ch in enumerate(g["reversed_tail"]):
+        assert msg[pos:pos + 1].decode() == ch
+        pos -= int(deltas[len(deltas) - 1 - j])
+
+
+# ---- differential tests against the oracle ---------------------------------------------
+ALPHABET = np.frombuffer(b'{}[]:,"\\\\\\ \t\n\r ab019.-etrufalsn\x00\x1f\x7f\x80\xc3\xa9/', dtype=np.uint8)
+
+
+def test_block_masks_random_vs_oracle(ctx, oracle):
+    rng = np.random.default_rng(1234)
+    n = 4096
+    blocks = ALPHABET[rng.integers(0, len(ALPHABET), size=(n, 64))]
+    blocks[:64] = ord("\\")  # all-backslash blocks
+    blocks[64:128, :32] = ord("\\")
+    carries = np.zeros((n, 4), dtype=np.uint64)
+    carries[:, 0] = rng.integers(0, 2, n)
+    carries[:, 1] = np.where(rng.integers(0, 2, n) == 1, np.uint64(M64), np.uint64(0))
+    carries[:, 2] = rng.integers(0, 2, n)
+    carries[:, 3] = rng.integers(0, 2, n)
+    got = ctx.block_masks(blocks, carries)
+    for i in range(n):
+        blk = blocks[i].tobytes()
+        po, pi, pp, nd = (int(x) for x in carries[i])
+        oe, oc = oracle.find_odd_backslash_sequences(blk, po)
+        qm, qb, pi2, em = oracle.find_quote_mask_and_bits(blk, oe, pi)
+        ws, st = oracle.find_whitespace_and_structurals(blk)
+        fin, pp2 = oracle.finalize_structurals(st, ws, qm, qb, pp)
+        nl = oracle.find_newline_delimiters(blk, 0)
+        if nd:
+            fin |= nl & ~qm & M64
+        want = [oe, qm, qb, em, ws, st, fin, nl, oc, pi2, pp2]
+        assert [int(x) for x in got[i][:11]] == want, i
+
+
+def _check(ctx, oracle, msg, ndjson):
+    ok_g, d_g = ctx.find_structural_indices(msg, ndjson)
+    ok_o, d_o = oracle.find_structural_indices(msg, ndjson)
+    assert ok_g == ok_o
+    assert len(d_g) == len(d_o)
+    assert np.array_equal(d_g, d_o)
+
+
+@pytest.mark.parametrize("name", TAPE_FILES + SMALL_FILES + ["parking-citations"])
+def test_fixture_deltas_vs_oracle(ctx, oracle_native, name):
+    msg = load_fixture(name).strip()
+    _check(ctx, oracle_native, msg, False)
+    _check(ctx, oracle_native, msg, True)
+
+
+def test_small_and_boundary_sizes(ctx, oracle_native):
+    tw = load_fixture("twitter")
+    for n in list(range(1, 70)) + [127, 128, 129, 2047, 2048, 2049, 8191, 8192, 8193, 16384, 16385, 98304, 98305, 200001]:
+        _check(ctx, oracle_native, tw[:n], False)
+    for doc in (b"{}", b"[]", b"[", b'"', b'"\\', b"\\", b" ", b"a", b'{"a":1}', b'["\\""]'):
+        _check(ctx, oracle_native, doc, False)
+
+
+def test_carries_across_slabs(ctx, oracle_native):
+    """strings, backslash runs and pseudo-structural predecessors straddling 8 KiB slab / 2 KiB step / 64 B block edges"""
+    rng = np.random.default_rng(7)
+    for edge in (64, 2048, 8192, 16384, 8192 * 13):
+        for run in (1, 2, 3, 31, 32, 33, 63, 64, 65, 127, 128, 129, 200):
+            for shift in (0, 1, 2):
+                pre = edge - run + shift
+                if pre < 2:
+                    continue
+                body = b'["' + b"x" * (pre - 2) + b"\\" * run + b'"q\\\\", "tail",true , 12]'
+                _check(ctx, oracle_native, body, False)
+    # a quote exactly at the last byte of a slab, escaped or not
+    for k in (0, 1, 2, 3):
+        pad = 8192 - 3 - k
+        _check(ctx, oracle_native, b'["' + b"y" * pad + b"\\" * k + b'","z"]', False)
+        _check(ctx, oracle_native, b'["' + b"y" * pad + b"\\" * k + b'"  ,  "z"  ]', False)
+    # random soup: every structural / escape class, sizes that leave partial slabs
+    for n in (5000, 8192, 20000, 70000, 300007):
+        buf = ALPHABET[rng.integers(0, len(ALPHABET), size=n)].tobytes()
+        _check(ctx, oracle_native, buf, False)
+        _check(ctx, oracle_native, buf, True)
+
+
+def test_large_replicated_input(ctx, oracle_native):
+    """many slabs in flight on every SM: 64 MiB of twitter-shaped data, bit-exact deltas"""
+    tw = load_fixture("twitter")
+    k = 100
+    msg = b"[" + b",".join([tw] * k) + b"]"
+    _check(ctx, oracle_native, np.frombuffer(msg, dtype=np.uint8), False)
+
+
+def test_ndjson_newlines(ctx, oracle_native):
+    pk = load_fixture("parking-citations").strip()
+    _check(ctx, oracle_native, b"\n".join([pk] * 40), True)
+    _check(ctx, oracle_native, b'{"a":"x\ny"}\n\n{"b":2}', True)  # raw newline inside a string => stage-1 error
+
+
+def test_control_char_error(ctx, oracle_native):
+    for c in (0, 1, 9, 10, 13, 31):
+        _check(ctx, oracle_native, b'{"a":"x' + bytes([c]) + b'y"}', False)
+        _check(ctx, oracle_native, b'{"a" ' + bytes([c]) + b' :"xy"}', False)
