@@ -204,20 +204,26 @@ static int launch_stage1(sj_ctx* c, const uint8_t* d_msg, size_t len, bool ndjso
     if (len == 0 || len > SJ_MAX_MESSAGE) return SJ_ERR_TOO_LARGE;
     if ((reinterpret_cast<uintptr_t>(d_msg) & 15) != 0) return SJ_ERR_ARGUMENT;
     int nslabs = (int)((len + S1_SLAB_BYTES - 1) / S1_SLAB_BYTES);
-    int rc = c->desc.reserve((size_t)nslabs * 3 * sizeof(uint64_t));
+    // descriptor block: [dinc u64 x n][lastp1 u32 x n][dagg u16 x n8][dpar u8 x n16], every part 16-byte aligned
+    const size_t n16 = ((size_t)nslabs + 15) & ~(size_t)15;
+    const size_t off_inc = 0, off_last = off_inc + n16 * 8, off_agg = off_last + n16 * 4, off_par = off_agg + n16 * 2;
+    const size_t desc_bytes = off_par + n16 + 16;
+    int rc = c->desc.reserve(desc_bytes);
     if (rc) return rc;
-    SJ_CUDA_CHECK(cudaMemsetAsync(c->desc.p, 0, (size_t)nslabs * 3 * sizeof(uint64_t), c->stream));
+    SJ_CUDA_CHECK(cudaMemsetAsync(c->desc.p, 0, desc_bytes, c->stream));
     SJ_CUDA_CHECK(cudaMemsetAsync(c->result.p, 0, sizeof(Stage1Result), c->stream));
     Stage1Params p;
     p.msg = d_msg;
     p.len = len;
     p.out = d_out;
     p.out_cap = cap;
-    p.desc_par = c->desc.as<uint64_t>();
-    p.desc_cnt = p.desc_par + nslabs;
-    p.desc_pos = p.desc_cnt + nslabs;
+    p.dinc = reinterpret_cast<uint64_t*>(c->desc.as<uint8_t>() + off_inc);
+    p.lastp1 = reinterpret_cast<uint32_t*>(c->desc.as<uint8_t>() + off_last);
+    p.dagg = reinterpret_cast<uint16_t*>(c->desc.as<uint8_t>() + off_agg);
+    p.dpar = c->desc.as<uint8_t>() + off_par;
     p.result = c->result.as<Stage1Result>();
     p.nslabs = nslabs;
+    p.prof = reinterpret_cast<unsigned long long*>(c->result.as<uint8_t>() + 128);
     int grid = (nslabs + S1_WARPS - 1) / S1_WARPS;
     if (grid > c->sm_count) grid = c->sm_count;
     if (ndjson) {
@@ -231,7 +237,12 @@ static int launch_stage1(sj_ctx* c, const uint8_t* d_msg, size_t len, bool ndjso
         else
             stage1_flatten_kernel<false, false><<<grid, S1_THREADS, S1_SMEM_BYTES, c->stream>>>(p);
     }
-    c->launches++;
+    const int fgrid = (nslabs + 255) / 256;
+    if (deltas)
+        stage1_finish_kernel<true><<<fgrid, 256, 0, c->stream>>>(p);
+    else
+        stage1_finish_kernel<false><<<fgrid, 256, 0, c->stream>>>(p);
+    c->launches += 2;
     SJ_CUDA_CHECK(cudaGetLastError());
     return SJ_OK;
 }
@@ -387,3 +398,14 @@ extern "C" int sj_test_flatten_bits(sj_ctx* c, const uint64_t* masks, size_t nma
 }
 
 #include "sj_parse.inl"
+
+#ifdef SJ_PROFILE_PHASES
+// development aid (not part of the C ABI): read / clear the per-phase cycle counters
+extern "C" int sj_debug_read_prof(sj_ctx* c, unsigned long long* out, int clear) {
+    unsigned long long* d = reinterpret_cast<unsigned long long*>(c->result.as<uint8_t>() + 128);
+    SJ_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    SJ_CUDA_CHECK(cudaMemcpy(out, d, 64, cudaMemcpyDeviceToHost));
+    if (clear) SJ_CUDA_CHECK(cudaMemset(d, 0, 64));
+    return SJ_OK;
+}
+#endif

@@ -1,5 +1,419 @@
-// placeholder until stage 2 lands
-extern "C" int sj_parse(sj_ctx*, const uint8_t*, size_t, uint32_t, uint64_t*, size_t, size_t*, uint8_t*, size_t, size_t*, size_t*, size_t*) { return SJ_ERR_ARGUMENT; }
-extern "C" int sj_parse_device(sj_ctx*, const uint8_t*, size_t, uint32_t, uint64_t*, size_t, size_t*, uint8_t*, size_t, size_t*) { return SJ_ERR_ARGUMENT; }
-extern "C" int sj_test_parse_strings(sj_ctx*, const uint8_t*, const uint64_t*, size_t, const uint64_t*, uint8_t*, uint64_t*, uint64_t*, uint8_t*) { return SJ_ERR_ARGUMENT; }
-extern "C" int sj_test_parse_numbers(sj_ctx*, const uint8_t*, const uint64_t*, size_t, uint64_t*, uint64_t*) { return SJ_ERR_ARGUMENT; }
+// sj_parse.inl -- parseMessage replacement: host trim + upload, K1, K2a..K2f, read-back.
+// Included by sj_api.cu.
+
+// ---------------------------------------------------------------------------------
+// bytes.TrimSpace (parse_json_amd64.go:55; Go semantics incl. the unicode.IsSpace fall-back
+// once a byte >= 0x80 is met -- SURVEY.md appendix C.1).  Host-side pointer work only.
+// ---------------------------------------------------------------------------------
+namespace {
+
+inline bool ascii_space(uint8_t c) { return c == '\t' || c == '\n' || c == '\v' || c == '\f' || c == '\r' || c == ' '; }
+
+inline bool unicode_space(uint32_t r) {
+    if (r < 0x80) return ascii_space((uint8_t)r);
+    if (r == 0x85 || r == 0xA0 || r == 0x1680 || r == 0x2028 || r == 0x2029 || r == 0x202F || r == 0x205F || r == 0x3000)
+        return true;
+    return r >= 0x2000 && r <= 0x200A;
+}
+
+// utf8.DecodeRune: width (>= 1 for n > 0); invalid encodings give U+FFFD, width 1
+inline int decode_rune(const uint8_t* p, size_t n, uint32_t* r) {
+    *r = 0xFFFD;
+    if (n == 0) return 0;
+    uint8_t c = p[0];
+    if (c < 0x80) {
+        *r = c;
+        return 1;
+    }
+    int need;
+    uint32_t cp, lo;
+    if (c >= 0xC2 && c <= 0xDF) {
+        need = 1, cp = c & 0x1F, lo = 0x80;
+    } else if (c >= 0xE0 && c <= 0xEF) {
+        need = 2, cp = c & 0x0F, lo = 0x800;
+    } else if (c >= 0xF0 && c <= 0xF4) {
+        need = 3, cp = c & 0x07, lo = 0x10000;
+    } else {
+        return 1;
+    }
+    if (n < (size_t)need + 1) return 1;
+    for (int i = 1; i <= need; i++) {
+        if ((p[i] & 0xC0) != 0x80) return 1;
+        cp = (cp << 6) | (p[i] & 0x3F);
+    }
+    if (cp < lo || cp > 0x10FFFF || (cp >= 0xD800 && cp <= 0xDFFF)) return 1;
+    *r = cp;
+    return need + 1;
+}
+
+void trim_runes(const uint8_t* b, size_t* start, size_t* stop) {
+    size_t a = *start, e = *stop;
+    while (a < e) {
+        uint32_t r;
+        int w = decode_rune(b + a, e - a, &r);
+        if (!unicode_space(r)) break;
+        a += (size_t)w;
+    }
+    while (e > a) {
+        uint32_t r = 0xFFFD;
+        size_t w = 1;
+        if (b[e - 1] < 0x80) {
+            r = b[e - 1];
+        } else {
+            size_t lim = e - a < 4 ? e - a : 4;
+            for (size_t back = 1; back <= lim; back++) {
+                if ((b[e - back] & 0xC0) != 0x80) {  // first non-continuation byte from the end
+                    uint32_t rr;
+                    int ww = decode_rune(b + e - back, back, &rr);
+                    if ((size_t)ww == back) {
+                        r = rr;
+                        w = back;
+                    }
+                    break;
+                }
+            }
+        }
+        if (!unicode_space(r)) break;
+        e -= w;
+    }
+    *start = a;
+    *stop = e;
+}
+
+void trim_space(const uint8_t* b, size_t len, size_t* start_out, size_t* stop_out) {
+    size_t start = 0, stop = len;
+    bool done = false;
+    for (; start < len; start++) {
+        if (b[start] >= 0x80) {
+            trim_runes(b, &start, &stop);
+            done = true;
+            break;
+        }
+        if (!ascii_space(b[start])) break;
+    }
+    if (!done) {
+        for (; stop > start; stop--) {
+            if (b[stop - 1] >= 0x80) {
+                trim_runes(b, &start, &stop);
+                break;
+            }
+            if (!ascii_space(b[stop - 1])) break;
+        }
+    }
+    *start_out = start;
+    *stop_out = stop;
+}
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct Carver {  // sub-allocates one DevBuf
+    uint8_t* base;
+    size_t off = 0;
+    explicit Carver(void* p) : base(reinterpret_cast<uint8_t*>(p)) {}
+    template <typename T>
+    T* take(size_t count) {
+        T* r = reinterpret_cast<T*>(base + off);
+        off += align_up(count * sizeof(T) + 16, 256);
+        return r;
+    }
+    static size_t need(std::initializer_list<size_t> bytes) {
+        size_t t = 0;
+        for (size_t b : bytes) t += align_up(b + 16, 256);
+        return t;
+    }
+};
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------
+// stage 2 driver.  d_tape / d_strings may be null: then the context's own output buffers
+// are sized from the totals (host-buffer API).
+// ---------------------------------------------------------------------------------
+static int run_stage2(sj_ctx* c, const uint8_t* d_msg, size_t len, const uint32_t* d_idx, uint32_t n, uint32_t flags,
+                      uint64_t* d_tape, size_t tape_cap, uint8_t* d_strings, size_t strings_cap, Stage2Result* out) {
+    const uint32_t ntiles = (n + S2_THREADS - 1) / S2_THREADS;
+    const uint32_t ngroups = (ntiles + 1023) / 1024;
+    // ---- phase 1 scratch ----
+    size_t need1 = Carver::need({(size_t)n, (size_t)n * 4, (size_t)n * 4, (size_t)ntiles * sizeof(ScanVal),
+                                 (size_t)ntiles * sizeof(ScanVal), (size_t)ngroups * sizeof(ScanVal),
+                                 (size_t)ngroups * sizeof(ScanVal)});
+    int rc = c->s2a.reserve(need1);
+    if (rc) return rc;
+    Carver k1(c->s2a.p);
+    Stage2Params p;
+    memset(&p, 0, sizeof p);
+    p.msg = d_msg;
+    p.len = len;
+    p.idx = d_idx;
+    p.n = n;
+    p.ndjson = (flags & SJ_FLAG_NDJSON) ? 1 : 0;
+    p.copy_strings = (flags & SJ_FLAG_COPY_STRINGS) ? 1 : 0;
+    p.typ = k1.take<uint8_t>(n);
+    p.aux = k1.take<uint32_t>(n);
+    p.kb = k1.take<uint32_t>(n);
+    p.tile_sum = k1.take<ScanVal>(ntiles);
+    p.tile_pre = k1.take<ScanVal>(ntiles);
+    p.grp_sum = k1.take<ScanVal>(ngroups);
+    p.grp_pre = k1.take<ScanVal>(ngroups);
+    p.ntiles = ntiles;
+    p.ngroups = ngroups;
+    Stage2Result* d_res = reinterpret_cast<Stage2Result*>(c->result.as<uint8_t>() + 64);
+    p.result = d_res;
+    SJ_CUDA_CHECK(cudaMemsetAsync(d_res, 0, sizeof(Stage2Result), c->stream));
+
+    s2_classify_measure_kernel<<<ntiles, S2_THREADS, 0, c->stream>>>(p);
+    s2_scan_groups_kernel<<<ngroups, 1024, 0, c->stream>>>(p.tile_sum, ntiles, p.tile_pre, p.grp_sum);
+    s2_scan_top_kernel<<<1, 1024, 0, c->stream>>>(p.grp_sum, ngroups, p.grp_pre, d_res);
+    c->launches += 3;
+    SJ_CUDA_CHECK(cudaGetLastError());
+    Stage2Result* h_res = reinterpret_cast<Stage2Result*>(reinterpret_cast<uint8_t*>(c->host_result) + 64);
+    SJ_CUDA_CHECK(cudaMemcpyAsync(h_res, d_res, sizeof(Stage2Result), cudaMemcpyDeviceToHost, c->stream));
+    SJ_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    Stage2Result tot = *h_res;
+    *out = tot;
+
+    // ---- outputs ----
+    if (!d_tape) {
+        rc = c->tape.reserve(tot.tape_len * 8 + 64);
+        if (rc) return rc;
+        rc = c->strings.reserve(tot.strings_len + 64);
+        if (rc) return rc;
+        d_tape = c->tape.as<uint64_t>();
+        tape_cap = tot.tape_len;
+        d_strings = c->strings.as<uint8_t>();
+        strings_cap = tot.strings_len;
+    } else if (tot.tape_len > tape_cap || tot.strings_len > strings_cap) {
+        return SJ_ERR_CAPACITY;
+    }
+    p.tape = d_tape;
+    p.tape_cap = tape_cap;
+    p.strings = d_strings;
+    p.strings_cap = strings_cap;
+
+    // ---- phase 2 scratch ----
+    const size_t nb = (size_t)tot.n_brackets;
+    size_t lvl_total = 0;
+    {
+        size_t sz = nb;
+        while (sz > 32) {
+            sz = (sz + 31) / 32;
+            lvl_total += sz;
+        }
+    }
+    size_t need2 = Carver::need({nb * 4, nb * 4, nb * 4, nb * 4, (lvl_total + 8) * 4, ((size_t)tot.n_records + 2) * 4});
+    rc = c->s2b.reserve(need2);
+    if (rc) return rc;
+    Carver k2(c->s2b.p);
+    p.brk_i = k2.take<uint32_t>(nb);
+    p.brk_tp = k2.take<uint32_t>(nb);
+    p.brk_depth = k2.take<int32_t>(nb);
+    p.par = k2.take<int32_t>(nb);
+    int32_t* lvl_mem = k2.take<int32_t>(lvl_total + 8);
+    p.rootpos = k2.take<uint32_t>((size_t)tot.n_records + 2);
+
+    s2_emit_kernel<<<ntiles, S2_THREADS, 0, c->stream>>>(p);
+    c->launches++;
+    if (nb > 0) {
+        AnsvLevels L;
+        memset(&L, 0, sizeof L);
+        L.lv[0] = p.brk_depth;
+        L.n[0] = (uint32_t)nb;
+        L.nlevels = 1;
+        size_t sz = nb;
+        int32_t* next = lvl_mem;
+        while (sz > 32 && L.nlevels < ANSV_MAX_LEVELS) {
+            size_t nsz = (sz + 31) / 32;
+            const unsigned threads = 256;
+            const unsigned blocks = (unsigned)((nsz * 32 + threads - 1) / threads);
+            s2_min32_kernel<<<blocks, threads, 0, c->stream>>>(L.lv[L.nlevels - 1], (uint32_t)sz, next, (uint32_t)nsz);
+            c->launches++;
+            L.lv[L.nlevels] = next;
+            L.n[L.nlevels] = (uint32_t)nsz;
+            L.nlevels++;
+            next += nsz;
+            sz = nsz;
+        }
+        s2_ansv_kernel<<<(unsigned)((nb + S2_THREADS - 1) / S2_THREADS), S2_THREADS, 0, c->stream>>>(L, p.par);
+        c->launches++;
+    }
+    s2_grammar_kernel<<<ntiles, S2_THREADS, 0, c->stream>>>(p);
+    {
+        const uint64_t nrec = tot.n_records;
+        const unsigned blocks = (unsigned)((nrec + 1 + 255) / 256);
+        s2_roots_kernel<<<blocks, 256, 0, c->stream>>>(p, nrec, tot.tape_len);
+    }
+    c->launches += 2;
+    SJ_CUDA_CHECK(cudaGetLastError());
+    SJ_CUDA_CHECK(cudaMemcpyAsync(h_res, d_res, sizeof(Stage2Result), cudaMemcpyDeviceToHost, c->stream));
+    SJ_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    *out = *h_res;
+    return SJ_OK;
+}
+
+static int stage2_verdict(const Stage2Result& r) {
+    if (r.overflow) return SJ_ERR_CAPACITY;
+    if (r.error || r.final_depth != 0) return SJ_ERR_STAGE2;  // stage2...go:428-436: leftover scope
+    return SJ_OK;
+}
+
+// stage 1 into the context's index buffer (absolute positions), growing it once if needed
+static int stage1_positions(sj_ctx* c, const uint8_t* d_msg, size_t len, bool ndjson, Stage1Result* r) {
+    size_t dcap = len / 4 + 1024;
+    if (c->idx.cap / sizeof(uint32_t) > dcap) dcap = c->idx.cap / sizeof(uint32_t);
+    for (int attempt = 0; attempt < 2; attempt++) {
+        int rc = c->idx.reserve(dcap * sizeof(uint32_t));
+        if (rc) return rc;
+        rc = launch_stage1(c, d_msg, len, ndjson, false, c->idx.as<uint32_t>(), dcap);
+        if (rc) return rc;
+        rc = fetch_stage1_result(c, r);
+        if (rc) return rc;
+        if (!r->overflow) return SJ_OK;
+        dcap = (size_t)r->n_idx + 64;
+    }
+    return SJ_ERR_CAPACITY;
+}
+
+extern "C" int sj_parse_device(sj_ctx* c, const uint8_t* d_msg, size_t len, uint32_t flags, uint64_t* d_tape,
+                               size_t tape_cap, size_t* tape_len, uint8_t* d_strings, size_t strings_cap,
+                               size_t* strings_len) {
+    if (!c || !tape_len || !strings_len || !d_tape || !d_strings) return SJ_ERR_ARGUMENT;
+    *tape_len = 0;
+    *strings_len = 0;
+    if (len == 0) return SJ_ERR_STAGE1;
+    if (len > SJ_MAX_MESSAGE) return SJ_ERR_TOO_LARGE;
+    SJ_CUDA_CHECK(cudaSetDevice(c->device));
+    Stage1Result r1;
+    int rc = stage1_positions(c, d_msg, len, (flags & SJ_FLAG_NDJSON) != 0, &r1);
+    if (rc) return rc;
+    uint8_t last_char = 0;
+    if (r1.n_idx && r1.last_pos < len) {
+        SJ_CUDA_CHECK(cudaMemcpyAsync(c->host_result, d_msg + r1.last_pos, 1, cudaMemcpyDeviceToHost, c->stream));
+        SJ_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        last_char = *reinterpret_cast<uint8_t*>(c->host_result);
+    }
+    if (!stage1_ok(r1, last_char)) return SJ_ERR_STAGE1;
+    Stage2Result r2;
+    rc = run_stage2(c, d_msg, len, c->idx.as<uint32_t>(), r1.n_idx, flags, d_tape, tape_cap, d_strings, strings_cap, &r2);
+    *tape_len = r2.tape_len;
+    *strings_len = r2.strings_len;
+    if (rc) return rc;
+    return stage2_verdict(r2);
+}
+
+extern "C" int sj_parse(sj_ctx* c, const uint8_t* msg, size_t len, uint32_t flags, uint64_t* tape, size_t tape_cap,
+                        size_t* tape_len, uint8_t* strings, size_t strings_cap, size_t* strings_len, size_t* msg_off,
+                        size_t* msg_len) {
+    if (!c || !tape_len || !strings_len) return SJ_ERR_ARGUMENT;
+    *tape_len = 0;
+    *strings_len = 0;
+    size_t a = 0, b = 0;
+    if (len) trim_space(msg, len, &a, &b);
+    if (msg_off) *msg_off = a;
+    if (msg_len) *msg_len = b - a;
+    const size_t n = b - a;
+    if (n == 0) return SJ_ERR_STAGE1;  // nothing to index: findStructuralIndices reports failure
+    if (n > SJ_MAX_MESSAGE) return SJ_ERR_TOO_LARGE;
+    SJ_CUDA_CHECK(cudaSetDevice(c->device));
+    int rc = upload_message(c, msg + a, n);
+    if (rc) return rc;
+    Stage1Result r1;
+    rc = stage1_positions(c, c->msg.as<uint8_t>(), n, (flags & SJ_FLAG_NDJSON) != 0, &r1);
+    if (rc) return rc;
+    uint8_t last_char = r1.n_idx && r1.last_pos < n ? msg[a + r1.last_pos] : 0;
+    if (!stage1_ok(r1, last_char)) return SJ_ERR_STAGE1;
+    Stage2Result r2;
+    rc = run_stage2(c, c->msg.as<uint8_t>(), n, c->idx.as<uint32_t>(), r1.n_idx, flags, nullptr, 0, nullptr, 0, &r2);
+    *tape_len = r2.tape_len;
+    *strings_len = r2.strings_len;
+    if (rc) return rc;
+    rc = stage2_verdict(r2);
+    if (rc) return rc;
+    if (r2.tape_len > tape_cap || r2.strings_len > strings_cap) return SJ_ERR_CAPACITY;
+    SJ_CUDA_CHECK(cudaMemcpyAsync(tape, c->tape.p, r2.tape_len * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (r2.strings_len)
+        SJ_CUDA_CHECK(cudaMemcpyAsync(strings, c->strings.p, r2.strings_len, cudaMemcpyDeviceToHost, c->stream));
+    SJ_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return SJ_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// unit-test hooks for the stage-2 leaf routines
+// ---------------------------------------------------------------------------------
+__global__ void test_strings_kernel(const uint8_t* buf, const uint64_t* offs, size_t n, const uint64_t* max_size,
+                                    uint8_t* ok, uint64_t* src_len, uint64_t* dst_len, uint8_t* dst) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t o = offs[i], e = offs[i + 1];
+    StrCursor s{buf + o + 1, e > o ? e - o - 1 : 0};
+    uint64_t sl = 0, dl = 0;
+    bool good = e > o && string_measure(s, max_size[i], &sl, &dl);
+    ok[i] = good;
+    src_len[i] = sl;
+    dst_len[i] = dl;
+    if (good) string_copy(s, dst + o);
+}
+
+__global__ void test_numbers_kernel(const uint8_t* buf, const uint64_t* offs, size_t n, uint64_t* tag, uint64_t* val) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t v = 0;
+    tag[i] = parse_number(buf + offs[i], offs[i + 1] - offs[i], &v);
+    val[i] = v;
+}
+
+extern "C" int sj_test_parse_strings(sj_ctx* c, const uint8_t* buf, const uint64_t* offs, size_t n,
+                                     const uint64_t* max_size, uint8_t* ok, uint64_t* src_len, uint64_t* dst_len,
+                                     uint8_t* dst) {
+    if (!c || n == 0) return SJ_ERR_ARGUMENT;
+    SJ_CUDA_CHECK(cudaSetDevice(c->device));
+    const size_t total = offs[n];
+    size_t need = Carver::need({total + 64, (n + 1) * 8, n * 8, n, n * 8, n * 8, total + 64});
+    int rc = c->test_in.reserve(need);
+    if (rc) return rc;
+    Carver k(c->test_in.p);
+    uint8_t* d_buf = k.take<uint8_t>(total + 64);
+    uint64_t* d_offs = k.take<uint64_t>(n + 1);
+    uint64_t* d_max = k.take<uint64_t>(n);
+    uint8_t* d_ok = k.take<uint8_t>(n);
+    uint64_t* d_sl = k.take<uint64_t>(n);
+    uint64_t* d_dl = k.take<uint64_t>(n);
+    uint8_t* d_dst = k.take<uint8_t>(total + 64);
+    SJ_CUDA_CHECK(cudaMemsetAsync(d_buf, 0, total + 64, c->stream));
+    SJ_CUDA_CHECK(cudaMemcpyAsync(d_buf, buf, total, cudaMemcpyHostToDevice, c->stream));
+    SJ_CUDA_CHECK(cudaMemcpyAsync(d_offs, offs, (n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    SJ_CUDA_CHECK(cudaMemcpyAsync(d_max, max_size, n * 8, cudaMemcpyHostToDevice, c->stream));
+    SJ_CUDA_CHECK(cudaMemsetAsync(d_dst, 0, total + 64, c->stream));
+    test_strings_kernel<<<(unsigned)((n + 63) / 64), 64, 0, c->stream>>>(d_buf, d_offs, n, d_max, d_ok, d_sl, d_dl, d_dst);
+    c->launches++;
+    SJ_CUDA_CHECK(cudaGetLastError());
+    SJ_CUDA_CHECK(cudaMemcpyAsync(ok, d_ok, n, cudaMemcpyDeviceToHost, c->stream));
+    SJ_CUDA_CHECK(cudaMemcpyAsync(src_len, d_sl, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    SJ_CUDA_CHECK(cudaMemcpyAsync(dst_len, d_dl, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    SJ_CUDA_CHECK(cudaMemcpyAsync(dst, d_dst, total, cudaMemcpyDeviceToHost, c->stream));
+    SJ_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return SJ_OK;
+}
+
+extern "C" int sj_test_parse_numbers(sj_ctx* c, const uint8_t* buf, const uint64_t* offs, size_t n, uint64_t* tag,
+                                     uint64_t* val) {
+    if (!c || n == 0) return SJ_ERR_ARGUMENT;
+    SJ_CUDA_CHECK(cudaSetDevice(c->device));
+    const size_t total = offs[n];
+    size_t need = Carver::need({total + 64, (n + 1) * 8, n * 8, n * 8});
+    int rc = c->test_in.reserve(need);
+    if (rc) return rc;
+    Carver k(c->test_in.p);
+    uint8_t* d_buf = k.take<uint8_t>(total + 64);
+    uint64_t* d_offs = k.take<uint64_t>(n + 1);
+    uint64_t* d_tag = k.take<uint64_t>(n);
+    uint64_t* d_val = k.take<uint64_t>(n);
+    SJ_CUDA_CHECK(cudaMemcpyAsync(d_buf, buf, total, cudaMemcpyHostToDevice, c->stream));
+    SJ_CUDA_CHECK(cudaMemcpyAsync(d_offs, offs, (n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    test_numbers_kernel<<<(unsigned)((n + 63) / 64), 64, 0, c->stream>>>(d_buf, d_offs, n, d_tag, d_val);
+    c->launches++;
+    SJ_CUDA_CHECK(cudaGetLastError());
+    SJ_CUDA_CHECK(cudaMemcpyAsync(tag, d_tag, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    SJ_CUDA_CHECK(cudaMemcpyAsync(val, d_val, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    SJ_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return SJ_OK;
+}

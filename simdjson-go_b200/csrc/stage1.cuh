@@ -24,7 +24,10 @@
 
 namespace sj {
 
-constexpr int S1_WARPS = 12;
+#ifndef SJ_S1_WARPS
+#define SJ_S1_WARPS 12
+#endif
+constexpr int S1_WARPS = SJ_S1_WARPS;
 constexpr int S1_THREADS = S1_WARPS * 32;
 constexpr int S1_STEPS = 4;
 constexpr int S1_STEP_BYTES = 32 * 64;
@@ -277,69 +280,122 @@ __device__ __forceinline__ uint32_t flatten_step(uint64_t S, uint32_t blockpos, 
 }
 
 // ---------------------------------------------------------------------------------
-// look-back chains.  Descriptor word = value << 2 | status (0 empty, 1 aggregate of the
-// slab alone, 2 inclusive prefix).  One warp inspects 32 predecessors per round.
+// look-back chains.  A look-back can only advance one window of predecessors per L2
+// round trip, so the windows are made wide with narrow descriptors:
+//   chain 1 (in-string parity): one BYTE per slab  {bit0 valid, bit1 inclusive, bit2 parity};
+//           a lane reads 16 descriptors with one 16-byte load -> 512 slabs (4 MiB) per round
+//   chain 2 (structural count): one uint16 aggregate per slab {bit15 valid, count <= 8192}
+//           -> 8 per lane, 256 slabs (2 MiB) per round -- plus one uint64 inclusive prefix
+//           per slab {bit63 valid}; a lane checks the prefix just in front of its group.
 // ---------------------------------------------------------------------------------
-constexpr uint64_t ST_AGG = 1, ST_INC = 2;
+constexpr uint32_t DP_VALID = 1, DP_INCL = 2, DP_PAR = 4;
+constexpr uint32_t DA_VALID = 0x8000u;
+constexpr uint64_t DI_VALID = 1ull << 63;
 
-__device__ __forceinline__ uint32_t lookback_parity(const uint64_t* desc, int slab) {
+__device__ __forceinline__ uint4 ld_relaxed_v4(const void* p) {
+    uint4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p)
+                 : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u8(uint8_t* p, uint32_t v) {
+    asm volatile("st.relaxed.gpu.global.u8 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_u16(uint16_t* p, uint32_t v) {
+    asm volatile("st.relaxed.gpu.global.u16 [%0], %1;" ::"l"(p), "h"((unsigned short)v) : "memory");
+}
+
+// bit k of each of the 16 bytes of q -> 16-bit mask (byte i -> bit i)
+__device__ __forceinline__ uint32_t gather_bit16(const uint4& q, int k) {
+    const uint32_t M = 0x10204080u;  // flags at bits 0,8,16,24 -> bits 28..31
+    uint32_t a = (((q.x >> k) & 0x01010101u) * M) >> 28;
+    uint32_t b = (((q.y >> k) & 0x01010101u) * M) >> 28;
+    uint32_t c = (((q.z >> k) & 0x01010101u) * M) >> 28;
+    uint32_t d = (((q.w >> k) & 0x01010101u) * M) >> 28;
+    return a | (b << 4) | (c << 8) | (d << 12);
+}
+
+// exclusive in-string parity at the entry of `slab` (slab > 0)
+__device__ __forceinline__ uint32_t lookback_parity(const uint8_t* dpar, int slab) {
     const int lane = threadIdx.x & 31;
     uint32_t par = 0;
-    for (int j = slab - 1;; j -= 32) {
-        int idx = j - lane;
-        uint64_t d;
+    for (int g = slab >> 4;; g -= 32) {  // lane L inspects the 16-slab group g - L
+        const int grp = g - lane;
+        uint32_t V, I, P;
         do {
-            d = idx >= 0 ? ld_relaxed_u64(desc + idx) : ST_INC;
-        } while (__any_sync(FULL, (d & 3) == 0));
-        uint32_t incl = __ballot_sync(FULL, (d & 3) == ST_INC);
-        uint32_t bits = __ballot_sync(FULL, (d >> 2) & 1);
-        if (incl) {
-            int f = __ffs(incl) - 1;
-            uint32_t m = f == 31 ? FULL : ((2u << f) - 1);
-            return par ^ (__popc(bits & m) & 1);
-        }
-        par ^= __popc(bits) & 1;
+            if (grp >= 0) {
+                uint4 q = ld_relaxed_v4(dpar + (size_t)grp * 16);
+                V = gather_bit16(q, 0);
+                I = gather_bit16(q, 1);
+                P = gather_bit16(q, 2);
+                if (grp == (slab >> 4)) {  // own group: only slabs in front of `slab` count
+                    uint32_t keep = (1u << (slab & 15)) - 1;
+                    V |= ~keep & 0xffffu;
+                    I &= keep;
+                    P &= keep;
+                }
+            } else {  // before the message: an inclusive prefix of parity 0
+                V = 0xffffu;
+                I = 0x8000u;
+                P = 0;
+            }
+        } while (__any_sync(FULL, V != 0xffffu));
+        uint32_t has = __ballot_sync(FULL, I != 0);
+        int f = has ? __ffs(has) - 1 : 32;
+        uint32_t contrib = 0;
+        if (lane < f)
+            contrib = __popc(P) & 1;
+        else if (lane == f)
+            contrib = __popc(P >> (31 - __clz(I))) & 1;  // the inclusive slab and every slab after it
+        par ^= __popc(__ballot_sync(FULL, contrib)) & 1;
+        if (has) return par;
     }
 }
 
-// count chain (desc_c) and last-structural-position chain (desc_p, value = pos + 1, 0 = none).
-// The two words of a slab are separate relaxed stores, so each chain trusts only the
-// status bits of its own word.
-__device__ __forceinline__ void lookback_count(const uint64_t* desc_c, const uint64_t* desc_p, int slab,
-                                               uint64_t& count, uint32_t& last_plus1) {
+// number of structurals in all slabs in front of `slab` (slab > 0)
+__device__ __forceinline__ uint64_t lookback_count(const uint16_t* dagg, const uint64_t* dinc, int slab) {
     const int lane = threadIdx.x & 31;
     uint64_t total = 0;
-    uint32_t last = 0;
-    bool cdone = false, pdone = false;
-    for (int j = slab - 1; !(cdone && pdone); j -= 32) {
-        int idx = j - lane;
-        uint64_t c, p;
+    for (int g = slab >> 3;; g -= 32) {  // lane L inspects the 8-slab group g - L
+        const int grp = g - lane;
+        uint32_t sum = 0, valid = 1;
+        uint64_t inc = 0;
         do {
-            c = idx >= 0 ? ld_relaxed_u64(desc_c + idx) : ST_INC;
-            p = idx >= 0 ? ld_relaxed_u64(desc_p + idx) : ST_INC;
-        } while (__any_sync(FULL, (c & 3) == 0 || (p & 3) == 0));
-        if (!cdone) {
-            uint32_t incl = __ballot_sync(FULL, (c & 3) == ST_INC);
-            int f = incl ? __ffs(incl) - 1 : 31;
-            uint64_t v = lane <= f ? (c >> 2) : 0;
+            if (grp >= 0) {
+                uint4 q = ld_relaxed_v4(dagg + (size_t)grp * 8);
+                inc = grp > 0 ? ld_relaxed_u64(dinc + (size_t)grp * 8 - 1) : DI_VALID;
+                uint32_t w[4] = {q.x, q.y, q.z, q.w};
+                if (grp == (slab >> 3)) {  // own group: drop slabs >= slab (pretend valid, count 0)
+                    const int keep = slab & 7;
 #pragma unroll
-            for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
-            total += v;
-            cdone = incl != 0;
-        }
-        if (!pdone) {
-            uint32_t incl = __ballot_sync(FULL, (p & 3) == ST_INC);
-            int f = incl ? __ffs(incl) - 1 : 31;
-            uint32_t m = f == 31 ? FULL : ((2u << f) - 1);
-            uint32_t pv = (uint32_t)(p >> 2);
-            uint32_t nz = __ballot_sync(FULL, pv != 0) & m;
-            uint32_t cand = __shfl_sync(FULL, pv, nz ? __ffs(nz) - 1 : 0);
-            if (nz) last = cand;
-            pdone = nz != 0 || incl != 0;
+                    for (int i = 0; i < 4; i++) {
+                        if (2 * i >= keep) w[i] = 0x80008000u;
+                        else if (2 * i + 1 >= keep) w[i] = (w[i] & 0xffffu) | 0x80000000u;
+                    }
+                }
+                valid = (w[0] & w[1] & w[2] & w[3] & 0x80008000u) == 0x80008000u;
+                sum = 0;
+#pragma unroll
+                for (int i = 0; i < 4; i++) sum += (w[i] & 0x3fffu) + ((w[i] >> 16) & 0x3fffu);
+            } else {
+                valid = 1;
+                sum = 0;
+                inc = DI_VALID;  // before the message: prefix 0
+            }
+        } while (__any_sync(FULL, !valid));
+        uint32_t has = __ballot_sync(FULL, (inc & DI_VALID) != 0);
+        int f = has ? __ffs(has) - 1 : 31;
+        uint32_t v = lane <= f ? sum : 0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+        total += v;
+        if (has) {
+            uint64_t pre = __shfl_sync(FULL, inc, f) & ~DI_VALID;
+            return total + pre;
         }
     }
-    count = total;
-    last_plus1 = last;
 }
 
 // ---------------------------------------------------------------------------------
@@ -359,16 +415,36 @@ __device__ __forceinline__ uint32_t backslash_run_before(const uint8_t* __restri
     }
 }
 
+#ifdef SJ_PROFILE_PHASES
+// development aid: per-phase cycle totals (lane 0 of every warp), summed into prof[0..7]
+#define SJ_PROF_DECL unsigned long long prof_t0 = clock64(), prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define SJ_PROF_MARK(k)                                  \
+    {                                                    \
+        unsigned long long t_ = clock64();               \
+        prof_acc[k] += t_ - prof_t0;                     \
+        prof_t0 = t_;                                    \
+    }
+#define SJ_PROF_FLUSH                                                                   \
+    if (lane == 0)                                                                      \
+        for (int k_ = 0; k_ < 8; k_++) atomicAdd(p.prof + k_, prof_acc[k_]);
+#else
+#define SJ_PROF_DECL
+#define SJ_PROF_MARK(k)
+#define SJ_PROF_FLUSH
+#endif
+
 struct Stage1Params {
     const uint8_t* msg;  // 16-byte aligned, readable up to round_up(len, 16)
     uint64_t len;
     uint32_t* out;       // positions (or deltas)
     uint64_t out_cap;
-    uint64_t* desc_par;  // [nslabs] zeroed
-    uint64_t* desc_cnt;  // [nslabs] zeroed
-    uint64_t* desc_pos;  // [nslabs] zeroed
+    uint8_t* dpar;       // [nslabs rounded up to 16] zeroed: chain-1 descriptors
+    uint16_t* dagg;      // [nslabs rounded up to 8] zeroed: chain-2 aggregates
+    uint64_t* dinc;      // [nslabs] zeroed: chain-2 inclusive prefixes
+    uint32_t* lastp1;    // [nslabs] position + 1 of the slab's last structural (0 = none)
     Stage1Result* result;
     int nslabs;
+    unsigned long long* prof;  // [8] cycle totals when built with -DSJ_PROFILE_PHASES
 };
 
 __device__ __forceinline__ void load_block_words(const uint8_t* buf, uint32_t lane, uint32_t (&w)[16]) {
@@ -436,14 +512,21 @@ __global__ void __launch_bounds__(S1_THREADS, 1) stage1_flatten_kernel(const Sta
         return __shfl_sync(FULL, t, 0);
     };
 
+    SJ_PROF_DECL
     int slab = ticket();
     uint32_t phasebits = 0;
     int b = 0;
     issue(slab, 0);
 
     while (slab < p.nslabs) {
+        SJ_PROF_MARK(7)
+#ifdef SJ_NO_PREFETCH_TICKET
+        const int next_slab = 0x7fffffff;
+#else
         const int next_slab = ticket();
-        issue(next_slab, b ^ 1);  // next slab streams in while this one is processed
+        issue(next_slab, b ^ 1);
+#endif
+        SJ_PROF_MARK(0)  // next slab streams in while this one is processed
         const uint64_t slab_start = (uint64_t)slab * S1_SLAB_BYTES;
         const uint8_t* buf = wbuf + (size_t)b * S1_SLAB_BYTES;
 
@@ -455,7 +538,9 @@ __global__ void __launch_bounds__(S1_THREADS, 1) stage1_flatten_kernel(const Sta
             if (prevc == '"') prevc_esc = backslash_run_before(p.msg, slab_start - 1) & 1;  // warp-uniform
         }
 
+        SJ_PROF_MARK(1)
         mbar_wait(&bars[b], (phasebits >> b) & 1);
+        SJ_PROF_MARK(2)
         phasebits ^= 1u << b;
 
         // ---------------- phase A: classify, escape analysis, slab quote parity ----------------
@@ -496,11 +581,13 @@ __global__ void __launch_bounds__(S1_THREADS, 1) stage1_flatten_kernel(const Sta
         // ---------------- chain 1: in-string parity at slab entry ----------------
         uint32_t par_in = 0;
         if (slab == 0) {
-            if (lane == 0) st_relaxed_u64(p.desc_par + slab, ((uint64_t)slab_par << 2) | ST_INC);
+            if (lane == 0) st_relaxed_u8(p.dpar + slab, DP_VALID | DP_INCL | (slab_par ? DP_PAR : 0));
         } else {
-            if (lane == 0) st_relaxed_u64(p.desc_par + slab, ((uint64_t)slab_par << 2) | ST_AGG);
-            par_in = lookback_parity(p.desc_par, slab);
-            if (lane == 0) st_relaxed_u64(p.desc_par + slab, ((uint64_t)(slab_par ^ par_in) << 2) | ST_INC);
+            if (lane == 0) st_relaxed_u8(p.dpar + slab, DP_VALID | (slab_par ? DP_PAR : 0));
+            SJ_PROF_MARK(3)
+            par_in = lookback_parity(p.dpar, slab);
+            SJ_PROF_MARK(4)
+            if (lane == 0) st_relaxed_u8(p.dpar + slab, DP_VALID | DP_INCL | ((slab_par ^ par_in) ? DP_PAR : 0));
         }
 
         // pseudo-structural predecessor carry into the slab (finalize_structurals_amd64.s:24-27;
@@ -566,29 +653,21 @@ __global__ void __launch_bounds__(S1_THREADS, 1) stage1_flatten_kernel(const Sta
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) own_last1 = max(own_last1, __shfl_xor_sync(FULL, own_last1, d));
 
-        // ---------------- chain 2: output offset and previous structural ----------------
+        // ---------------- chain 2: output offset ----------------
         uint64_t base = 0;
-        uint32_t prev_last1 = 0;
-        if (slab == 0) {
-            if (lane == 0) {
-                st_relaxed_u64(p.desc_pos + slab, ((uint64_t)own_last1 << 2) | ST_INC);
-                st_relaxed_u64(p.desc_cnt + slab, ((uint64_t)slab_count << 2) | ST_INC);
-            }
-        } else {
-            if (lane == 0) {
-                st_relaxed_u64(p.desc_pos + slab, ((uint64_t)own_last1 << 2) | ST_AGG);
-                st_relaxed_u64(p.desc_cnt + slab, ((uint64_t)slab_count << 2) | ST_AGG);
-            }
-            lookback_count(p.desc_cnt, p.desc_pos, slab, base, prev_last1);
-            if (lane == 0) {
-                uint32_t inc_last1 = own_last1 ? own_last1 : prev_last1;
-                st_relaxed_u64(p.desc_pos + slab, ((uint64_t)inc_last1 << 2) | ST_INC);
-                st_relaxed_u64(p.desc_cnt + slab, ((base + slab_count) << 2) | ST_INC);
-            }
+        if (lane == 0) {
+            p.lastp1[slab] = own_last1;
+            st_relaxed_u16(p.dagg + slab, DA_VALID | slab_count);
         }
+        SJ_PROF_MARK(5)
+        if (slab > 0) base = lookback_count(p.dagg, p.dinc, slab);
+        SJ_PROF_MARK(6)
+        if (lane == 0) st_relaxed_u64(p.dinc + slab, DI_VALID | (base + slab_count));
 
         // ---------------- flatten ----------------
-        uint32_t prev_last = prev_last1 - 1;  // 0xffffffff when there is none (first delta = pos + 1)
+        // deltas: the first structural of a slab is written as pos + 1 here and rebased on the
+        // previous slab's last structural by stage1_finish_kernel
+        uint32_t prev_last = 0xffffffffu;
         uint32_t overflow = 0;
         uint64_t off = base;
 #pragma unroll
@@ -601,12 +680,40 @@ __global__ void __launch_bounds__(S1_THREADS, 1) stage1_flatten_kernel(const Sta
         if (slab == p.nslabs - 1 && lane == 0) {
             p.result->n_idx = (uint32_t)(base + slab_count);
             p.result->ends_in_string = par;
-            p.result->last_pos = (own_last1 ? own_last1 : prev_last1) - 1;
         }
         __syncwarp();  // every lane is done with buf before the next TMA may overwrite it
+#ifdef SJ_NO_PREFETCH_TICKET
+        slab = ticket();
+        issue(slab, b ^ 1);
+#else
         slab = next_slab;
+#endif
         b ^= 1;
     }
+    SJ_PROF_FLUSH
+}
+
+// After K1: rebase the first delta of every slab on the last structural of the slabs in
+// front of it (delta mode), and record the position of the last structural of the message.
+template <bool DELTAS>
+__global__ void stage1_finish_kernel(const Stage1Params p) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= p.nslabs) return;
+    const uint32_t own = p.lastp1[s];
+    if (s == p.nslabs - 1) {
+        int t = s;
+        uint32_t l = own;
+        while (l == 0 && t > 0) l = p.lastp1[--t];
+        p.result->last_pos = l - 1;
+    }
+    if (!DELTAS || own == 0 || s == 0) return;
+    int t = s - 1;
+    uint32_t prev = p.lastp1[t];
+    while (prev == 0 && t > 0) prev = p.lastp1[--t];
+    if (prev == 0) return;  // no structural in front: the first delta stays pos + 1
+    const uint64_t incl = p.dinc[s] & ~DI_VALID;
+    const uint64_t first = incl - (p.dagg[s] & 0x3fffu);
+    if (first < p.out_cap) p.out[first] -= prev;  // (pos + 1) - (prev_pos + 1)
 }
 
 }  // namespace sj

@@ -1,2 +1,647 @@
+// stage2.cuh -- tape construction (unifiedMachine, stage2_build_tape_amd64.go:160-446) as a
+// data-parallel pipeline over the structural positions emitted by K1.
+//
+// The reference walks the structurals with a goto state machine and a scope stack.  Here
+// every structural is handled by its own thread:
+//   K2a classify_measure  type of each structural, atom validation (stage2...go:124-158),
+//                         string validate-only pass (parse_string_amd64.s:72-258)
+//                         -> per-structural tape-word / bracket / string-byte / record counts
+//   K2b scans             exclusive prefix sums of those counts (tile sums -> 2-level scan)
+//   K2c emit              tape slots, parse_number (parse_number.go:65), parse_string copy
+//                         (parse_string_amd64.s:260-479), bracket compaction
+//   K2d ansv              nearest-smaller-depth search over the brackets = the scope stack:
+//                         gives every close its open and every value its enclosing container
+//   K2e grammar           the state machine's transition checks, evaluated locally from
+//                         (previous two structurals, enclosing container); cross-links { } [ ]
+//   K2f roots             root words and NDJSON root chaining (stage2...go:190-221, 428-441)
 #pragma once
 #include "common.cuh"
+#include "number.cuh"
+
+namespace sj {
+
+enum : uint8_t {
+    T_INVALID = 0,
+    T_OBJ_OPEN = 1,
+    T_ARR_OPEN = 2,
+    T_OBJ_CLOSE = 3,
+    T_ARR_CLOSE = 4,
+    T_COLON = 5,
+    T_COMMA = 6,
+    T_STRING = 7,
+    T_NUMBER = 8,
+    T_TRUE = 9,
+    T_FALSE = 10,
+    T_NULL = 11,
+    T_NEWLINE = 12,
+    T_START = 13,
+};
+
+constexpr uint64_t STRINGBUFBIT = 0x80000000000000ull;  // parsed_json.go:29
+constexpr uint32_t AUX_COPY = 0x80000000u;              // string goes to the string buffer
+constexpr int S2_THREADS = 256;
+
+struct ScanVal {
+    uint32_t w;     // tape words
+    uint32_t brk;   // brackets
+    uint32_t str;   // string-buffer bytes
+    uint32_t rec;   // record boundaries (effective NDJSON newlines)
+    int32_t depth;  // +1 open, -1 close
+};
+
+__device__ __forceinline__ ScanVal sv_add(const ScanVal& a, const ScanVal& b) {
+    ScanVal r;
+    r.w = a.w + b.w;
+    r.brk = a.brk + b.brk;
+    r.str = a.str + b.str;
+    r.rec = a.rec + b.rec;
+    r.depth = a.depth + b.depth;
+    return r;
+}
+__device__ __forceinline__ ScanVal sv_zero() { return ScanVal{0, 0, 0, 0, 0}; }
+__device__ __forceinline__ ScanVal sv_shfl_up(const ScanVal& a, int d) {
+    ScanVal r;
+    r.w = __shfl_up_sync(FULL, a.w, d);
+    r.brk = __shfl_up_sync(FULL, a.brk, d);
+    r.str = __shfl_up_sync(FULL, a.str, d);
+    r.rec = __shfl_up_sync(FULL, a.rec, d);
+    r.depth = __shfl_up_sync(FULL, a.depth, d);
+    return r;
+}
+__device__ __forceinline__ ScanVal sv_shfl(const ScanVal& a, int src) {
+    ScanVal r;
+    r.w = __shfl_sync(FULL, a.w, src);
+    r.brk = __shfl_sync(FULL, a.brk, src);
+    r.str = __shfl_sync(FULL, a.str, src);
+    r.rec = __shfl_sync(FULL, a.rec, src);
+    r.depth = __shfl_sync(FULL, a.depth, src);
+    return r;
+}
+
+// block-wide exclusive scan (blockDim.x = NT, a multiple of 32, <= 1024); returns the
+// exclusive prefix of the calling thread and the block total
+template <int NT>
+__device__ __forceinline__ ScanVal block_exclusive_scan(ScanVal v, ScanVal& total) {
+    __shared__ ScanVal warp_tot[NT / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    ScanVal inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        ScanVal t = sv_shfl_up(inc, d);
+        if (lane >= d) inc = sv_add(inc, t);
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    ScanVal wpre = sv_zero(), tot = sv_zero();
+#pragma unroll
+    for (int i = 0; i < NT / 32; i++) {
+        if (i < warp) wpre = sv_add(wpre, warp_tot[i]);
+        tot = sv_add(tot, warp_tot[i]);
+    }
+    __syncthreads();
+    total = tot;
+    ScanVal exc = sv_shfl_up(inc, 1);
+    if (lane == 0) exc = sv_zero();
+    return sv_add(wpre, exc);
+}
+
+struct Stage2Result {
+    uint64_t tape_len;     // total tape words (including both root words of the last record)
+    uint64_t strings_len;  // bytes of the string buffer
+    uint64_t n_brackets;
+    uint64_t n_records;    // record boundaries (roots - 1)
+    int64_t final_depth;
+    uint32_t error;        // any stage-2 failure
+    uint32_t overflow;     // tape / string capacity exceeded
+};
+
+struct Stage2Params {
+    const uint8_t* msg;
+    uint64_t len;
+    const uint32_t* idx;  // structural positions
+    uint32_t n;
+    uint32_t ndjson, copy_strings;
+    // scratch
+    uint8_t* typ;        // [n]
+    uint32_t* aux;       // [n] strings: dst_len | AUX_COPY
+    uint32_t* kb;        // [n] index of the nearest bracket strictly before i (or 0xffffffff)
+    ScanVal* tile_sum;   // [ntiles]
+    ScanVal* tile_pre;   // [ntiles] exclusive within its group of 1024 tiles
+    ScanVal* grp_sum;    // [ngroups]
+    ScanVal* grp_pre;    // [ngroups] exclusive
+    uint32_t ntiles, ngroups;
+    // brackets
+    uint32_t* brk_i;     // [nb] structural index
+    uint32_t* brk_tp;    // [nb] tape slot
+    int32_t* brk_depth;  // [nb] depth before the bracket  (= level 0 of the min hierarchy)
+    int32_t* par;        // [nb] nearest previous bracket with smaller depth (-1 none)
+    uint32_t* rootpos;   // [records + 1] tape slot of each record's root-open word
+    // outputs
+    uint64_t* tape;
+    uint64_t tape_cap;
+    uint8_t* strings;
+    uint64_t strings_cap;
+    Stage2Result* result;
+};
+
+// ---------------------------------------------------------------------------------
+// atoms (stage2_build_tape_amd64.go:124-158, 455-476)
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ bool structural_or_ws_or_nul(uint32_t c) {
+    return c == 0 || c == '\t' || c == '\n' || c == '\r' || c == ' ' || c == ',' || c == ':' || c == '[' ||
+           c == ']' || c == '{' || c == '}';
+}
+__device__ __forceinline__ bool atom_ok(const uint8_t* m, uint64_t pos, uint64_t len, const char* lit, int n) {
+    if (pos + n + 1 > len) return false;  // needs one byte after the literal (len(buf) >= n+1)
+    for (int i = 0; i < n; i++)
+        if (m[pos + i] != (uint8_t)lit[i]) return false;
+    return structural_or_ws_or_nul(m[pos + n]);
+}
+
+// ---------------------------------------------------------------------------------
+// strings
+// ---------------------------------------------------------------------------------
+// parse_string_amd64.s:4-69 digittoval: bytes below '0' map to 0 (no DATA line), hex digits to
+// their value, everything else to -1
+__device__ __forceinline__ int32_t digit_to_val(uint32_t c) {
+    if (c < 0x30) return 0;
+    if (c <= '9') return (int32_t)c - '0';
+    uint32_t l = c | 0x20;
+    if (c < 0x80 && l >= 'a' && l <= 'f' && c >= 'A') return (int32_t)l - 'a' + 10;
+    return -1;
+}
+__device__ __forceinline__ uint32_t escape_map(uint32_t e) {
+    switch (e) {
+    case '"': return 0x22;
+    case '/': return 0x2f;
+    case '\\': return 0x5c;
+    case 'b': return 0x08;
+    case 'f': return 0x0c;
+    case 'n': return 0x0a;
+    case 'r': return 0x0d;
+    case 't': return 0x09;
+    default: return 0;
+    }
+}
+
+struct StrCursor {
+    const uint8_t* body;  // first byte after the opening quote
+    uint64_t avail;       // bytes readable from body; beyond that the reference reads zeros
+    __device__ __forceinline__ uint32_t at(uint64_t i) const { return i < avail ? body[i] : 0; }
+};
+
+// One \-escape starting at body[b].  The window logic of the assembly reduces to: D = distance
+// from the backslash to the next raw '"' byte (looked for within 12 bytes);  \uXXXX needs
+// D >= 6, a surrogate pair D >= 12 (parse_string_amd64.s:101-148,178-180).
+__device__ __forceinline__ bool escape_step(const StrCursor& s, uint64_t b, uint32_t* adv, uint32_t* cp_out,
+                                            uint32_t* nbytes) {
+    uint32_t e = s.at(b + 1);
+    if (e != 'u') {
+        uint32_t m = escape_map(e);
+        if (m == 0) return false;
+        *cp_out = m;
+        *adv = 2;
+        *nbytes = 1;
+        return true;
+    }
+    uint32_t D = 12;
+    for (uint32_t d = 1; d < 12; d++)
+        if (s.at(b + d) == '"') {
+            D = d;
+            break;
+        }
+    if (D < 6) return false;
+    uint32_t cp = ((uint32_t)digit_to_val(s.at(b + 2)) << 12) | ((uint32_t)digit_to_val(s.at(b + 3)) << 8) |
+                  ((uint32_t)digit_to_val(s.at(b + 4)) << 4) | (uint32_t)digit_to_val(s.at(b + 5));
+    uint32_t a = 6;
+    if ((cp & 0xFFFFFC00u) == 0xD800u) {
+        if (D < 12) return false;
+        if (s.at(b + 6) != '\\' || s.at(b + 7) != 'u') return false;
+        uint32_t cp2 = ((uint32_t)digit_to_val(s.at(b + 8)) << 12) | ((uint32_t)digit_to_val(s.at(b + 9)) << 8) |
+                       ((uint32_t)digit_to_val(s.at(b + 10)) << 4) | (uint32_t)digit_to_val(s.at(b + 11));
+        if ((cp | cp2) > 0xFFFFu) return false;
+        cp = (((cp << 10) + 0xFCA00000u) | (cp2 + 0xFFFF2400u)) + 0x10000u;  // low surrogate range NOT checked
+        a = 12;
+    }
+    uint32_t n;
+    if (cp < 0x80u)
+        n = 1;
+    else if (cp < 0x800u)
+        n = 2;
+    else if (cp < 0x10000u)
+        n = 3;
+    else if (cp <= 0x10FFFFu)
+        n = 4;
+    else
+        return false;
+    *cp_out = cp;
+    *adv = a;
+    *nbytes = n;
+    return true;
+}
+
+// _parse_string_validate_only (parse_string_amd64.s:72-258): 32-byte windows starting at p;
+// the bound `p < maxStringSize` is tested when a window is left, exactly like the assembly
+__device__ __forceinline__ bool string_measure(const StrCursor& s, uint64_t max_string_size, uint64_t* src_len,
+                                               uint64_t* dst_len) {
+    if (max_string_size == 0) return false;
+    uint64_t p = 0, dl = 0;
+    for (;;) {
+        uint32_t j = 0, c = 0;
+        for (; j < 32; j++) {
+            c = s.at(p + j);
+            if (c == '"' || c == '\\') break;
+        }
+        if (j == 32) {
+            p += 32;
+            dl += 32;
+        } else if (c == '"') {
+            *src_len = p + j;
+            *dst_len = dl + j;
+            return true;
+        } else {
+            uint32_t adv, cp, n;
+            if (!escape_step(s, p + j, &adv, &cp, &n)) return false;
+            dl += j + n;
+            p += j + adv;
+        }
+        if (!(p < max_string_size)) return false;
+    }
+}
+
+// _parse_string (parse_string_amd64.s:260-479) for a string that already validated
+__device__ __forceinline__ void string_copy(const StrCursor& s, uint8_t* dst) {
+    uint64_t p = 0, dl = 0;
+    for (;;) {
+        uint32_t c = s.at(p);
+        if (c == '"') return;
+        if (c != '\\') {
+            dst[dl++] = (uint8_t)c;
+            p++;
+            continue;
+        }
+        uint32_t adv, cp, n;
+        if (!escape_step(s, p, &adv, &cp, &n)) return;  // cannot happen after validation
+        if (n == 1) {
+            dst[dl++] = (uint8_t)cp;
+        } else if (n == 2) {
+            dst[dl++] = (uint8_t)(0xC0 + (cp >> 6));
+            dst[dl++] = (uint8_t)(0x80 | (cp & 63));
+        } else if (n == 3) {
+            dst[dl++] = (uint8_t)(0xE0 + (cp >> 12));
+            dst[dl++] = (uint8_t)(0x80 | ((cp >> 6) & 63));
+            dst[dl++] = (uint8_t)(0x80 | (cp & 63));
+        } else {
+            dst[dl++] = (uint8_t)(0xF0 + (cp >> 18));
+            dst[dl++] = (uint8_t)(0x80 | ((cp >> 12) & 63));
+            dst[dl++] = (uint8_t)(0x80 | ((cp >> 6) & 63));
+            dst[dl++] = (uint8_t)(0x80 | (cp & 63));
+        }
+        p += adv;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// K2a
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ ScanVal contribution(uint32_t t, uint32_t aux, uint32_t next_t) {
+    ScanVal v = sv_zero();
+    switch (t) {
+    case T_OBJ_OPEN:
+    case T_ARR_OPEN:
+        v.w = 1;
+        v.brk = 1;
+        v.depth = 1;
+        break;
+    case T_OBJ_CLOSE:
+    case T_ARR_CLOSE:
+        v.w = 1;
+        v.brk = 1;
+        v.depth = -1;
+        break;
+    case T_STRING:
+        v.w = 2;
+        v.str = (aux & AUX_COPY) ? (aux & ~AUX_COPY) : 0;
+        break;
+    case T_NUMBER: v.w = 2; break;
+    case T_TRUE:
+    case T_FALSE:
+    case T_NULL: v.w = 1; break;
+    case T_NEWLINE:
+        // the last newline of a run closes the current root and opens the next one
+        // (stage2_build_tape_amd64.go:200-219); trailing newlines produce nothing
+        if (next_t != T_NEWLINE && next_t != T_START) {
+            v.w = 2;
+            v.rec = 1;
+        }
+        break;
+    default: break;
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(S2_THREADS) s2_classify_measure_kernel(const Stage2Params p) {
+    const uint32_t i = blockIdx.x * S2_THREADS + threadIdx.x;
+    ScanVal v = sv_zero();
+    if (i < p.n) {
+        const uint64_t pos = p.idx[i];
+        const uint32_t c = p.msg[pos];
+        const bool has_next = i + 1 < p.n;
+        const uint64_t next_pos = has_next ? p.idx[i + 1] : pos;
+        uint32_t t = T_INVALID, aux = 0;
+        switch (c) {
+        case '{': t = T_OBJ_OPEN; break;
+        case '[': t = T_ARR_OPEN; break;
+        case '}': t = T_OBJ_CLOSE; break;
+        case ']': t = T_ARR_CLOSE; break;
+        case ':': t = T_COLON; break;
+        case ',': t = T_COMMA; break;
+        case 't': t = atom_ok(p.msg, pos, p.len, "true", 4) ? T_TRUE : T_INVALID; break;
+        case 'f': t = atom_ok(p.msg, pos, p.len, "false", 5) ? T_FALSE : T_INVALID; break;
+        case 'n': t = atom_ok(p.msg, pos, p.len, "null", 4) ? T_NULL : T_INVALID; break;
+        case '\n': t = p.ndjson ? T_NEWLINE : T_INVALID; break;
+        case '"': {
+            StrCursor s{p.msg + pos + 1, p.len - pos - 1};
+            uint64_t sl = 0, dl = 0;
+            // peekSize: distance to the next structural, 0 when there is none (stage2...go:63-70)
+            if (string_measure(s, next_pos - pos, &sl, &dl)) {
+                t = T_STRING;
+                aux = (uint32_t)dl | ((p.copy_strings || sl != dl) ? AUX_COPY : 0);  // parse_string_amd64.go:40
+            }
+            break;
+        }
+        default:
+            if (c == '-' || (c - '0') <= 9u) t = T_NUMBER;
+            break;
+        }
+        p.typ[i] = (uint8_t)t;
+        p.aux[i] = aux;
+        uint32_t next_t = T_START;
+        if (has_next) next_t = p.msg[next_pos] == '\n' ? T_NEWLINE : T_INVALID;  // only "newline or not" matters
+        v = contribution(t, aux, next_t);
+    }
+    ScanVal total;
+    block_exclusive_scan<S2_THREADS>(v, total);
+    if (threadIdx.x == 0) p.tile_sum[blockIdx.x] = total;
+}
+
+// ---------------------------------------------------------------------------------
+// K2b: exclusive scan of `in[0..n)` in groups of 1024 (one block per group)
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) s2_scan_groups_kernel(const ScanVal* in, uint32_t n, ScanVal* pre,
+                                                              ScanVal* group_total) {
+    const uint32_t i = blockIdx.x * 1024 + threadIdx.x;
+    ScanVal v = i < n ? in[i] : sv_zero();
+    ScanVal total;
+    ScanVal e = block_exclusive_scan<1024>(v, total);
+    if (i < n) pre[i] = e;
+    if (threadIdx.x == 0) group_total[blockIdx.x] = total;
+}
+
+// single block: exclusive scan of all group totals (looping), grand total into result
+__global__ void __launch_bounds__(1024) s2_scan_top_kernel(const ScanVal* in, uint32_t n, ScanVal* pre,
+                                                           Stage2Result* res) {
+    ScanVal carry = sv_zero();
+    for (uint32_t base = 0; base < n; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        ScanVal v = i < n ? in[i] : sv_zero();
+        ScanVal total;
+        ScanVal e = block_exclusive_scan<1024>(v, total);
+        if (i < n) pre[i] = sv_add(carry, e);
+        carry = sv_add(carry, total);
+    }
+    if (threadIdx.x == 0) {
+        res->tape_len = (uint64_t)carry.w + 2;  // + root open + root close
+        res->strings_len = carry.str;
+        res->n_brackets = carry.brk;
+        res->n_records = carry.rec;
+        res->final_depth = carry.depth;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// K2c
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(S2_THREADS) s2_emit_kernel(const Stage2Params p) {
+    const uint32_t i = blockIdx.x * S2_THREADS + threadIdx.x;
+    uint32_t t = T_INVALID, aux = 0;
+    ScanVal v = sv_zero();
+    if (i < p.n) {
+        t = p.typ[i];
+        aux = p.aux[i];
+        uint32_t next_t = i + 1 < p.n ? p.typ[i + 1] : (uint32_t)T_START;
+        v = contribution(t, aux, next_t);
+    }
+    ScanVal total;
+    ScanVal e = block_exclusive_scan<S2_THREADS>(v, total);
+    if (i >= p.n) return;
+    const uint32_t tile = blockIdx.x;
+    e = sv_add(e, sv_add(p.tile_pre[tile], p.grp_pre[tile >> 10]));
+    const uint64_t tp = 1 + (uint64_t)e.w;  // slot 0 is the first root word
+    p.kb[i] = e.brk - 1;                    // 0xffffffff when no bracket precedes
+    if (tp + v.w > p.tape_cap) {
+        if (v.w) atomicOr(&p.result->overflow, 1u);
+        return;
+    }
+    const uint64_t pos = p.idx[i];
+    switch (t) {
+    case T_OBJ_OPEN:
+    case T_ARR_OPEN:
+    case T_OBJ_CLOSE:
+    case T_ARR_CLOSE:
+        p.brk_i[e.brk] = i;
+        p.brk_tp[e.brk] = (uint32_t)tp;
+        p.brk_depth[e.brk] = e.depth;
+        p.tape[tp] = (uint64_t)p.msg[pos] << 56;  // payload cross-linked by K2e
+        break;
+    case T_STRING: {
+        const uint32_t dl = aux & ~AUX_COPY;
+        if (aux & AUX_COPY) {
+            p.tape[tp] = ((uint64_t)'"' << 56) | (STRINGBUFBIT + e.str);
+            if ((uint64_t)e.str + dl <= p.strings_cap) {
+                StrCursor s{p.msg + pos + 1, p.len - pos - 1};
+                string_copy(s, p.strings + e.str);
+            } else {
+                atomicOr(&p.result->overflow, 1u);
+            }
+        } else {
+            p.tape[tp] = ((uint64_t)'"' << 56) | (pos + 1);  // stage2...go:90-92
+        }
+        p.tape[tp + 1] = dl;
+        break;
+    }
+    case T_NUMBER: {
+        uint64_t val = 0;
+        uint64_t tag = parse_number(p.msg + pos, p.len - pos, &val);
+        if (tag == 0) atomicOr(&p.result->error, 1u);
+        p.tape[tp] = tag;
+        p.tape[tp + 1] = val;
+        break;
+    }
+    case T_TRUE: p.tape[tp] = (uint64_t)'t' << 56; break;
+    case T_FALSE: p.tape[tp] = (uint64_t)'f' << 56; break;
+    case T_NULL: p.tape[tp] = (uint64_t)'n' << 56; break;
+    case T_NEWLINE:
+        if (v.rec) p.rootpos[e.rec + 1] = (uint32_t)tp + 1;  // the new record's root-open slot
+        break;
+    default: break;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// K2d: min hierarchy + nearest-smaller-to-the-left
+// ---------------------------------------------------------------------------------
+constexpr int ANSV_MAX_LEVELS = 8;
+struct AnsvLevels {
+    const int32_t* lv[ANSV_MAX_LEVELS];
+    uint32_t n[ANSV_MAX_LEVELS];
+    int nlevels;
+};
+
+__global__ void s2_min32_kernel(const int32_t* in, uint32_t n_in, int32_t* out, uint32_t n_out) {
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n_out) return;
+    const uint32_t j = w * 32 + lane;
+    int32_t v = j < n_in ? in[j] : 0x7fffffff;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v = min(v, __shfl_xor_sync(FULL, v, d));
+    if (lane == 0) out[w] = v;
+}
+
+__global__ void __launch_bounds__(S2_THREADS) s2_ansv_kernel(AnsvLevels L, int32_t* par) {
+    const uint32_t k = blockIdx.x * S2_THREADS + threadIdx.x;
+    if (k >= L.n[0]) return;
+    const int32_t* D = L.lv[0];
+    const int32_t t = D[k];
+    int64_t found = -1;
+    {
+        int64_t lo = k & ~31u;
+        for (int64_t m = (int64_t)k - 1; m >= lo; m--)
+            if (D[m] < t) {
+                found = m;
+                break;
+            }
+    }
+    if (found < 0) {
+        int lvl = 1;
+        int64_t idx = (int64_t)(k >> 5) - 1;
+        while (lvl < L.nlevels && idx >= 0) {
+            const int32_t* A = L.lv[lvl];
+            const int64_t lo = idx & ~31ll;
+            int64_t hit = -1;
+            for (int64_t j = idx; j >= lo; j--)
+                if (A[j] < t) {
+                    hit = j;
+                    break;
+                }
+            if (hit >= 0) {
+                int64_t cur = hit;
+                for (int l = lvl; l >= 1; l--) {  // descend: last child below the bound
+                    const int32_t* B = L.lv[l - 1];
+                    int64_t base = cur * 32, hi = base + 31;
+                    if (hi >= (int64_t)L.n[l - 1]) hi = (int64_t)L.n[l - 1] - 1;
+                    int64_t c = hi;
+                    while (c > base && !(B[c] < t)) c--;
+                    cur = c;
+                }
+                found = cur;
+                break;
+            }
+            idx = (lo >> 5) - 1;
+            lvl++;
+        }
+    }
+    par[k] = (int32_t)found;
+}
+
+// ---------------------------------------------------------------------------------
+// K2e: grammar (the state machine's transitions) and bracket cross-links
+// ---------------------------------------------------------------------------------
+enum : uint32_t { CTX_ROOT = 0, CTX_OBJ = 1, CTX_ARR = 2 };
+
+__device__ __forceinline__ bool is_value_start(uint32_t c) {
+    return c == T_STRING || c == T_NUMBER || c == T_TRUE || c == T_FALSE || c == T_NULL || c == T_OBJ_OPEN ||
+           c == T_ARR_OPEN;
+}
+__device__ __forceinline__ bool is_scalar_or_close(uint32_t c) {
+    return c == T_NUMBER || c == T_TRUE || c == T_FALSE || c == T_NULL || c == T_OBJ_CLOSE || c == T_ARR_CLOSE;
+}
+
+// stage2_build_tape_amd64.go:176-425, restated as "is c allowed after p (after pp) inside ctx"
+__device__ __forceinline__ bool transition_ok(uint32_t ctx, uint32_t pp, uint32_t p, uint32_t c) {
+    if (c == T_INVALID) return false;
+    if (ctx == CTX_OBJ) {
+        if (p == T_OBJ_OPEN) return c == T_STRING || c == T_OBJ_CLOSE;                // object_begin :225-240
+        if (p == T_STRING) {
+            const bool is_key = pp == T_OBJ_OPEN || pp == T_COMMA;
+            return is_key ? c == T_COLON : (c == T_COMMA || c == T_OBJ_CLOSE);         // :242-248 / objectContinue :302-324
+        }
+        if (p == T_COLON) return is_value_start(c);                                      // :251-300
+        if (is_scalar_or_close(p)) return c == T_COMMA || c == T_OBJ_CLOSE;             // objectContinue
+        if (p == T_COMMA) return c == T_STRING;                                          // :309-316
+        return false;
+    }
+    if (ctx == CTX_ARR) {
+        if (p == T_ARR_OPEN) return is_value_start(c) || c == T_ARR_CLOSE;             // arrayBegin :347-353
+        if (p == T_STRING || is_scalar_or_close(p)) return c == T_COMMA || c == T_ARR_CLOSE;  // arrayContinue :409-425
+        if (p == T_COMMA) return is_value_start(c);                                      // mainArraySwitch :355-407
+        return false;
+    }
+    // top level
+    if (p == T_START) return c == T_OBJ_OPEN || c == T_ARR_OPEN;                       // continueRoot :176-188
+    if (p == T_OBJ_CLOSE || p == T_ARR_CLOSE) return c == T_NEWLINE;                   // startContinue :196-198
+    if (p == T_NEWLINE) return c == T_NEWLINE || c == T_OBJ_OPEN || c == T_ARR_OPEN;   // :200-221
+    return false;
+}
+
+__global__ void __launch_bounds__(S2_THREADS) s2_grammar_kernel(const Stage2Params p) {
+    const uint32_t i = blockIdx.x * S2_THREADS + threadIdx.x;
+    if (i >= p.n) return;
+    const uint32_t c = p.typ[i];
+    const uint32_t pv = i >= 1 ? p.typ[i - 1] : (uint32_t)T_START;
+    const uint32_t ppv = i >= 2 ? p.typ[i - 2] : (uint32_t)T_START;
+    const uint32_t k = p.kb[i];  // nearest bracket strictly before i
+    const bool is_brk = c >= T_OBJ_OPEN && c <= T_ARR_CLOSE;
+    int32_t enclosing = -1;  // bracket index of the innermost open scope before i
+    if (is_brk) {
+        enclosing = p.par[k + 1];  // own bracket index is k + 1
+    } else if (k != 0xffffffffu) {
+        const uint32_t bt = p.typ[p.brk_i[k]];
+        if (bt == T_OBJ_OPEN || bt == T_ARR_OPEN) {
+            enclosing = (int32_t)k;
+        } else {
+            const int32_t m = p.par[k];  // the close's open
+            enclosing = m >= 0 ? p.par[m] : -1;
+        }
+    }
+    uint32_t ctx = CTX_ROOT;
+    if (enclosing >= 0) ctx = p.typ[p.brk_i[enclosing]] == T_OBJ_OPEN ? CTX_OBJ : CTX_ARR;
+    if (!transition_ok(ctx, ppv, pv, c)) {
+        atomicOr(&p.result->error, 1u);
+        return;
+    }
+    if (c == T_OBJ_CLOSE || c == T_ARR_CLOSE) {  // scopeEnd, stage2...go:327-334
+        const uint32_t open_tp = p.brk_tp[enclosing], close_tp = p.brk_tp[k + 1];
+        if (close_tp < p.tape_cap) {
+            p.tape[open_tp] = ((uint64_t)(c == T_OBJ_CLOSE ? '{' : '[') << 56) | ((uint64_t)close_tp + 1);
+            p.tape[close_tp] = ((uint64_t)(c == T_OBJ_CLOSE ? '}' : ']') << 56) | open_tp;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// K2f: root words.  Record r opens at rootpos[r]; its close sits right before the next
+// record's open (or is the last word of the tape).  stage2...go:170,207-218,428-441
+// ---------------------------------------------------------------------------------
+__global__ void s2_roots_kernel(const Stage2Params p, uint64_t n_records, uint64_t tape_len) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > n_records) return;
+    const uint64_t R = (uint64_t)'r' << 56;
+    const uint64_t open = r == 0 ? 0 : p.rootpos[r];
+    const uint64_t next_open = r == n_records ? tape_len : p.rootpos[r + 1];
+    if (next_open > p.tape_cap || next_open == 0) return;
+    p.tape[open] = R | next_open;
+    p.tape[next_open - 1] = R | open;
+}
+
+}  // namespace sj

@@ -1,0 +1,231 @@
+"""GPU parity tests for the whole parse (K1 + K2a..K2f) through the C ABI: tape and string
+buffer bit-exact against the CPU oracle, plus the reference's goldens (G11..G19) and its fuzz
+seed corpora (G20)."""
+import struct
+
+import numpy as np
+import pytest
+
+from tests.util import SMALL_FILES, TAPE_FILES, fuzz_corpus, golden, load_fixture, unhex
+
+pytestmark = pytest.mark.gpu
+M64 = (1 << 64) - 1
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import simdjson_b200 as sj
+    assert sj.SupportedCPU(), "no sm_100 device (the CUDA path has no fallback)"
+    c = sj.Context(0)
+    yield c
+    c.close()
+
+
+def _same_parse(ctx, oracle, msg, ndjson=False, copy=True):
+    rc_g, tape_g, str_g, win_g = ctx.parse(msg, ndjson=ndjson, copy_strings=copy)
+    rc_o, tape_o, str_o, win_o = oracle.parse(msg, ndjson=ndjson, copy_strings=copy)
+    assert rc_g == rc_o, (rc_g, rc_o, bytes(msg[:80]))
+    assert win_g == win_o
+    if rc_o == 0:
+        assert len(tape_g) == len(tape_o)
+        if not np.array_equal(tape_g, tape_o):
+            bad = int(np.nonzero(tape_g != tape_o)[0][0])
+            raise AssertionError("tape differs at %d: gpu %016x oracle %016x" % (bad, int(tape_g[bad]), int(tape_o[bad])))
+        assert str_g == str_o
+    return rc_g
+
+
+def test_g11_stage2_tapes(ctx):
+    for i, tc in enumerate(golden("G11_tapes")):
+        rc, tape, strs, _ = ctx.parse(unhex(tc["input"]), copy_strings=False)
+        assert rc == 0 and [int(x) for x in tape] == tc["tape"], i
+
+
+def test_g12_demo_ndjson_tape(ctx):
+    g = golden("G12_ndjson_tape")
+    rc, tape, _, _ = ctx.parse(unhex(g["input"]), ndjson=True, copy_strings=False)
+    assert rc == 0 and [int(x) for x in tape] == list(g["tape"])
+
+
+def test_g13_atoms(ctx, oracle):
+    g = golden("G13_atoms")
+    for kind in ("true", "false", "null"):
+        for tc in g[kind]:
+            txt = unhex(tc["input"])
+            doc = b"[" + txt.rstrip(b" ") + b"]" if tc["expected"] else b"[" + txt.rstrip(b" ") + b" ]"
+            _same_parse(ctx, oracle, doc)
+
+
+def test_g14_strings(ctx):
+    tcs = golden("G14_strings")
+    items = [b'"' + unhex(tc["str"]) + b'"' for tc in tcs]
+    res = ctx.parse_strings(items)
+    for tc, (ok, sl, dl, out) in zip(tcs, res):
+        assert ok == tc["success"], tc["name"]
+        if ok:
+            assert out == unhex(tc["want"]) and dl == len(out), tc["name"]
+
+
+def test_strings_random_vs_oracle(ctx, oracle):
+    rng = np.random.default_rng(99)
+    alphabet = [b"a", b"\\", b'"', b"u", b"d", b"8", b"0", b"F", b"c", b"\\u", b"\\ud83d", b"\\ude00", b"n", b"/", b"\x00",
+                b"-", b"\xc3\xa9", b"\\\\", b'\\"', b"xyz" * 5, b"t" * 31, b"q" * 33]
+    items, maxs = [], []
+    for _ in range(6000):
+        body = b"".join(alphabet[j] for j in rng.integers(0, len(alphabet), rng.integers(0, 14)))
+        tail = b'"' if rng.integers(0, 8) else b""
+        it = b'"' + body + tail + b"," * int(rng.integers(0, 3))
+        items.append(it)
+        maxs.append(int(rng.integers(0, len(it) + 40)))
+    res = ctx.parse_strings(items, maxs)
+    for it, mx, (ok, sl, dl, out) in zip(items, maxs, res):
+        ok_o, sl_o, dl_o = oracle.parse_string_validate_only(it, mx)
+        assert ok == ok_o, (it, mx)
+        if ok:
+            assert (sl, dl) == (sl_o, dl_o), it
+            assert out == oracle.parse_string(it)[1], it
+
+
+def _tagname(tag):
+    return chr(tag >> 56) if tag else ""
+
+
+def test_g15_numbers(ctx):
+    g = golden("G15_numbers")
+    res = ctx.parse_numbers([tc["input"].encode() + b":" for tc in g["parse_number"]])
+    for tc, (tag, val) in zip(g["parse_number"], res):
+        assert _tagname(tag) == tc["tag"] and tag & ((1 << 56) - 1) == tc["flags"], tc
+        if tc["tag"] == "d":
+            assert struct.pack("<Q", val) == struct.pack("<d", float(tc["d"])), tc
+        elif tc["tag"] == "l":
+            assert val == tc["i"] & M64, tc
+        else:
+            assert val == tc["u"], tc
+    res = ctx.parse_numbers([tc["input"].encode() + b":" for tc in g["parse_int64"]])
+    for tc, (tag, val) in zip(g["parse_int64"], res):
+        assert _tagname(tag) == tc["tag"], tc
+        if tc["tag"] == "l":
+            assert val == tc["out"] & M64, tc
+    res = ctx.parse_numbers([tc["input"].encode() + b":" for tc in g["atof"]])
+    for tc, (tag, val) in zip(g["atof"], res):
+        t = _tagname(tag)
+        if t == "":
+            assert tc["err"], tc
+        elif t == "d":
+            want = float(tc["out"].replace("+Inf", "inf").replace("-Inf", "-inf"))
+            assert struct.pack("<Q", val) == struct.pack("<d", want), tc
+        else:
+            assert str(val if t == "u" else struct.unpack("<q", struct.pack("<Q", val))[0]) == tc["out"], tc
+    for (tag, _), s in zip(ctx.parse_numbers([s.encode() for s in g["valid"]]), g["valid"]):
+        assert tag != 0, s
+    for (tag, _), s in zip(ctx.parse_numbers([s.encode() if s else b" " for s in g["invalid"]]), g["invalid"]):
+        assert tag == 0, s
+
+
+def test_numbers_random_vs_oracle(ctx, oracle):
+    """bit-exact float64 (not just 1 ULP): Clinger / Eisel-Lemire / exact decimal paths"""
+    rng = np.random.default_rng(2024)
+    items = []
+    for _ in range(40000):
+        kind = rng.integers(0, 8)
+        nd = int(rng.integers(1, 25 if kind < 6 else 60))
+        digits = "".join(str(d) for d in rng.integers(0, 10, nd))
+        s = digits.lstrip("0") or "0"
+        if kind in (1, 3, 5, 7):
+            k = int(rng.integers(0, len(s) + 1))
+            s = (s[:k] or "0") + "." + (s[k:] or "0")
+        if kind in (2, 3, 6, 7):
+            s += "eE"[rng.integers(0, 2)] + ["", "+", "-"][rng.integers(0, 3)] + str(int(rng.integers(0, 340)))
+        if rng.integers(0, 2):
+            s = "-" + s
+        items.append(s.encode() + b",")
+    # doubles printed with 17 significant digits, their neighbours' midpoints, subnormals, extremes
+    raw = rng.integers(0, 1 << 63, 20000, dtype=np.int64).view(np.float64)
+    for x in raw[np.isfinite(raw)]:
+        items.append(("%.17g" % x).replace("inf", "1e999").encode() + b"]")
+        items.append(("%.25e" % x).encode() + b"]")
+    for s in ("4.9e-324", "2.4703282292062327e-324", "2.4703282292062328e-324", "1.7976931348623157e308",
+              "1.7976931348623158e308", "1.797693134862315807e308", "8.98846567431158e307", "2.2250738585072011e-308",
+              "0.000000000000000000000000000000000000000000000000000001e-290", "9007199254740993", "9007199254740992.5",
+              "9007199254740993.0000000000000000000000000001", "1e23", "8.5e-323", "123456789012345678901234567890e-30"):
+        items.append(s.encode() + b" ")
+    res = ctx.parse_numbers(items)
+    for it, (tag, val) in zip(items, res):
+        otag, oval = oracle.parse_number(it)
+        assert (tag, val) == (otag, oval), (it, hex(tag), hex(val), hex(otag), hex(oval))
+
+
+def test_g16_g17_documents(ctx, oracle):
+    g = golden("G16_G17_documents")
+    for key, nd in (("fail_cases", False), ("pass_cases", False), ("parse_nd", True)):
+        for tc in g[key]:
+            for copy in (True, False):
+                rc = _same_parse(ctx, oracle, unhex(tc["js"]), ndjson=nd, copy=copy)
+                assert (rc != 0) == tc["want_err"], (key, tc["name"], rc)
+    for hx in g["ndjson_emptylines"]:
+        assert _same_parse(ctx, oracle, unhex(hx), ndjson=True) == 0
+
+
+@pytest.mark.parametrize("name", TAPE_FILES + SMALL_FILES)
+def test_g19_fixture_tapes_vs_oracle(ctx, oracle_native, name):
+    """BASELINE configs 2 and 3 live here: canada (number-heavy), twitterescaped (bit-exact tape check)"""
+    msg = load_fixture(name)
+    for copy in (True, False):
+        assert _same_parse(ctx, oracle_native, msg, copy=copy) == 0
+
+
+def test_g18_parking_citations_ndjson(ctx, oracle_native):
+    msg = load_fixture("parking-citations")
+    for copy in (True, False):
+        assert _same_parse(ctx, oracle_native, msg, ndjson=True, copy=copy) == 0
+    rc, tape, strs, (off, ln) = ctx.parse(msg, ndjson=True)
+    roots = int((tape >> np.uint64(56) == ord("r")).sum()) // 2
+    assert roots == golden("G18_G19_fixtures")["parking_citations"]["roots"]
+
+
+def test_twitter_vs_twitterescaped_identical(ctx):
+    a = ctx.parse(load_fixture("twitter"))
+    b = ctx.parse(load_fixture("twitterescaped"))
+    assert a[0] == b[0] == 0 and np.array_equal(a[1], b[1]) and a[2] == b[2]
+
+
+def test_structure_edge_cases(ctx, oracle):
+    docs = [b"{}", b"[]", b"[[]]", b"[{}]", b'{"a":{}}', b"[" * 300 + b"]" * 300, b"[" * 300 + b"]" * 299, b"[" * 2 + b"]" * 3,
+            b'{"a":[1,2,{"b":[]}],"c":null}', b"[1,2,3", b"[1,,2]", b'{"a" 1}', b'{"a":1,}', b"[1 2]", b'["a":1]', b'{"a":1}}',
+            b"[}", b"{]", b"[true,false,null,tru,falsee]", b"[nul]", b'{"a":truex}', b'{1:2}', b"[-]", b"[1e]", b"[01]", b"[-0]",
+            b"[1.]", b'["\\x"]', b'["\\ud800"]', b'["\\ud800\\u0041"]', b'["a\\"b"]', b" \n\t [1] \r\n", b"\xc2\xa0[1]\xe2\x80\x83",
+            b"", b"   ", b"[\x80]", b'{"k":"v"} x', b'"str"', b"123", b"[1]x", b'[{"a":[{"b":[{"c":[1,2,3]}]}]}]',
+            b'[' + b",".join(b"[%d,%d]" % (i, i) for i in range(5000)) + b"]",      # canada-like: long runs of siblings
+            b'{"a":' * 70 + b"1" + b"}" * 70, b'[' + b'"s",' * 40000 + b'"e"]',      # long flat array: multi-level ANSV
+            ]
+    for d in docs:
+        for copy in (True, False):
+            _same_parse(ctx, oracle, d, copy=copy)
+    nd = [b'{"a":1}\n{"b":2}', b'{"a":1}\n\n\n{"b":2}\n[3]', b'{"a":1}{"b":2}', b'{"a":1}\n', b'{"a":\n1}', b'{"a":1}\n2',
+          b'[1]\n[2]\n[3]\n[4]', b'\n\n[1]\n\n', b'{"a":"x\\ny"}\n{"b":2}', b"[1]\n]", b"[1]\n[", b'{"a":1} \n {"b":2}']
+    for d in nd:
+        for copy in (True, False):
+            _same_parse(ctx, oracle, d, ndjson=True, copy=copy)
+        _same_parse(ctx, oracle, d, ndjson=False)
+
+
+def test_large_documents(ctx, oracle_native):
+    tw = load_fixture("twitter")
+    big = b"[" + b",".join([tw] * 24) + b"]"           # ~15 MB single document, 60 k brackets per copy
+    assert _same_parse(ctx, oracle_native, np.frombuffer(big, dtype=np.uint8)) == 0
+    pk = load_fixture("parking-citations").strip()
+    nd = b"\n".join([pk] * 30)                          # 30 000 NDJSON records
+    assert _same_parse(ctx, oracle_native, np.frombuffer(nd, dtype=np.uint8), ndjson=True) == 0
+    ca = load_fixture("canada")
+    assert _same_parse(ctx, oracle_native, b"[" + b",".join([ca] * 4) + b"]") == 0
+
+
+@pytest.mark.parametrize("which,limit", [("corpus", 1500), ("go-corpus", 400)])
+def test_g20_fuzz_corpus_differential(ctx, oracle_native, which, limit):
+    """fuzz_test.go:40 FuzzParse seeds: same accept/reject and same tape as the oracle"""
+    n = 0
+    for name, data in fuzz_corpus(which, limit=limit, max_size=200_000):
+        for nd in (False, True):
+            _same_parse(ctx, oracle_native, data, ndjson=nd)
+        n += 1
+    assert n > 100
