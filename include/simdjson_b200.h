@@ -59,6 +59,10 @@ void sj_ctx_destroy(sj_ctx* ctx);
 void* sj_host_alloc(size_t bytes);
 void sj_host_free(void* p);
 
+/* Go bytes.TrimSpace as parseMessage applies it (parse_json_amd64.go:55): [*start, *stop) is
+ * the trimmed window.  Pure host helper (no device needed). */
+void sj_trim_space(const uint8_t* msg, size_t len, size_t* start, size_t* stop);
+
 /* Safe output sizes for a message of `len` bytes (SURVEY.md 8b "ownership"). */
 void sj_bounds(size_t len, size_t* tape_cap, size_t* strings_cap);
 

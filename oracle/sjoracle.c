@@ -354,6 +354,14 @@ static inline uint8_t at(const bytes_t *b, uint64_t i) { return i < b->n ? b->p[
 
 static inline void window_masks(const bytes_t *s, uint64_t p, uint32_t *bs, uint32_t *q) {
     uint32_t b = 0, qq = 0;
+#if SJO_SIMD
+    if (p + 32 <= s->n) { /* parse_string_amd64.s:92-100: one YMM load, two compares */
+        __m256i v = _mm256_loadu_si256((const __m256i *)(s->p + p));
+        *bs = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(v, _mm256_set1_epi8('\\')));
+        *q = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(v, _mm256_set1_epi8('"')));
+        return;
+    }
+#endif
     for (int i = 0; i < 32; i++) {
         uint8_t c = at(s, p + (uint64_t)i);
         b |= (uint32_t)(c == '\\') << i;
@@ -361,6 +369,14 @@ static inline void window_masks(const bytes_t *s, uint64_t p, uint32_t *bs, uint
     }
     *bs = b;
     *q = qq;
+}
+
+static inline void copy_bytes(const bytes_t *s, uint64_t p, uint8_t *dst, uint32_t n) {
+    if (p + n <= s->n) {
+        memcpy(dst, s->p + p, n);
+        return;
+    }
+    for (uint32_t i = 0; i < n; i++) dst[i] = at(s, p + i);
 }
 
 static inline int32_t hex4(const bytes_t *s, uint64_t p) {
@@ -465,19 +481,19 @@ int sjo_parse_string(const uint8_t *buf, size_t avail, uint8_t *dst, uint64_t *d
         window_masks(&s, p, &bs, &q);
         if (((bs - 1) & q) != 0) {
             uint32_t t = (uint32_t)__builtin_ctz(q);
-            for (uint32_t i = 0; i < t; i++) dst[dl + i] = at(&s, p + i);
+            copy_bytes(&s, p, dst + dl, t);
             *dst_len = dl + t;
             return 1;
         }
         if (((q - 1) & bs) == 0) {
-            for (uint32_t i = 0; i < 32; i++) dst[dl + i] = at(&s, p + i);
+            copy_bytes(&s, p, dst + dl, 32);
             p += 32;
             dl += 32;
             continue;
         }
         uint32_t b = (uint32_t)__builtin_ctz(bs), adv, cp, n;
         if (!escape_step(&s, p, b, q, &adv, &cp, &n)) return 0;
-        for (uint32_t i = 0; i < b; i++) dst[dl + i] = at(&s, p + i);
+        copy_bytes(&s, p, dst + dl, b);
         dl += b;
         if (n <= 1) {
             dst[dl++] = (uint8_t)cp;

@@ -203,10 +203,10 @@ static int launch_stage1(sj_ctx* c, const uint8_t* d_msg, size_t len, bool ndjso
                          size_t cap) {
     if (len == 0 || len > SJ_MAX_MESSAGE) return SJ_ERR_TOO_LARGE;
     if ((reinterpret_cast<uintptr_t>(d_msg) & 15) != 0) return SJ_ERR_ARGUMENT;
-    int nslabs = (int)((len + S1_SLAB_BYTES - 1) / S1_SLAB_BYTES);
-    // descriptor block: [dinc u64 x n][lastp1 u32 x n][dagg u16 x n8][dpar u8 x n16], every part 16-byte aligned
-    const size_t n16 = ((size_t)nslabs + 15) & ~(size_t)15;
-    const size_t off_inc = 0, off_last = off_inc + n16 * 8, off_agg = off_last + n16 * 4, off_par = off_agg + n16 * 2;
+    const int ntiles = (int)((len + S1_TILE_BYTES - 1) / S1_TILE_BYTES);
+    // descriptor block: [dinc u64][lastp1 u32][dagg u32][dpar u8], every part 16-byte aligned
+    const size_t n16 = ((size_t)ntiles + 15) & ~(size_t)15;
+    const size_t off_inc = 0, off_last = off_inc + n16 * 8, off_agg = off_last + n16 * 4, off_par = off_agg + n16 * 4;
     const size_t desc_bytes = off_par + n16 + 16;
     int rc = c->desc.reserve(desc_bytes);
     if (rc) return rc;
@@ -219,13 +219,13 @@ static int launch_stage1(sj_ctx* c, const uint8_t* d_msg, size_t len, bool ndjso
     p.out_cap = cap;
     p.dinc = reinterpret_cast<uint64_t*>(c->desc.as<uint8_t>() + off_inc);
     p.lastp1 = reinterpret_cast<uint32_t*>(c->desc.as<uint8_t>() + off_last);
-    p.dagg = reinterpret_cast<uint16_t*>(c->desc.as<uint8_t>() + off_agg);
+    p.dagg = reinterpret_cast<uint32_t*>(c->desc.as<uint8_t>() + off_agg);
     p.dpar = c->desc.as<uint8_t>() + off_par;
     p.result = c->result.as<Stage1Result>();
-    p.nslabs = nslabs;
+    p.ntiles = ntiles;
     p.prof = reinterpret_cast<unsigned long long*>(c->result.as<uint8_t>() + 128);
-    int grid = (nslabs + S1_WARPS - 1) / S1_WARPS;
-    if (grid > c->sm_count) grid = c->sm_count;
+    int grid = ntiles;
+    if (grid > c->sm_count * S1_CTAS_PER_SM) grid = c->sm_count * S1_CTAS_PER_SM;
     if (ndjson) {
         if (deltas)
             stage1_flatten_kernel<true, true><<<grid, S1_THREADS, S1_SMEM_BYTES, c->stream>>>(p);
@@ -237,7 +237,7 @@ static int launch_stage1(sj_ctx* c, const uint8_t* d_msg, size_t len, bool ndjso
         else
             stage1_flatten_kernel<false, false><<<grid, S1_THREADS, S1_SMEM_BYTES, c->stream>>>(p);
     }
-    const int fgrid = (nslabs + 255) / 256;
+    const int fgrid = (ntiles + 255) / 256;
     if (deltas)
         stage1_finish_kernel<true><<<fgrid, 256, 0, c->stream>>>(p);
     else
@@ -404,8 +404,8 @@ extern "C" int sj_test_flatten_bits(sj_ctx* c, const uint64_t* masks, size_t nma
 extern "C" int sj_debug_read_prof(sj_ctx* c, unsigned long long* out, int clear) {
     unsigned long long* d = reinterpret_cast<unsigned long long*>(c->result.as<uint8_t>() + 128);
     SJ_CUDA_CHECK(cudaStreamSynchronize(c->stream));
-    SJ_CUDA_CHECK(cudaMemcpy(out, d, 64, cudaMemcpyDeviceToHost));
-    if (clear) SJ_CUDA_CHECK(cudaMemset(d, 0, 64));
+    SJ_CUDA_CHECK(cudaMemcpy(out, d, 128, cudaMemcpyDeviceToHost));
+    if (clear) SJ_CUDA_CHECK(cudaMemset(d, 0, 128));
     return SJ_OK;
 }
 #endif

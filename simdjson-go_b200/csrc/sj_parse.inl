@@ -104,6 +104,17 @@ void trim_space(const uint8_t* b, size_t len, size_t* start_out, size_t* stop_ou
     *stop_out = stop;
 }
 
+}  // namespace
+
+extern "C" void sj_trim_space(const uint8_t* msg, size_t len, size_t* start, size_t* stop) {
+    size_t a = 0, b = 0;
+    if (len) trim_space(msg, len, &a, &b);
+    if (start) *start = a;
+    if (stop) *stop = b;
+}
+
+namespace {
+
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct Carver {  // sub-allocates one DevBuf

@@ -25,15 +25,20 @@
 namespace sj {
 
 #ifndef SJ_S1_WARPS
-#define SJ_S1_WARPS 12
+#define SJ_S1_WARPS 6
 #endif
-constexpr int S1_WARPS = SJ_S1_WARPS;
+#ifndef SJ_S1_CTAS_PER_SM
+#define SJ_S1_CTAS_PER_SM 2
+#endif
+constexpr int S1_WARPS = SJ_S1_WARPS;            // warps per CTA = slabs per tile
+constexpr int S1_CTAS_PER_SM = SJ_S1_CTAS_PER_SM;
 constexpr int S1_THREADS = S1_WARPS * 32;
 constexpr int S1_STEPS = 4;
 constexpr int S1_STEP_BYTES = 32 * 64;
-constexpr int S1_SLAB_BYTES = S1_STEPS * S1_STEP_BYTES;  // 8 KiB per look-back
+constexpr int S1_SLAB_BYTES = S1_STEPS * S1_STEP_BYTES;  // 8 KiB per warp
+constexpr int S1_TILE_BYTES = S1_WARPS * S1_SLAB_BYTES;  // one look-back per tile
 constexpr int S1_BUFS = 2;
-constexpr size_t S1_SMEM_BYTES = (size_t)S1_WARPS * S1_BUFS * S1_SLAB_BYTES + S1_WARPS * S1_BUFS * 8 + 128;
+constexpr size_t S1_SMEM_BYTES = (size_t)S1_BUFS * S1_TILE_BYTES + 64;
 
 struct Stage1Result {
     uint32_t n_idx;           // total structurals found
@@ -282,14 +287,16 @@ __device__ __forceinline__ uint32_t flatten_step(uint64_t S, uint32_t blockpos, 
 // ---------------------------------------------------------------------------------
 // look-back chains.  A look-back can only advance one window of predecessors per L2
 // round trip, so the windows are made wide with narrow descriptors:
-//   chain 1 (in-string parity): one BYTE per slab  {bit0 valid, bit1 inclusive, bit2 parity};
-//           a lane reads 16 descriptors with one 16-byte load -> 512 slabs (4 MiB) per round
-//   chain 2 (structural count): one uint16 aggregate per slab {bit15 valid, count <= 8192}
-//           -> 8 per lane, 256 slabs (2 MiB) per round -- plus one uint64 inclusive prefix
-//           per slab {bit63 valid}; a lane checks the prefix just in front of its group.
+//   chain 1 (in-string parity): one BYTE per tile  {bit0 valid, bit1 inclusive, bit2 parity};
+//           a lane reads 16 descriptors with one 16-byte load -> 512 tiles per round
+//   chain 2 (structural count): one uint32 aggregate per tile {bit31 valid, count}
+//           -> 4 per lane, 128 tiles per round -- plus one uint64 inclusive prefix per tile
+//           {bit63 valid}; a lane checks the prefix just in front of its group.
+// The unit of both chains is a TILE (all slabs of one CTA iteration): only one warp per CTA
+// polls, which keeps the descriptor lines from becoming an L2 hot spot.
 // ---------------------------------------------------------------------------------
 constexpr uint32_t DP_VALID = 1, DP_INCL = 2, DP_PAR = 4;
-constexpr uint32_t DA_VALID = 0x8000u;
+constexpr uint32_t DA_VALID = 0x80000000u;
 constexpr uint64_t DI_VALID = 1ull << 63;
 
 __device__ __forceinline__ uint4 ld_relaxed_v4(const void* p) {
@@ -303,9 +310,6 @@ __device__ __forceinline__ uint4 ld_relaxed_v4(const void* p) {
 __device__ __forceinline__ void st_relaxed_u8(uint8_t* p, uint32_t v) {
     asm volatile("st.relaxed.gpu.global.u8 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ void st_relaxed_u16(uint16_t* p, uint32_t v) {
-    asm volatile("st.relaxed.gpu.global.u16 [%0], %1;" ::"l"(p), "h"((unsigned short)v) : "memory");
-}
 
 // bit k of each of the 16 bytes of q -> 16-bit mask (byte i -> bit i)
 __device__ __forceinline__ uint32_t gather_bit16(const uint4& q, int k) {
@@ -318,13 +322,22 @@ __device__ __forceinline__ uint32_t gather_bit16(const uint4& q, int k) {
 }
 
 // exclusive in-string parity at the entry of `slab` (slab > 0)
-__device__ __forceinline__ uint32_t lookback_parity(const uint8_t* dpar, int slab) {
+__device__ __forceinline__ uint32_t lookback_parity(const uint8_t* dpar, int slab, unsigned long long* prof = nullptr) {
     const int lane = threadIdx.x & 31;
     uint32_t par = 0;
     for (int g = slab >> 4;; g -= 32) {  // lane L inspects the 16-slab group g - L
         const int grp = g - lane;
         uint32_t V, I, P;
+#ifdef SJ_PROFILE_PHASES
+        if (prof && lane == 0) atomicAdd(prof + 10, 1ull);
+#endif
         do {
+#ifdef SJ_PROFILE_PHASES
+            if (prof && lane == 0) atomicAdd(prof + 9, 1ull);
+#endif
+#ifdef SJ_SPIN_SLEEP
+            __nanosleep(SJ_SPIN_SLEEP);
+#endif
             if (grp >= 0) {
                 uint4 q = ld_relaxed_v4(dpar + (size_t)grp * 16);
                 V = gather_bit16(q, 0);
@@ -354,31 +367,37 @@ __device__ __forceinline__ uint32_t lookback_parity(const uint8_t* dpar, int sla
     }
 }
 
-// number of structurals in all slabs in front of `slab` (slab > 0)
-__device__ __forceinline__ uint64_t lookback_count(const uint16_t* dagg, const uint64_t* dinc, int slab) {
+// number of structurals in all tiles in front of `tile` (tile > 0)
+__device__ __forceinline__ uint64_t lookback_count(const uint32_t* dagg, const uint64_t* dinc, int tile,
+                                               unsigned long long* prof = nullptr) {
     const int lane = threadIdx.x & 31;
     uint64_t total = 0;
-    for (int g = slab >> 3;; g -= 32) {  // lane L inspects the 8-slab group g - L
+    for (int g = tile >> 2;; g -= 32) {  // lane L inspects the 4-tile group g - L
         const int grp = g - lane;
         uint32_t sum = 0, valid = 1;
         uint64_t inc = 0;
+#ifdef SJ_PROFILE_PHASES
+        if (prof && lane == 0) atomicAdd(prof + 13, 1ull);
+#endif
         do {
+#ifdef SJ_PROFILE_PHASES
+            if (prof && lane == 0) atomicAdd(prof + 12, 1ull);
+#endif
+#ifdef SJ_SPIN_SLEEP
+            __nanosleep(SJ_SPIN_SLEEP);
+#endif
             if (grp >= 0) {
-                uint4 q = ld_relaxed_v4(dagg + (size_t)grp * 8);
-                inc = grp > 0 ? ld_relaxed_u64(dinc + (size_t)grp * 8 - 1) : DI_VALID;
+                uint4 q = ld_relaxed_v4(dagg + (size_t)grp * 4);
+                inc = grp > 0 ? ld_relaxed_u64(dinc + (size_t)grp * 4 - 1) : DI_VALID;
                 uint32_t w[4] = {q.x, q.y, q.z, q.w};
-                if (grp == (slab >> 3)) {  // own group: drop slabs >= slab (pretend valid, count 0)
-                    const int keep = slab & 7;
+                if (grp == (tile >> 2)) {  // own group: drop tiles >= tile (pretend valid, count 0)
+                    const int keep = tile & 3;
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        if (2 * i >= keep) w[i] = 0x80008000u;
-                        else if (2 * i + 1 >= keep) w[i] = (w[i] & 0xffffu) | 0x80000000u;
-                    }
+                    for (int i = 0; i < 4; i++)
+                        if (i >= keep) w[i] = DA_VALID;
                 }
-                valid = (w[0] & w[1] & w[2] & w[3] & 0x80008000u) == 0x80008000u;
-                sum = 0;
-#pragma unroll
-                for (int i = 0; i < 4; i++) sum += (w[i] & 0x3fffu) + ((w[i] >> 16) & 0x3fffu);
+                valid = (w[0] & w[1] & w[2] & w[3] & DA_VALID) != 0;
+                sum = (w[0] & ~DA_VALID) + (w[1] & ~DA_VALID) + (w[2] & ~DA_VALID) + (w[3] & ~DA_VALID);
             } else {
                 valid = 1;
                 sum = 0;
@@ -387,7 +406,7 @@ __device__ __forceinline__ uint64_t lookback_count(const uint16_t* dagg, const u
         } while (__any_sync(FULL, !valid));
         uint32_t has = __ballot_sync(FULL, (inc & DI_VALID) != 0);
         int f = has ? __ffs(has) - 1 : 31;
-        uint32_t v = lane <= f ? sum : 0;
+        uint64_t v = lane <= f ? sum : 0;
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
         total += v;
@@ -438,12 +457,12 @@ struct Stage1Params {
     uint64_t len;
     uint32_t* out;       // positions (or deltas)
     uint64_t out_cap;
-    uint8_t* dpar;       // [nslabs rounded up to 16] zeroed: chain-1 descriptors
-    uint16_t* dagg;      // [nslabs rounded up to 8] zeroed: chain-2 aggregates
-    uint64_t* dinc;      // [nslabs] zeroed: chain-2 inclusive prefixes
-    uint32_t* lastp1;    // [nslabs] position + 1 of the slab's last structural (0 = none)
+    uint8_t* dpar;       // [ntiles rounded up to 16] zeroed: chain-1 descriptors
+    uint32_t* dagg;      // [ntiles rounded up to 4] zeroed: chain-2 aggregates
+    uint64_t* dinc;      // [ntiles] zeroed: chain-2 inclusive prefixes
+    uint32_t* lastp1;    // [ntiles] position + 1 of the tile's last structural (0 = none)
     Stage1Result* result;
-    int nslabs;
+    int ntiles;
     unsigned long long* prof;  // [8] cycle totals when built with -DSJ_PROFILE_PHASES
 };
 
@@ -483,56 +502,56 @@ __device__ __forceinline__ void mask_tail(uint32_t (&w)[16], uint32_t lane, uint
 }
 
 template <bool NDJSON, bool DELTAS>
-__global__ void __launch_bounds__(S1_THREADS, 1) stage1_flatten_kernel(const Stage1Params p) {
+__global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_kernel(const Stage1Params p) {
     extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ int s_ticket[2];
+    __shared__ uint32_t s_par[S1_WARPS], s_cnt[S1_WARPS], s_last[S1_WARPS];
+    __shared__ uint32_t s_parin;
+    __shared__ unsigned long long s_base;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint8_t* wbuf = smem + (size_t)warp * S1_BUFS * S1_SLAB_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S1_WARPS * S1_BUFS * S1_SLAB_BYTES) + warp * S1_BUFS;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S1_BUFS * S1_TILE_BYTES);
     const uint64_t len16 = (p.len + 15) & ~15ull;
 
-    if (lane == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
-        mbar_fence_init();
-    }
-    __syncwarp();
-
-    auto issue = [&](int slab, int b) {
-        if (lane == 0 && slab < p.nslabs) {
-            uint64_t start = (uint64_t)slab * S1_SLAB_BYTES;
-            uint32_t bytes = (uint32_t)min((uint64_t)S1_SLAB_BYTES, len16 - start);
+    // thread 0 claims tiles (dynamic tickets keep the look-back deadlock-free whatever the
+    // number of resident CTAs) and issues one TMA bulk copy per tile
+    auto claim_and_issue = [&](int b) {
+        int t = (int)atomicAdd(&p.result->ticket, 1u);
+        s_ticket[b] = t;
+        if (t < p.ntiles) {
+            uint64_t start = (uint64_t)t * S1_TILE_BYTES;
+            uint32_t bytes = (uint32_t)min((uint64_t)S1_TILE_BYTES, len16 - start);
             mbar_expect_tx(&bars[b], bytes);
-            tma_load_1d(wbuf + (size_t)b * S1_SLAB_BYTES, p.msg + start, bytes, &bars[b]);
+            tma_load_1d(smem + (size_t)b * S1_TILE_BYTES, p.msg + start, bytes, &bars[b]);
         }
     };
 
-    auto ticket = [&]() -> int {
-        int t = 0;
-        if (lane == 0) t = (int)atomicAdd(&p.result->ticket, 1u);
-        return __shfl_sync(FULL, t, 0);
-    };
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_fence_init();
+        claim_and_issue(0);
+    }
+    __syncthreads();
 
     SJ_PROF_DECL
-    int slab = ticket();
+    int tile = s_ticket[0];
     uint32_t phasebits = 0;
     int b = 0;
-    issue(slab, 0);
 
-    while (slab < p.nslabs) {
+    while (tile < p.ntiles) {
         SJ_PROF_MARK(7)
-#ifdef SJ_NO_PREFETCH_TICKET
-        const int next_slab = 0x7fffffff;
-#else
-        const int next_slab = ticket();
-        issue(next_slab, b ^ 1);
+#ifndef SJ_NO_PREFETCH_TICKET
+        if (threadIdx.x == 0) claim_and_issue(b ^ 1);  // the next tile streams in while this one is processed
 #endif
-        SJ_PROF_MARK(0)  // next slab streams in while this one is processed
+        SJ_PROF_MARK(0)
+        const int slab = tile * S1_WARPS + (int)warp;
         const uint64_t slab_start = (uint64_t)slab * S1_SLAB_BYTES;
-        const uint8_t* buf = wbuf + (size_t)b * S1_SLAB_BYTES;
+        const bool active = slab_start < p.len;  // warps past the end of the message only keep the barriers
+        const uint8_t* buf = smem + (size_t)b * S1_TILE_BYTES + (size_t)warp * S1_SLAB_BYTES;
 
         // carries that depend only on raw bytes in front of the slab
         uint32_t bs_carry = 0, prevc = 0x20, prevc_esc = 0;
-        if (slab > 0) {
+        if (active && slab > 0) {
             bs_carry = backslash_run_before(p.msg, slab_start) & 1;
             prevc = p.msg[slab_start - 1];
             if (prevc == '"') prevc_esc = backslash_run_before(p.msg, slab_start - 1) & 1;  // warp-uniform
@@ -547,48 +566,74 @@ __global__ void __launch_bounds__(S1_THREADS, 1) stage1_flatten_kernel(const Sta
         uint64_t qb[S1_STEPS], st[S1_STEPS], sp[S1_STEPS];
         uint32_t ctmask = 0;  // bit s: step s has a control character somewhere in the warp
         uint32_t slab_par = 0;
+        if (active) {
 #pragma unroll
-        for (int s = 0; s < S1_STEPS; s++) {
-            uint32_t w[16];
-            load_block_words(buf + s * S1_STEP_BYTES, lane, w);
-            const uint64_t blockpos = slab_start + (uint64_t)s * S1_STEP_BYTES + 64 * lane;
-            mask_tail(w, lane, blockpos, p.len);
-            BlockMasks m = classify_block(w);
-            const uint32_t r = (lane >> 1) & 3;
-            uint64_t bs = rotl16x(m.bs, r), qt = rotl16x(m.qt, r);
-            st[s] = rotl16x(m.st, r);
-            sp[s] = rotl16x(m.sp, r);
-            if (__any_sync(FULL, m.anyct != 0)) ctmask |= 1u << s;
+            for (int s = 0; s < S1_STEPS; s++) {
+                uint32_t w[16];
+                load_block_words(buf + s * S1_STEP_BYTES, lane, w);
+                const uint64_t blockpos = slab_start + (uint64_t)s * S1_STEP_BYTES + 64 * lane;
+                mask_tail(w, lane, blockpos, p.len);
+                BlockMasks m = classify_block(w);
+                const uint32_t r = (lane >> 1) & 3;
+                uint64_t bs = rotl16x(m.bs, r), qt = rotl16x(m.qt, r);
+                st[s] = rotl16x(m.st, r);
+                sp[s] = rotl16x(m.sp, r);
+                if (__any_sync(FULL, m.anyct != 0)) ctmask |= 1u << s;
 
-            // odd-backslash carry into each lane's block (warp-uniform fast path: no backslashes at all)
-            uint64_t odd_ends = 0;
-            if (__any_sync(FULL, bs != 0) || bs_carry) {
-                uint32_t allbs = bs == ~0ull;
-                uint32_t trail_odd = (bs == ~0ull) ? 0 : (__clzll(~bs) & 1);
-                uint32_t A = __ballot_sync(FULL, allbs);
-                uint32_t F = __ballot_sync(FULL, trail_odd);
-                uint32_t below = ~A & lanemask_lt();
-                uint32_t cin = below ? (F >> (31 - __clz(below))) & 1 : bs_carry;
-                uint32_t nonpass = ~A;
-                bs_carry = nonpass ? (F >> (31 - __clz(nonpass))) & 1 : bs_carry;
-                odd_ends = odd_backslash_ends(bs, cin, nullptr);
+                // odd-backslash carry into each lane's block (warp-uniform fast path: no backslashes at all)
+                uint64_t odd_ends = 0;
+                if (__any_sync(FULL, bs != 0) || bs_carry) {
+                    uint32_t allbs = bs == ~0ull;
+                    uint32_t trail_odd = (bs == ~0ull) ? 0 : (__clzll(~bs) & 1);
+                    uint32_t A = __ballot_sync(FULL, allbs);
+                    uint32_t F = __ballot_sync(FULL, trail_odd);
+                    uint32_t below = ~A & lanemask_lt();
+                    uint32_t cin = below ? (F >> (31 - __clz(below))) & 1 : bs_carry;
+                    uint32_t nonpass = ~A;
+                    bs_carry = nonpass ? (F >> (31 - __clz(nonpass))) & 1 : bs_carry;
+                    odd_ends = odd_backslash_ends(bs, cin, nullptr);
+                }
+                qb[s] = qt & ~odd_ends;
+                uint32_t P = __ballot_sync(FULL, (__popcll(qb[s]) & 1) != 0);
+                slab_par ^= __popc(P) & 1;
             }
-            qb[s] = qt & ~odd_ends;
-            uint32_t P = __ballot_sync(FULL, (__popcll(qb[s]) & 1) != 0);
-            slab_par ^= __popc(P) & 1;
-        }
-
-        // ---------------- chain 1: in-string parity at slab entry ----------------
-        uint32_t par_in = 0;
-        if (slab == 0) {
-            if (lane == 0) st_relaxed_u8(p.dpar + slab, DP_VALID | DP_INCL | (slab_par ? DP_PAR : 0));
         } else {
-            if (lane == 0) st_relaxed_u8(p.dpar + slab, DP_VALID | (slab_par ? DP_PAR : 0));
-            SJ_PROF_MARK(3)
-            par_in = lookback_parity(p.dpar, slab);
-            SJ_PROF_MARK(4)
-            if (lane == 0) st_relaxed_u8(p.dpar + slab, DP_VALID | DP_INCL | ((slab_par ^ par_in) ? DP_PAR : 0));
+#pragma unroll
+            for (int s = 0; s < S1_STEPS; s++) qb[s] = st[s] = sp[s] = 0;
         }
+        if (lane == 0) s_par[warp] = slab_par;
+        SJ_PROF_MARK(3)
+        __syncthreads();  // (1) slab parities of the tile are visible
+
+        // ---------------- chain 1: in-string parity at tile entry (warp 0 looks back) ----------------
+        uint32_t warp_pre = 0, tile_par = 0;
+#pragma unroll
+        for (int w2 = 0; w2 < S1_WARPS; w2++) {
+            uint32_t v = s_par[w2];
+            tile_par ^= v;
+            if (w2 < (int)warp) warp_pre ^= v;
+        }
+        if (warp == 0) {
+            uint32_t tin = 0;
+            if (tile == 0) {
+                if (lane == 0) st_relaxed_u8(p.dpar + tile, DP_VALID | DP_INCL | (tile_par ? DP_PAR : 0));
+            } else {
+                if (lane == 0) st_relaxed_u8(p.dpar + tile, DP_VALID | (tile_par ? DP_PAR : 0));
+#ifdef SJ_PROFILE_PHASES
+                unsigned long long lb_t0 = clock64();
+                tin = lookback_parity(p.dpar, tile, p.prof);
+                if (lane == 0) atomicAdd(p.prof + 8, clock64() - lb_t0), atomicAdd(p.prof + 14, 1ull);
+#else
+                tin = lookback_parity(p.dpar, tile);
+#endif
+                if (lane == 0) st_relaxed_u8(p.dpar + tile, DP_VALID | DP_INCL | ((tile_par ^ tin) ? DP_PAR : 0));
+            }
+            if (lane == 0) s_parin = tin;
+        }
+        SJ_PROF_MARK(4)
+        __syncthreads();  // (2)
+        const uint32_t tile_par_in = s_parin;
+        const uint32_t par_in = tile_par_in ^ warp_pre;
 
         // pseudo-structural predecessor carry into the slab (finalize_structurals_amd64.s:24-27;
         // initial value 1: stage1_find_marks_amd64.go:54)
@@ -634,6 +679,7 @@ __global__ void __launch_bounds__(S1_THREADS, 1) stage1_flatten_kernel(const Sta
             uint32_t dummy;
             uint64_t fin = finalize_structurals(st[s], ws, qm, qb[s], pp_in, &dummy);
             if (NDJSON) fin |= nl;
+            if (!active) fin = 0;
             S[s] = fin;
             slab_count += __popcll(fin);
         }
@@ -652,22 +698,55 @@ __global__ void __launch_bounds__(S1_THREADS, 1) stage1_flatten_kernel(const Sta
         }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) own_last1 = max(own_last1, __shfl_xor_sync(FULL, own_last1, d));
-
-        // ---------------- chain 2: output offset ----------------
-        uint64_t base = 0;
         if (lane == 0) {
-            p.lastp1[slab] = own_last1;
-            st_relaxed_u16(p.dagg + slab, DA_VALID | slab_count);
+            s_cnt[warp] = slab_count;
+            s_last[warp] = own_last1;
         }
         SJ_PROF_MARK(5)
-        if (slab > 0) base = lookback_count(p.dagg, p.dinc, slab);
+        __syncthreads();  // (3) slab counts of the tile are visible
+
+        // ---------------- chain 2: output offset (warp 0 looks back) ----------------
+        uint32_t warp_base = 0, tile_count = 0, tile_last1 = 0, prev_in_tile1 = 0;
+#pragma unroll
+        for (int w2 = 0; w2 < S1_WARPS; w2++) {
+            uint32_t cnt = s_cnt[w2], l1 = s_last[w2];
+            tile_count += cnt;
+            if (l1) tile_last1 = l1;
+            if (w2 < (int)warp) {
+                warp_base += cnt;
+                if (l1) prev_in_tile1 = l1;
+            }
+        }
+        if (warp == 0) {
+            uint64_t tb = 0;
+            if (lane == 0) {
+                p.lastp1[tile] = tile_last1;
+                st_relaxed_u32(p.dagg + tile, DA_VALID | tile_count);
+            }
+#ifdef SJ_PROFILE_PHASES
+            unsigned long long lb_t1 = clock64();
+            if (tile > 0) tb = lookback_count(p.dagg, p.dinc, tile, p.prof);
+            if (lane == 0) atomicAdd(p.prof + 11, clock64() - lb_t1);
+#else
+            if (tile > 0) tb = lookback_count(p.dagg, p.dinc, tile);
+#endif
+            if (lane == 0) {
+                st_relaxed_u64(p.dinc + tile, DI_VALID | (tb + tile_count));
+                s_base = tb;
+                if (tile == p.ntiles - 1) {
+                    p.result->n_idx = (uint32_t)(tb + tile_count);
+                    p.result->ends_in_string = tile_par_in ^ tile_par;
+                }
+            }
+        }
         SJ_PROF_MARK(6)
-        if (lane == 0) st_relaxed_u64(p.dinc + slab, DI_VALID | (base + slab_count));
+        __syncthreads();  // (4)
+        const uint64_t base = s_base + warp_base;
 
         // ---------------- flatten ----------------
-        // deltas: the first structural of a slab is written as pos + 1 here and rebased on the
-        // previous slab's last structural by stage1_finish_kernel
-        uint32_t prev_last = 0xffffffffu;
+        // deltas: the first structural of a tile is written as pos + 1 here and rebased on the
+        // previous tile's last structural by stage1_finish_kernel
+        uint32_t prev_last = prev_in_tile1 - 1;  // 0xffffffff when nothing precedes inside the tile
         uint32_t overflow = 0;
         uint64_t off = base;
 #pragma unroll
@@ -677,30 +756,27 @@ __global__ void __launch_bounds__(S1_THREADS, 1) stage1_flatten_kernel(const Sta
         }
         if (overflow && lane == 0) atomicOr(&p.result->overflow, 1u);
 
-        if (slab == p.nslabs - 1 && lane == 0) {
-            p.result->n_idx = (uint32_t)(base + slab_count);
-            p.result->ends_in_string = par;
-        }
-        __syncwarp();  // every lane is done with buf before the next TMA may overwrite it
+        // barrier (4) of this iteration ordered every read of buffer b before thread 0 re-arms it;
+        // s_ticket[b ^ 1] was written before barrier (1)
 #ifdef SJ_NO_PREFETCH_TICKET
-        slab = ticket();
-        issue(slab, b ^ 1);
-#else
-        slab = next_slab;
+        __syncthreads();
+        if (threadIdx.x == 0) claim_and_issue(b ^ 1);
+        __syncthreads();
 #endif
+        tile = s_ticket[b ^ 1];
         b ^= 1;
     }
     SJ_PROF_FLUSH
 }
 
-// After K1: rebase the first delta of every slab on the last structural of the slabs in
+// After K1: rebase the first delta of every tile on the last structural of the tiles in
 // front of it (delta mode), and record the position of the last structural of the message.
 template <bool DELTAS>
 __global__ void stage1_finish_kernel(const Stage1Params p) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= p.nslabs) return;
+    if (s >= p.ntiles) return;
     const uint32_t own = p.lastp1[s];
-    if (s == p.nslabs - 1) {
+    if (s == p.ntiles - 1) {
         int t = s;
         uint32_t l = own;
         while (l == 0 && t > 0) l = p.lastp1[--t];
@@ -712,7 +788,7 @@ __global__ void stage1_finish_kernel(const Stage1Params p) {
     while (prev == 0 && t > 0) prev = p.lastp1[--t];
     if (prev == 0) return;  // no structural in front: the first delta stays pos + 1
     const uint64_t incl = p.dinc[s] & ~DI_VALID;
-    const uint64_t first = incl - (p.dagg[s] & 0x3fffu);
+    const uint64_t first = incl - (p.dagg[s] & ~DA_VALID);
     if (first < p.out_cap) p.out[first] -= prev;  // (pos + 1) - (prev_pos + 1)
 }
 

@@ -1,0 +1,72 @@
+"""NDJSON sharding across ranks.
+
+Every raw 0x0A in a valid NDJSON stream is a record boundary (a newline inside a string is a
+stage-1 error, find_quote_mask_and_bits_amd64.s:69-80), so a shard boundary is simply the
+first '\\n' at or after byte k*N/G -- the rule ParseNDStream uses for its 10 MiB chunks
+(simdjson_amd64.go:165-174).  Shards parse independently with fresh carries; the only
+exchange is one all-gather of three integers per rank (shard bytes, tape words, string
+bytes), whose exclusive prefix tells each rank where its tape / strings / message would sit
+in one concatenated ParsedJson.  `rebase_shard_tape` applies those offsets.
+"""
+import numpy as np
+
+TAG_SHIFT = np.uint64(56)
+VAL_MASK = np.uint64((1 << 56) - 1)
+STRINGBUFBIT = np.uint64(1 << 55)
+
+
+def split_at_newlines(buf, world):
+    """[(start, stop)] per rank: contiguous, newline-aligned, covering buf."""
+    n = len(buf)
+    cuts = [0]
+    for r in range(1, world):
+        k = max(cuts[-1], r * n // world)
+        j = buf.find(b"\n", k) if isinstance(buf, (bytes, bytearray)) else _find_nl(buf, k)
+        cuts.append(n if j < 0 else j + 1)
+    cuts.append(n)
+    return [(cuts[i], cuts[i + 1]) for i in range(world)]
+
+
+def _find_nl(arr, k):
+    hit = np.nonzero(np.asarray(arr[k:]) == 0x0A)[0]
+    return -1 if hit.size == 0 else int(hit[0]) + k
+
+
+def exchange_totals(local, group=None, device=None):
+    """all_gather of (shard_bytes, tape_words, string_bytes); returns (exclusive prefix of this
+    rank, list of all ranks' totals).  Works on gloo (CPU tensors) and nccl (device tensors)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    mine = torch.tensor([int(x) for x in local], dtype=torch.int64, device=device)
+    allv = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allv, mine, group=group)
+    totals = [tuple(int(x) for x in t.tolist()) for t in allv]
+    base = tuple(sum(t[i] for t in totals[:rank]) for i in range(3))
+    return base, totals
+
+
+def rebase_shard_tape(tape, tape_base, strings_base, msg_base):
+    """Shift every tape-relative, string-buffer-relative and message-relative payload of a
+    shard-local tape (Appendix B of SURVEY.md) so the shard can be concatenated after
+    `tape_base` tape words / `strings_base` string bytes / `msg_base` message bytes."""
+    t = np.asarray(tape, dtype=np.uint64)
+    tags = (t >> TAG_SHIFT).astype(np.uint8)
+    two_word = np.isin(tags, np.frombuffer(b'"lud', dtype=np.uint8))
+    # the raw second word of a string / number can look like anything: inside a run of
+    # consecutive candidates the real first words sit at even positions
+    idx = np.arange(t.size)
+    run_start = two_word & ~np.concatenate(([False], two_word[:-1]))
+    start_idx = np.maximum.accumulate(np.where(run_start, idx, 0))
+    first = two_word & (((idx - start_idx) & 1) == 0)
+    second = np.concatenate(([False], first[:-1]))
+    out = t.copy()
+    links = ~second & np.isin(tags, np.frombuffer(b"r{}[]", dtype=np.uint8))
+    out[links] = t[links] + np.uint64(tape_base)
+    strs = first & (tags == ord('"'))
+    in_buf = strs & ((t & STRINGBUFBIT) != 0)
+    out[in_buf] = t[in_buf] + np.uint64(strings_base)
+    in_msg = strs & ~in_buf
+    out[in_msg] = t[in_msg] + np.uint64(msg_base)
+    return out

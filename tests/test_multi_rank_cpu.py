@@ -1,0 +1,71 @@
+"""World-size-2 gloo test of the N > 1 path's host logic (CPU only): newline-aligned
+sharding, the 3-integer all_gather, and tape rebasing.  Shards are parsed with the CPU oracle
+here (no GPU in this container); on the GPU box the same code runs over NCCL in bench.py."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, copy, outdir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "simdjson-go_b200"))
+    import torch.distributed as dist
+    from oracle.pyoracle import Oracle
+    from simdjson_b200.parallel import exchange_totals, rebase_shard_tape, split_at_newlines
+    from tests.util import load_fixture
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    stream = load_fixture("parking-citations").strip()
+    a, b = split_at_newlines(stream, world)[rank]
+    o = Oracle("native")
+    rc, tape, strings, (off, ln) = o.parse(stream[a:b], ndjson=True, copy_strings=copy)
+    assert rc == 0
+    base, totals = exchange_totals((b - a, len(tape), len(strings)))
+    assert base[0] == a and len(totals) == world
+    reb = rebase_shard_tape(tape, base[1], base[2], a + off)
+    np.save(os.path.join(outdir, "tape%d.npy" % rank), reb)
+    with open(os.path.join(outdir, "str%d.bin" % rank), "wb") as f:
+        f.write(strings)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("copy", [True, False])
+def test_two_rank_sharded_parse_equals_whole(tmp_path, oracle_native, copy):
+    import torch.multiprocessing as mp
+    from tests.util import load_fixture
+    world = 2
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, copy, str(tmp_path)), nprocs=world, join=True)
+    stream = load_fixture("parking-citations").strip()
+    rc, tape, strings, _ = oracle_native.parse(stream, ndjson=True, copy_strings=copy)
+    assert rc == 0
+    got = np.concatenate([np.load(tmp_path / ("tape%d.npy" % r)) for r in range(world)])
+    gstr = b"".join(open(tmp_path / ("str%d.bin" % r), "rb").read() for r in range(world))
+    assert np.array_equal(got, tape)
+    assert gstr == strings
+
+
+def test_split_at_newlines_covers_and_aligns():
+    sys.path.insert(0, os.path.join(ROOT, "simdjson-go_b200"))
+    from simdjson_b200.parallel import split_at_newlines
+    buf = b"\n".join(b'{"i":%d}' % i for i in range(1000))
+    for world in (1, 2, 3, 4, 8):
+        parts = split_at_newlines(buf, world)
+        assert parts[0][0] == 0 and parts[-1][1] == len(buf)
+        for (a, b), (c, d) in zip(parts, parts[1:]):
+            assert b == c and (b == len(buf) or buf[b - 1:b] == b"\n")

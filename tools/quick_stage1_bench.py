@@ -52,7 +52,7 @@ for lib in libs:
             L.sj_stage1_launch(h, d_msg.data_ptr(), n, 0, deltas, d_out.data_ptr(), cap)
         L.sj_ctx_sync(h)
         if has_prof:
-            buf = (C.c_ulonglong * 8)()
+            buf = (C.c_ulonglong * 16)()
             L.sj_debug_read_prof.argtypes = [vp, C.c_void_p, C.c_int]
             L.sj_debug_read_prof(h, buf, 1)
         reps = 10
@@ -67,6 +67,9 @@ for lib in libs:
         print("  deltas=%d: %.3f ms  input %.1f GB/s  algorithmic %.1f GB/s" % (deltas, t * 1e3, n / t / 1e9, alg / t / 1e9))
         if has_prof:
             L.sj_debug_read_prof(h, buf, 1)
-            tot = float(sum(buf))
+            tot = float(sum(buf[:8]))
             names = ["ticket+issue", "peek", "tma wait", "phaseA", "lookback1", "phaseB", "lookback2", "flatten"]
             print("   " + "  ".join("%s %.1f%%" % (nm, 100 * v / tot) for nm, v in zip(names, buf)))
+            nt = max(1, buf[14])
+            print("   per tile: LB1 %.0f cyc, %.1f spins, %.2f rounds | LB2 %.0f cyc, %.1f spins, %.2f rounds | tiles %d" % (
+                buf[8] / nt, buf[9] / nt, buf[10] / nt, buf[11] / nt, buf[12] / nt, buf[13] / nt, buf[14]))
