@@ -1104,7 +1104,15 @@ int sjo_parse(const uint8_t *msg, size_t len, uint32_t flags, uint64_t *tape, si
     *tape_len = 0;
     *strings_len = 0;
 
-    uint32_t *deltas = (uint32_t *)malloc((n + 64) * sizeof(uint32_t) + 64);
+    /* per-thread scratch, kept across calls (the reference reuses its index ring the same way) */
+    static __thread uint32_t *tl_deltas = NULL;
+    static __thread size_t tl_cap = 0;
+    if (tl_cap < n + 64) {
+        free(tl_deltas);
+        tl_cap = n + 64 + (n >> 3);
+        tl_deltas = (uint32_t *)malloc(tl_cap * sizeof(uint32_t) + 64);
+    }
+    uint32_t *deltas = tl_deltas;
     size_t n_idx = 0;
     int s1 = stage1_driver(m0, n, (flags & SJO_FLAG_NDJSON) != 0, deltas, n + 64, &n_idx);
 
@@ -1121,7 +1129,6 @@ int sjo_parse(const uint8_t *msg, size_t len, uint32_t flags, uint64_t *tape, si
     m.copy_strings = (flags & SJO_FLAG_COPY_STRINGS) != 0;
     int s2 = unified_machine(&m);
     free(m.scope);
-    free(deltas);
     *tape_len = m.tape_len;
     *strings_len = m.str_len;
     if (s1 != 1) return SJO_ERR_STAGE1;

@@ -39,6 +39,7 @@ struct DevBuf {
 struct sj_ctx {
     int device = 0;
     int sm_count = 0;
+    int s1_max_ctas = 0;  // co-resident CTAs of the stage-1 kernel (cooperative launch bound)
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[2] = {nullptr, nullptr};
     uint64_t launches = 0;

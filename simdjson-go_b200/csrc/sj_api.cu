@@ -145,6 +145,12 @@ extern "C" int sj_ctx_create(int device, sj_ctx** out) {
                                        (int)S1_SMEM_BYTES));
     SJ_CUDA_CHECK(cudaFuncSetAttribute(stage1_flatten_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)S1_SMEM_BYTES));
+    int per_sm = 0;
+    SJ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stage1_flatten_kernel<true, true>, S1_THREADS,
+                                                                S1_SMEM_BYTES));
+    if (per_sm < 1) return SJ_ERR_NO_DEVICE;
+    if (per_sm > S1_CTAS_PER_SM) per_sm = S1_CTAS_PER_SM;
+    c->s1_max_ctas = per_sm * c->sm_count;
     *out = c;
     return SJ_OK;
 }
@@ -200,7 +206,7 @@ extern "C" int sj_kernel_launches(sj_ctx* c, uint64_t* count) {
 // stage 1
 // ---------------------------------------------------------------------------------
 static int launch_stage1(sj_ctx* c, const uint8_t* d_msg, size_t len, bool ndjson, bool deltas, uint32_t* d_out,
-                         size_t cap) {
+                         size_t cap, uint32_t* d_bsmap = nullptr) {
     if (len == 0 || len > SJ_MAX_MESSAGE) return SJ_ERR_TOO_LARGE;
     if ((reinterpret_cast<uintptr_t>(d_msg) & 15) != 0) return SJ_ERR_ARGUMENT;
     const int ntiles = (int)((len + S1_TILE_BYTES - 1) / S1_TILE_BYTES);
@@ -223,20 +229,15 @@ static int launch_stage1(sj_ctx* c, const uint8_t* d_msg, size_t len, bool ndjso
     p.dpar = c->desc.as<uint8_t>() + off_par;
     p.result = c->result.as<Stage1Result>();
     p.ntiles = ntiles;
+    p.bsmap = d_bsmap;
     p.prof = reinterpret_cast<unsigned long long*>(c->result.as<uint8_t>() + 128);
     int grid = ntiles;
-    if (grid > c->sm_count * S1_CTAS_PER_SM) grid = c->sm_count * S1_CTAS_PER_SM;
-    if (ndjson) {
-        if (deltas)
-            stage1_flatten_kernel<true, true><<<grid, S1_THREADS, S1_SMEM_BYTES, c->stream>>>(p);
-        else
-            stage1_flatten_kernel<true, false><<<grid, S1_THREADS, S1_SMEM_BYTES, c->stream>>>(p);
-    } else {
-        if (deltas)
-            stage1_flatten_kernel<false, true><<<grid, S1_THREADS, S1_SMEM_BYTES, c->stream>>>(p);
-        else
-            stage1_flatten_kernel<false, false><<<grid, S1_THREADS, S1_SMEM_BYTES, c->stream>>>(p);
-    }
+    if (grid > c->s1_max_ctas) grid = c->s1_max_ctas;
+    // cooperative launch: the static tile deal needs every CTA of the grid resident at once
+    void* args[] = {&p};
+    const void* fn = ndjson ? (deltas ? (const void*)stage1_flatten_kernel<true, true> : (const void*)stage1_flatten_kernel<true, false>)
+                            : (deltas ? (const void*)stage1_flatten_kernel<false, true> : (const void*)stage1_flatten_kernel<false, false>);
+    SJ_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(S1_THREADS), args, S1_SMEM_BYTES, c->stream));
     const int fgrid = (ntiles + 255) / 256;
     if (deltas)
         stage1_finish_kernel<true><<<fgrid, 256, 0, c->stream>>>(p);

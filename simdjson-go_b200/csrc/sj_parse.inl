@@ -141,7 +141,8 @@ struct Carver {  // sub-allocates one DevBuf
 // are sized from the totals (host-buffer API).
 // ---------------------------------------------------------------------------------
 static int run_stage2(sj_ctx* c, const uint8_t* d_msg, size_t len, const uint32_t* d_idx, uint32_t n, uint32_t flags,
-                      uint64_t* d_tape, size_t tape_cap, uint8_t* d_strings, size_t strings_cap, Stage2Result* out) {
+                      uint64_t* d_tape, size_t tape_cap, uint8_t* d_strings, size_t strings_cap, Stage2Result* out,
+                      const uint32_t* d_bsmap) {
     const uint32_t ntiles = (n + S2_THREADS - 1) / S2_THREADS;
     const uint32_t ngroups = (ntiles + 1023) / 1024;
     // ---- phase 1 scratch ----
@@ -156,6 +157,7 @@ static int run_stage2(sj_ctx* c, const uint8_t* d_msg, size_t len, const uint32_
     p.msg = d_msg;
     p.len = len;
     p.idx = d_idx;
+    p.bsmap = d_bsmap;
     p.n = n;
     p.ndjson = (flags & SJ_FLAG_NDJSON) ? 1 : 0;
     p.copy_strings = (flags & SJ_FLAG_COPY_STRINGS) ? 1 : 0;
@@ -271,10 +273,14 @@ static int stage2_verdict(const Stage2Result& r) {
 static int stage1_positions(sj_ctx* c, const uint8_t* d_msg, size_t len, bool ndjson, Stage1Result* r) {
     size_t dcap = len / 4 + 1024;
     if (c->idx.cap / sizeof(uint32_t) > dcap) dcap = c->idx.cap / sizeof(uint32_t);
+    // one bit per 64-byte block, one word per 2 KiB step, rounded up to whole tiles
+    const size_t bs_words = ((len + S1_TILE_BYTES - 1) / S1_TILE_BYTES) * (S1_TILE_BYTES / S1_STEP_BYTES) + 64;
+    int rcb = c->s2c.reserve(bs_words * sizeof(uint32_t));
+    if (rcb) return rcb;
     for (int attempt = 0; attempt < 2; attempt++) {
         int rc = c->idx.reserve(dcap * sizeof(uint32_t));
         if (rc) return rc;
-        rc = launch_stage1(c, d_msg, len, ndjson, false, c->idx.as<uint32_t>(), dcap);
+        rc = launch_stage1(c, d_msg, len, ndjson, false, c->idx.as<uint32_t>(), dcap, c->s2c.as<uint32_t>());
         if (rc) return rc;
         rc = fetch_stage1_result(c, r);
         if (rc) return rc;
@@ -304,7 +310,8 @@ extern "C" int sj_parse_device(sj_ctx* c, const uint8_t* d_msg, size_t len, uint
     }
     if (!stage1_ok(r1, last_char)) return SJ_ERR_STAGE1;
     Stage2Result r2;
-    rc = run_stage2(c, d_msg, len, c->idx.as<uint32_t>(), r1.n_idx, flags, d_tape, tape_cap, d_strings, strings_cap, &r2);
+    rc = run_stage2(c, d_msg, len, c->idx.as<uint32_t>(), r1.n_idx, flags, d_tape, tape_cap, d_strings, strings_cap, &r2,
+                    c->s2c.as<uint32_t>());
     *tape_len = r2.tape_len;
     *strings_len = r2.strings_len;
     if (rc) return rc;
@@ -333,7 +340,8 @@ extern "C" int sj_parse(sj_ctx* c, const uint8_t* msg, size_t len, uint32_t flag
     uint8_t last_char = r1.n_idx && r1.last_pos < n ? msg[a + r1.last_pos] : 0;
     if (!stage1_ok(r1, last_char)) return SJ_ERR_STAGE1;
     Stage2Result r2;
-    rc = run_stage2(c, c->msg.as<uint8_t>(), n, c->idx.as<uint32_t>(), r1.n_idx, flags, nullptr, 0, nullptr, 0, &r2);
+    rc = run_stage2(c, c->msg.as<uint8_t>(), n, c->idx.as<uint32_t>(), r1.n_idx, flags, nullptr, 0, nullptr, 0, &r2,
+                    c->s2c.as<uint32_t>());
     *tape_len = r2.tape_len;
     *strings_len = r2.strings_len;
     if (rc) return rc;

@@ -25,10 +25,10 @@
 namespace sj {
 
 #ifndef SJ_S1_WARPS
-#define SJ_S1_WARPS 6
+#define SJ_S1_WARPS 12
 #endif
 #ifndef SJ_S1_CTAS_PER_SM
-#define SJ_S1_CTAS_PER_SM 2
+#define SJ_S1_CTAS_PER_SM 1
 #endif
 constexpr int S1_WARPS = SJ_S1_WARPS;            // warps per CTA = slabs per tile
 constexpr int S1_CTAS_PER_SM = SJ_S1_CTAS_PER_SM;
@@ -236,9 +236,12 @@ __device__ __forceinline__ uint64_t finalize_structurals(uint64_t st, uint64_t w
 // `prev_last` is the position of the last structural before this step (0xffffffff = none).
 // Returns the number of structurals in the step; updates prev_last.
 // ---------------------------------------------------------------------------------
+// `stage` (optional): 2048 x uint32 of shared memory private to the warp; the lanes drop their
+// entries there and the warp then streams them out with fully coalesced 128-byte stores.
 template <bool DELTAS>
 __device__ __forceinline__ uint32_t flatten_step(uint64_t S, uint32_t blockpos, uint32_t* __restrict__ out,
-                                                 uint64_t base, uint64_t cap, uint32_t& prev_last, uint32_t& overflow) {
+                                                 uint64_t base, uint64_t cap, uint32_t& prev_last, uint32_t& overflow,
+                                                 uint32_t* stage = nullptr) {
     const uint32_t lane = threadIdx.x & 31;
     uint32_t lo = (uint32_t)S, hi = (uint32_t)(S >> 32);
     uint32_t c = __popc(lo) + __popc(hi);
@@ -266,6 +269,28 @@ __device__ __forceinline__ uint32_t flatten_step(uint64_t S, uint32_t blockpos, 
         return total;
     }
     uint32_t pos0 = blockpos;
+    if (stage) {
+        uint32_t so = inc - c;
+        while (lo) {
+            uint32_t b = __ffs(lo) - 1;
+            lo &= lo - 1;
+            uint32_t p = pos0 + b;
+            stage[so++] = DELTAS ? p - prev : p;
+            prev = p;
+        }
+        pos0 += 32;
+        while (hi) {
+            uint32_t b = __ffs(hi) - 1;
+            hi &= hi - 1;
+            uint32_t p = pos0 + b;
+            stage[so++] = DELTAS ? p - prev : p;
+            prev = p;
+        }
+        __syncwarp();
+        for (uint32_t k = lane; k < total; k += 32) out[base + k] = stage[k];
+        __syncwarp();
+        return total;
+    }
     while (lo) {
         uint32_t b = __ffs(lo) - 1;
         lo &= lo - 1;
@@ -461,6 +486,7 @@ struct Stage1Params {
     uint32_t* dagg;      // [ntiles rounded up to 4] zeroed: chain-2 aggregates
     uint64_t* dinc;      // [ntiles] zeroed: chain-2 inclusive prefixes
     uint32_t* lastp1;    // [ntiles] position + 1 of the tile's last structural (0 = none)
+    uint32_t* bsmap;     // optional: bit k = 64-byte block k contains a backslash (lets stage 2 skip the string scan)
     Stage1Result* result;
     int ntiles;
     unsigned long long* prof;  // [8] cycle totals when built with -DSJ_PROFILE_PHASES
@@ -504,19 +530,18 @@ __device__ __forceinline__ void mask_tail(uint32_t (&w)[16], uint32_t lane, uint
 template <bool NDJSON, bool DELTAS>
 __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_kernel(const Stage1Params p) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ int s_ticket[2];
     __shared__ uint32_t s_par[S1_WARPS], s_cnt[S1_WARPS], s_last[S1_WARPS];
     __shared__ uint32_t s_parin;
     __shared__ unsigned long long s_base;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S1_BUFS * S1_TILE_BYTES);
     const uint64_t len16 = (p.len + 15) & ~15ull;
+    const int G = (int)gridDim.x;
 
-    // thread 0 claims tiles (dynamic tickets keep the look-back deadlock-free whatever the
-    // number of resident CTAs) and issues one TMA bulk copy per tile
-    auto claim_and_issue = [&](int b) {
-        int t = (int)atomicAdd(&p.result->ticket, 1u);
-        s_ticket[b] = t;
+    // Tiles are dealt round-robin to the CTAs of a COOPERATIVE launch (all CTAs co-resident), so
+    // every predecessor a look-back waits for is owned by a running CTA; thread 0 issues one TMA
+    // bulk copy per tile, one tile ahead.
+    auto issue = [&](int t, int b) {
         if (t < p.ntiles) {
             uint64_t start = (uint64_t)t * S1_TILE_BYTES;
             uint32_t bytes = (uint32_t)min((uint64_t)S1_TILE_BYTES, len16 - start);
@@ -525,28 +550,34 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
         }
     };
 
+    int tile = blockIdx.x;
     if (threadIdx.x == 0) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
         mbar_fence_init();
-        claim_and_issue(0);
+        issue(tile, 0);
     }
     __syncthreads();
 
     SJ_PROF_DECL
-    int tile = s_ticket[0];
     uint32_t phasebits = 0;
     int b = 0;
 
-    while (tile < p.ntiles) {
+    // software pipeline: iteration i runs phase A / chain 1 / phase B of tile T_i and the chain-2
+    // look-back + flatten of tile T_(i-1); one drain iteration flattens the last tile
+    bool have_prev = false;
+    uint64_t S_prev[S1_STEPS];
+#pragma unroll
+    for (int s = 0; s < S1_STEPS; s++) S_prev[s] = 0;
+    int prev_tile = 0;
+    uint32_t prev_warp_base = 0, prev_tile_count = 0, prev_in_tile1 = 0, prev_par_out = 0;
+
+    while (tile < p.ntiles || have_prev) {
+        const bool cur = tile < p.ntiles;  // CTA-uniform
         SJ_PROF_MARK(7)
-#ifndef SJ_NO_PREFETCH_TICKET
-        if (threadIdx.x == 0) claim_and_issue(b ^ 1);  // the next tile streams in while this one is processed
-#endif
-        SJ_PROF_MARK(0)
         const int slab = tile * S1_WARPS + (int)warp;
         const uint64_t slab_start = (uint64_t)slab * S1_SLAB_BYTES;
-        const bool active = slab_start < p.len;  // warps past the end of the message only keep the barriers
+        const bool active = cur && slab_start < p.len;  // warps past the end of the message only keep the barriers
         const uint8_t* buf = smem + (size_t)b * S1_TILE_BYTES + (size_t)warp * S1_SLAB_BYTES;
 
         // carries that depend only on raw bytes in front of the slab
@@ -556,16 +587,18 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
             prevc = p.msg[slab_start - 1];
             if (prevc == '"') prevc_esc = backslash_run_before(p.msg, slab_start - 1) & 1;  // warp-uniform
         }
-
         SJ_PROF_MARK(1)
-        mbar_wait(&bars[b], (phasebits >> b) & 1);
+        if (cur) {
+            mbar_wait(&bars[b], (phasebits >> b) & 1);
+            phasebits ^= 1u << b;
+        }
         SJ_PROF_MARK(2)
-        phasebits ^= 1u << b;
 
         // ---------------- phase A: classify, escape analysis, slab quote parity ----------------
-        uint64_t qb[S1_STEPS], st[S1_STEPS], sp[S1_STEPS];
-        uint32_t ctmask = 0;  // bit s: step s has a control character somewhere in the warp
+        uint64_t qb[S1_STEPS], st[S1_STEPS], ws[S1_STEPS], ct[S1_STEPS], nl[S1_STEPS];
         uint32_t slab_par = 0;
+#pragma unroll
+        for (int s = 0; s < S1_STEPS; s++) qb[s] = st[s] = ws[s] = ct[s] = nl[s] = 0;
         if (active) {
 #pragma unroll
             for (int s = 0; s < S1_STEPS; s++) {
@@ -577,8 +610,13 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
                 const uint32_t r = (lane >> 1) & 3;
                 uint64_t bs = rotl16x(m.bs, r), qt = rotl16x(m.qt, r);
                 st[s] = rotl16x(m.st, r);
-                sp[s] = rotl16x(m.sp, r);
-                if (__any_sync(FULL, m.anyct != 0)) ctmask |= 1u << s;
+                ws[s] = rotl16x(m.sp, r);
+                if (__any_sync(FULL, m.anyct != 0)) {  // warp-uniform: tab / LF / CR / other control characters
+                    SlowMasks sm = classify_block_slow(w);
+                    ws[s] |= rotl16x(sm.wsc, r);
+                    ct[s] = rotl16x(sm.ct, r);
+                    if (NDJSON) nl[s] = rotl16x(sm.nl, r);
+                }
 
                 // odd-backslash carry into each lane's block (warp-uniform fast path: no backslashes at all)
                 uint64_t odd_ends = 0;
@@ -596,16 +634,19 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
                 qb[s] = qt & ~odd_ends;
                 uint32_t P = __ballot_sync(FULL, (__popcll(qb[s]) & 1) != 0);
                 slab_par ^= __popc(P) & 1;
+                if (p.bsmap) {
+                    uint32_t hasbs = __ballot_sync(FULL, bs != 0);
+                    if (lane == 0) p.bsmap[slab * S1_STEPS + s] = hasbs;
+                }
             }
-        } else {
-#pragma unroll
-            for (int s = 0; s < S1_STEPS; s++) qb[s] = st[s] = sp[s] = 0;
         }
         if (lane == 0) s_par[warp] = slab_par;
         SJ_PROF_MARK(3)
-        __syncthreads();  // (1) slab parities of the tile are visible
+        __syncthreads();  // (1) slab parities visible; buffer b is dead (nothing re-reads the bytes) and
+                          //     buffer b^1 is free (the previous iteration's staging is finished)
+        if (threadIdx.x == 0) issue(tile + G, b ^ 1);
 
-        // ---------------- chain 1: in-string parity at tile entry (warp 0 looks back) ----------------
+        // ---------------- chains (warp 0): parity of this tile, output offset of the previous one ----------------
         uint32_t warp_pre = 0, tile_par = 0;
 #pragma unroll
         for (int w2 = 0; w2 < S1_WARPS; w2++) {
@@ -614,11 +655,27 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
             if (w2 < (int)warp) warp_pre ^= v;
         }
         if (warp == 0) {
+            if (cur && lane == 0)
+                st_relaxed_u8(p.dpar + tile, DP_VALID | (tile == 0 ? DP_INCL : 0) | (tile_par ? DP_PAR : 0));
+            uint64_t tb = 0;
+            if (have_prev) {  // every tile in front of prev_tile published its count one iteration ago
+#ifdef SJ_PROFILE_PHASES
+                unsigned long long lb_t1 = clock64();
+                if (prev_tile > 0) tb = lookback_count(p.dagg, p.dinc, prev_tile, p.prof);
+                if (lane == 0) atomicAdd(p.prof + 11, clock64() - lb_t1);
+#else
+                if (prev_tile > 0) tb = lookback_count(p.dagg, p.dinc, prev_tile);
+#endif
+                if (lane == 0) {
+                    st_relaxed_u64(p.dinc + prev_tile, DI_VALID | (tb + prev_tile_count));
+                    if (prev_tile == p.ntiles - 1) {
+                        p.result->n_idx = (uint32_t)(tb + prev_tile_count);
+                        p.result->ends_in_string = prev_par_out;
+                    }
+                }
+            }
             uint32_t tin = 0;
-            if (tile == 0) {
-                if (lane == 0) st_relaxed_u8(p.dpar + tile, DP_VALID | DP_INCL | (tile_par ? DP_PAR : 0));
-            } else {
-                if (lane == 0) st_relaxed_u8(p.dpar + tile, DP_VALID | (tile_par ? DP_PAR : 0));
+            if (cur && tile > 0) {
 #ifdef SJ_PROFILE_PHASES
                 unsigned long long lb_t0 = clock64();
                 tin = lookback_parity(p.dpar, tile, p.prof);
@@ -628,12 +685,34 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
 #endif
                 if (lane == 0) st_relaxed_u8(p.dpar + tile, DP_VALID | DP_INCL | ((tile_par ^ tin) ? DP_PAR : 0));
             }
-            if (lane == 0) s_parin = tin;
+            if (lane == 0) {
+                s_parin = tin;
+                s_base = tb;
+            }
         }
         SJ_PROF_MARK(4)
         __syncthreads();  // (2)
         const uint32_t tile_par_in = s_parin;
         const uint32_t par_in = tile_par_in ^ warp_pre;
+
+        // ---------------- flatten of the previous tile ----------------
+        if (have_prev) {
+            // deltas: the first structural of a tile is written as pos + 1 here and rebased on the
+            // previous tile's last structural by stage1_finish_kernel
+            uint32_t prev_last = prev_in_tile1 - 1;  // 0xffffffff when nothing precedes inside the tile
+            uint32_t overflow = 0;
+            uint64_t off = s_base + prev_warp_base;
+            // the warp's own 8 KiB slab of buffer b is dead after phase A: reuse it as the staging area
+            uint32_t* stage = reinterpret_cast<uint32_t*>(smem + (size_t)b * S1_TILE_BYTES + (size_t)warp * S1_SLAB_BYTES);
+            const uint64_t pslab_start = ((uint64_t)prev_tile * S1_WARPS + warp) * S1_SLAB_BYTES;
+#pragma unroll
+            for (int s = 0; s < S1_STEPS; s++) {
+                uint32_t blockpos = (uint32_t)(pslab_start + (uint64_t)s * S1_STEP_BYTES + 64 * lane);
+                off += flatten_step<DELTAS>(S_prev[s], blockpos, p.out, off, p.out_cap, prev_last, overflow, stage);
+            }
+            if (overflow && lane == 0) atomicOr(&p.result->overflow, 1u);
+        }
+        SJ_PROF_MARK(5)
 
         // pseudo-structural predecessor carry into the slab (finalize_structurals_amd64.s:24-27;
         // initial value 1: stage1_find_marks_amd64.go:54)
@@ -647,7 +726,6 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
         }
 
         // ---------------- phase B: quote mask, finalize, counts ----------------
-        uint64_t S[S1_STEPS];
         uint32_t err = 0;
         uint32_t par = par_in;
         uint32_t slab_count = 0;
@@ -657,30 +735,18 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
             uint32_t lane_in = par ^ (__popc(P & lanemask_lt()) & 1);
             par ^= __popc(P) & 1;
             uint64_t qm = prefix_xor64(qb[s]) ^ (lane_in ? ~0ull : 0ull);
-            uint64_t ws = sp[s];
-            uint64_t nl = 0;
-            if (ctmask & (1u << s)) {  // warp-uniform slow path: tab / LF / CR / other control characters present
-                uint32_t w[16];
-                load_block_words(buf + s * S1_STEP_BYTES, lane, w);
-                const uint64_t blockpos = slab_start + (uint64_t)s * S1_STEP_BYTES + 64 * lane;
-                mask_tail(w, lane, blockpos, p.len);
-                SlowMasks sm = classify_block_slow(w);
-                const uint32_t r = (lane >> 1) & 3;
-                ws |= rotl16x(sm.wsc, r);
-                if (rotl16x(sm.ct, r) & qm) err = 1;  // find_quote_mask_and_bits_amd64.s:69-80
-                if (NDJSON) nl = rotl16x(sm.nl, r) & ~qm;  // find_newline_delimiters_amd64.s:17-27
-            }
+            if (ct[s] & qm) err = 1;  // find_quote_mask_and_bits_amd64.s:69-80
             // pseudo_pred bit of the previous block: previous lane, or the carry for lane 0
             uint64_t s0 = (st[s] & ~qm) | qb[s];
-            uint32_t my_pp = (uint32_t)((s0 | ws) >> 63);
+            uint32_t my_pp = (uint32_t)((s0 | ws[s]) >> 63);
             uint32_t up = __shfl_up_sync(FULL, my_pp, 1);
             uint32_t pp_in = lane == 0 ? pp_carry : up;
             pp_carry = __shfl_sync(FULL, my_pp, 31);
             uint32_t dummy;
-            uint64_t fin = finalize_structurals(st[s], ws, qm, qb[s], pp_in, &dummy);
-            if (NDJSON) fin |= nl;
+            uint64_t fin = finalize_structurals(st[s], ws[s], qm, qb[s], pp_in, &dummy);
+            if (NDJSON) fin |= nl[s] & ~qm;  // find_newline_delimiters_amd64.s:17-27
             if (!active) fin = 0;
-            S[s] = fin;
+            S_prev[s] = fin;  // flattened in the next iteration
             slab_count += __popcll(fin);
         }
 #pragma unroll
@@ -693,8 +759,8 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
         uint32_t own_last1 = 0;
 #pragma unroll
         for (int s = S1_STEPS - 1; s >= 0; s--) {
-            if (own_last1 == 0 && S[s] != 0)
-                own_last1 = (uint32_t)(slab_start + (uint64_t)s * S1_STEP_BYTES + 64 * lane + 63 - __clzll(S[s])) + 1;
+            if (own_last1 == 0 && S_prev[s] != 0)
+                own_last1 = (uint32_t)(slab_start + (uint64_t)s * S1_STEP_BYTES + 64 * lane + 63 - __clzll(S_prev[s])) + 1;
         }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) own_last1 = max(own_last1, __shfl_xor_sync(FULL, own_last1, d));
@@ -702,11 +768,10 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
             s_cnt[warp] = slab_count;
             s_last[warp] = own_last1;
         }
-        SJ_PROF_MARK(5)
+        SJ_PROF_MARK(6)
         __syncthreads();  // (3) slab counts of the tile are visible
 
-        // ---------------- chain 2: output offset (warp 0 looks back) ----------------
-        uint32_t warp_base = 0, tile_count = 0, tile_last1 = 0, prev_in_tile1 = 0;
+        uint32_t warp_base = 0, tile_count = 0, tile_last1 = 0, in_tile1 = 0;
 #pragma unroll
         for (int w2 = 0; w2 < S1_WARPS; w2++) {
             uint32_t cnt = s_cnt[w2], l1 = s_last[w2];
@@ -714,56 +779,20 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
             if (l1) tile_last1 = l1;
             if (w2 < (int)warp) {
                 warp_base += cnt;
-                if (l1) prev_in_tile1 = l1;
+                if (l1) in_tile1 = l1;
             }
         }
-        if (warp == 0) {
-            uint64_t tb = 0;
-            if (lane == 0) {
-                p.lastp1[tile] = tile_last1;
-                st_relaxed_u32(p.dagg + tile, DA_VALID | tile_count);
-            }
-#ifdef SJ_PROFILE_PHASES
-            unsigned long long lb_t1 = clock64();
-            if (tile > 0) tb = lookback_count(p.dagg, p.dinc, tile, p.prof);
-            if (lane == 0) atomicAdd(p.prof + 11, clock64() - lb_t1);
-#else
-            if (tile > 0) tb = lookback_count(p.dagg, p.dinc, tile);
-#endif
-            if (lane == 0) {
-                st_relaxed_u64(p.dinc + tile, DI_VALID | (tb + tile_count));
-                s_base = tb;
-                if (tile == p.ntiles - 1) {
-                    p.result->n_idx = (uint32_t)(tb + tile_count);
-                    p.result->ends_in_string = tile_par_in ^ tile_par;
-                }
-            }
+        if (cur && threadIdx.x == 0) {  // chain-2 aggregate; its look-back runs one iteration later
+            p.lastp1[tile] = tile_last1;
+            st_relaxed_u32(p.dagg + tile, DA_VALID | tile_count);
         }
-        SJ_PROF_MARK(6)
-        __syncthreads();  // (4)
-        const uint64_t base = s_base + warp_base;
-
-        // ---------------- flatten ----------------
-        // deltas: the first structural of a tile is written as pos + 1 here and rebased on the
-        // previous tile's last structural by stage1_finish_kernel
-        uint32_t prev_last = prev_in_tile1 - 1;  // 0xffffffff when nothing precedes inside the tile
-        uint32_t overflow = 0;
-        uint64_t off = base;
-#pragma unroll
-        for (int s = 0; s < S1_STEPS; s++) {
-            uint32_t blockpos = (uint32_t)(slab_start + (uint64_t)s * S1_STEP_BYTES + 64 * lane);
-            off += flatten_step<DELTAS>(S[s], blockpos, p.out, off, p.out_cap, prev_last, overflow);
-        }
-        if (overflow && lane == 0) atomicOr(&p.result->overflow, 1u);
-
-        // barrier (4) of this iteration ordered every read of buffer b before thread 0 re-arms it;
-        // s_ticket[b ^ 1] was written before barrier (1)
-#ifdef SJ_NO_PREFETCH_TICKET
-        __syncthreads();
-        if (threadIdx.x == 0) claim_and_issue(b ^ 1);
-        __syncthreads();
-#endif
-        tile = s_ticket[b ^ 1];
+        have_prev = cur;
+        prev_tile = tile;
+        prev_warp_base = warp_base;
+        prev_tile_count = tile_count;
+        prev_in_tile1 = in_tile1;
+        prev_par_out = tile_par_in ^ tile_par;
+        tile += G;
         b ^= 1;
     }
     SJ_PROF_FLUSH

@@ -39,6 +39,8 @@ enum : uint8_t {
 
 constexpr uint64_t STRINGBUFBIT = 0x80000000000000ull;  // parsed_json.go:29
 constexpr uint32_t AUX_COPY = 0x80000000u;              // string goes to the string buffer
+constexpr uint32_t AUX_ESC = 0x40000000u;               // string contains escapes (source length != unescaped length)
+constexpr uint32_t AUX_LEN = 0x3fffffffu;
 constexpr int S2_THREADS = 256;
 
 struct ScanVal {
@@ -119,6 +121,7 @@ struct Stage2Params {
     const uint8_t* msg;
     uint64_t len;
     const uint32_t* idx;  // structural positions
+    const uint32_t* bsmap;  // from K1: bit k = 64-byte block k contains a backslash
     uint32_t n;
     uint32_t ndjson, copy_strings;
     // scratch
@@ -321,7 +324,7 @@ __device__ __forceinline__ ScanVal contribution(uint32_t t, uint32_t aux, uint32
         break;
     case T_STRING:
         v.w = 2;
-        v.str = (aux & AUX_COPY) ? (aux & ~AUX_COPY) : 0;
+        v.str = (aux & AUX_COPY) ? (aux & AUX_LEN) : 0;
         break;
     case T_NUMBER: v.w = 2; break;
     case T_TRUE:
@@ -361,12 +364,41 @@ __global__ void __launch_bounds__(S2_THREADS) s2_classify_measure_kernel(const S
         case 'n': t = atom_ok(p.msg, pos, p.len, "null", 4) ? T_NULL : T_INVALID; break;
         case '\n': t = p.ndjson ? T_NEWLINE : T_INVALID; break;
         case '"': {
-            StrCursor s{p.msg + pos + 1, p.len - pos - 1};
             uint64_t sl = 0, dl = 0;
-            // peekSize: distance to the next structural, 0 when there is none (stage2...go:63-70)
-            if (string_measure(s, next_pos - pos, &sl, &dl)) {
+            bool ok = false, fast = false;
+            if (has_next) {
+                // Stage 1 succeeded, so the string closes before the next structural and only
+                // whitespace separates its closing quote from that structural: the quote is the
+                // last non-blank byte in front of it.  With no backslash in the blocks the body
+                // touches (K1's per-block map) nothing needs scanning: src_len == dst_len.
+                uint64_t e = next_pos - 1;
+                while (e > pos) {
+                    uint32_t ce = p.msg[e];
+                    if (!(ce == 0x20 || ce == 0x0a || ce == 0x09 || ce == 0x0d)) break;
+                    e--;
+                }
+                if (e > pos && p.msg[e] == '"') {
+                    fast = true;
+                    for (uint64_t blk = (pos + 1) >> 6; blk <= (e >> 6); blk++)
+                        if ((p.bsmap[blk >> 5] >> (blk & 31)) & 1) {
+                            fast = false;
+                            break;
+                        }
+                    if (fast) {
+                        sl = dl = e - pos - 1;
+                        ok = true;
+                    }
+                }
+            }
+            if (!fast) {
+                StrCursor s{p.msg + pos + 1, p.len - pos - 1};
+                // peekSize: distance to the next structural, 0 when there is none (stage2...go:63-70)
+                ok = string_measure(s, next_pos - pos, &sl, &dl);
+            }
+            if (ok) {
                 t = T_STRING;
-                aux = (uint32_t)dl | ((p.copy_strings || sl != dl) ? AUX_COPY : 0);  // parse_string_amd64.go:40
+                aux = (uint32_t)dl | ((p.copy_strings || sl != dl) ? AUX_COPY : 0) |  // parse_string_amd64.go:40
+                      (sl != dl ? AUX_ESC : 0);
             }
             break;
         }
@@ -424,6 +456,7 @@ __global__ void __launch_bounds__(1024) s2_scan_top_kernel(const ScanVal* in, ui
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(S2_THREADS) s2_emit_kernel(const Stage2Params p) {
     const uint32_t i = blockIdx.x * S2_THREADS + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
     uint32_t t = T_INVALID, aux = 0;
     ScanVal v = sv_zero();
     if (i < p.n) {
@@ -434,57 +467,87 @@ __global__ void __launch_bounds__(S2_THREADS) s2_emit_kernel(const Stage2Params 
     }
     ScanVal total;
     ScanVal e = block_exclusive_scan<S2_THREADS>(v, total);
-    if (i >= p.n) return;
     const uint32_t tile = blockIdx.x;
     e = sv_add(e, sv_add(p.tile_pre[tile], p.grp_pre[tile >> 10]));
     const uint64_t tp = 1 + (uint64_t)e.w;  // slot 0 is the first root word
-    p.kb[i] = e.brk - 1;                    // 0xffffffff when no bracket precedes
-    if (tp + v.w > p.tape_cap) {
+    bool live = i < p.n;
+    if (live) p.kb[i] = e.brk - 1;  // 0xffffffff when no bracket precedes
+    if (live && tp + v.w > p.tape_cap) {
         if (v.w) atomicOr(&p.result->overflow, 1u);
-        return;
+        live = false;
     }
-    const uint64_t pos = p.idx[i];
-    switch (t) {
-    case T_OBJ_OPEN:
-    case T_ARR_OPEN:
-    case T_OBJ_CLOSE:
-    case T_ARR_CLOSE:
-        p.brk_i[e.brk] = i;
-        p.brk_tp[e.brk] = (uint32_t)tp;
-        p.brk_depth[e.brk] = e.depth;
-        p.tape[tp] = (uint64_t)p.msg[pos] << 56;  // payload cross-linked by K2e
-        break;
-    case T_STRING: {
-        const uint32_t dl = aux & ~AUX_COPY;
-        if (aux & AUX_COPY) {
-            p.tape[tp] = ((uint64_t)'"' << 56) | (STRINGBUFBIT + e.str);
-            if ((uint64_t)e.str + dl <= p.strings_cap) {
-                StrCursor s{p.msg + pos + 1, p.len - pos - 1};
-                string_copy(s, p.strings + e.str);
+    const uint64_t pos = live ? p.idx[i] : 0;
+    uint32_t fast_len = 0;  // escape-free string to be copied by the whole warp below
+    if (live) {
+        switch (t) {
+        case T_OBJ_OPEN:
+        case T_ARR_OPEN:
+        case T_OBJ_CLOSE:
+        case T_ARR_CLOSE:
+            p.brk_i[e.brk] = i;
+            p.brk_tp[e.brk] = (uint32_t)tp;
+            p.brk_depth[e.brk] = e.depth;
+            p.tape[tp] = (uint64_t)p.msg[pos] << 56;  // payload cross-linked by K2e
+            break;
+        case T_STRING: {
+            const uint32_t dl = aux & AUX_LEN;
+            if (aux & AUX_COPY) {
+                p.tape[tp] = ((uint64_t)'"' << 56) | (STRINGBUFBIT + e.str);
+                if ((uint64_t)e.str + dl <= p.strings_cap) {
+                    if (aux & AUX_ESC) {
+                        StrCursor s{p.msg + pos + 1, p.len - pos - 1};
+                        string_copy(s, p.strings + e.str);
+                    } else {
+                        fast_len = dl;
+                    }
+                } else {
+                    atomicOr(&p.result->overflow, 1u);
+                }
             } else {
-                atomicOr(&p.result->overflow, 1u);
+                p.tape[tp] = ((uint64_t)'"' << 56) | (pos + 1);  // stage2...go:90-92
             }
-        } else {
-            p.tape[tp] = ((uint64_t)'"' << 56) | (pos + 1);  // stage2...go:90-92
+            p.tape[tp + 1] = dl;
+            break;
         }
-        p.tape[tp + 1] = dl;
-        break;
+        case T_NUMBER: {
+            uint64_t val = 0;
+            uint64_t tag = parse_number(p.msg + pos, p.len - pos, &val);
+            if (tag == 0) atomicOr(&p.result->error, 1u);
+            p.tape[tp] = tag;
+            p.tape[tp + 1] = val;
+            break;
+        }
+        case T_TRUE: p.tape[tp] = (uint64_t)'t' << 56; break;
+        case T_FALSE: p.tape[tp] = (uint64_t)'f' << 56; break;
+        case T_NULL: p.tape[tp] = (uint64_t)'n' << 56; break;
+        case T_NEWLINE:
+            if (v.rec) p.rootpos[e.rec + 1] = (uint32_t)tp + 1;  // the new record's root-open slot
+            break;
+        default: break;
+        }
     }
-    case T_NUMBER: {
-        uint64_t val = 0;
-        uint64_t tag = parse_number(p.msg + pos, p.len - pos, &val);
-        if (tag == 0) atomicOr(&p.result->error, 1u);
-        p.tape[tp] = tag;
-        p.tape[tp + 1] = val;
-        break;
+    // ---- warp-cooperative copy of the warp's escape-free strings: byte k of their concatenation is
+    // moved by lane k mod 32, so both the reads and the writes of the warp are contiguous runs ----
+    uint32_t finc = fast_len;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t up = __shfl_up_sync(FULL, finc, d);
+        if (lane >= d) finc += up;
     }
-    case T_TRUE: p.tape[tp] = (uint64_t)'t' << 56; break;
-    case T_FALSE: p.tape[tp] = (uint64_t)'f' << 56; break;
-    case T_NULL: p.tape[tp] = (uint64_t)'n' << 56; break;
-    case T_NEWLINE:
-        if (v.rec) p.rootpos[e.rec + 1] = (uint32_t)tp + 1;  // the new record's root-open slot
-        break;
-    default: break;
+    const uint32_t T = __shfl_sync(FULL, finc, 31);
+    const uint32_t fo = finc - fast_len;  // exclusive offset of this lane's string
+    const uint32_t src0 = (uint32_t)pos + 1, dst0 = e.str;
+    for (uint32_t base = 0; base < T; base += 32) {
+        const uint32_t k = base + lane;
+        int lo = 0, hi = 31;  // largest lane whose offset is <= k
+#pragma unroll
+        for (int step = 0; step < 5; step++) {
+            int mid = (lo + hi + 1) >> 1;
+            uint32_t vm = __shfl_sync(FULL, fo, mid);
+            if (vm <= k) lo = mid; else hi = mid - 1;
+        }
+        const uint32_t so = __shfl_sync(FULL, fo, lo), ss = __shfl_sync(FULL, src0, lo), sd = __shfl_sync(FULL, dst0, lo);
+        if (k < T) p.strings[sd + (k - so)] = p.msg[ss + (k - so)];
     }
 }
 
