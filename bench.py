@@ -246,6 +246,7 @@ def main():
     # ---- value: device resident ----
     for _ in range(args.warmup):
         step_device()
+        exchange_totals()  # the collective is part of a step: warm its communicator up too
     ms = C.c_float(0)
     launches0 = ctx.launches()
     sampler = ClockSampler(local_rank)

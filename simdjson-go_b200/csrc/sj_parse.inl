@@ -146,7 +146,7 @@ static int run_stage2(sj_ctx* c, const uint8_t* d_msg, size_t len, const uint32_
     const uint32_t ntiles = (n + S2_THREADS - 1) / S2_THREADS;
     const uint32_t ngroups = (ntiles + 1023) / 1024;
     // ---- phase 1 scratch ----
-    size_t need1 = Carver::need({(size_t)n, (size_t)n * 4, (size_t)n * 4, (size_t)ntiles * sizeof(ScanVal),
+    size_t need1 = Carver::need({(size_t)n, (size_t)n * 4, (size_t)ntiles * sizeof(ScanVal),
                                  (size_t)ntiles * sizeof(ScanVal), (size_t)ngroups * sizeof(ScanVal),
                                  (size_t)ngroups * sizeof(ScanVal)});
     int rc = c->s2a.reserve(need1);
@@ -163,7 +163,6 @@ static int run_stage2(sj_ctx* c, const uint8_t* d_msg, size_t len, const uint32_
     p.copy_strings = (flags & SJ_FLAG_COPY_STRINGS) ? 1 : 0;
     p.typ = k1.take<uint8_t>(n);
     p.aux = k1.take<uint32_t>(n);
-    p.kb = k1.take<uint32_t>(n);
     p.tile_sum = k1.take<ScanVal>(ntiles);
     p.tile_pre = k1.take<ScanVal>(ntiles);
     p.grp_sum = k1.take<ScanVal>(ngroups);

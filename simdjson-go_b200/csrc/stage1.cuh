@@ -33,7 +33,10 @@ namespace sj {
 constexpr int S1_WARPS = SJ_S1_WARPS;            // warps per CTA = slabs per tile
 constexpr int S1_CTAS_PER_SM = SJ_S1_CTAS_PER_SM;
 constexpr int S1_THREADS = S1_WARPS * 32;
-constexpr int S1_STEPS = 4;
+#ifndef SJ_S1_STEPS
+#define SJ_S1_STEPS 4
+#endif
+constexpr int S1_STEPS = SJ_S1_STEPS;            // 2 KiB steps per slab
 constexpr int S1_STEP_BYTES = 32 * 64;
 constexpr int S1_SLAB_BYTES = S1_STEPS * S1_STEP_BYTES;  // 8 KiB per warp
 constexpr int S1_TILE_BYTES = S1_WARPS * S1_SLAB_BYTES;  // one look-back per tile
@@ -236,12 +239,12 @@ __device__ __forceinline__ uint64_t finalize_structurals(uint64_t st, uint64_t w
 // `prev_last` is the position of the last structural before this step (0xffffffff = none).
 // Returns the number of structurals in the step; updates prev_last.
 // ---------------------------------------------------------------------------------
-// `stage` (optional): 2048 x uint32 of shared memory private to the warp; the lanes drop their
+// `stage` (optional): stage_cap x uint32 of shared memory private to the warp; the lanes drop their
 // entries there and the warp then streams them out with fully coalesced 128-byte stores.
 template <bool DELTAS>
 __device__ __forceinline__ uint32_t flatten_step(uint64_t S, uint32_t blockpos, uint32_t* __restrict__ out,
                                                  uint64_t base, uint64_t cap, uint32_t& prev_last, uint32_t& overflow,
-                                                 uint32_t* stage = nullptr) {
+                                                 uint32_t* stage = nullptr, uint32_t stage_cap = 0) {
     const uint32_t lane = threadIdx.x & 31;
     uint32_t lo = (uint32_t)S, hi = (uint32_t)(S >> 32);
     uint32_t c = __popc(lo) + __popc(hi);
@@ -269,7 +272,7 @@ __device__ __forceinline__ uint32_t flatten_step(uint64_t S, uint32_t blockpos, 
         return total;
     }
     uint32_t pos0 = blockpos;
-    if (stage) {
+    if (stage && total <= stage_cap) {  // warp-uniform
         uint32_t so = inc - c;
         while (lo) {
             uint32_t b = __ffs(lo) - 1;
@@ -708,7 +711,8 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
 #pragma unroll
             for (int s = 0; s < S1_STEPS; s++) {
                 uint32_t blockpos = (uint32_t)(pslab_start + (uint64_t)s * S1_STEP_BYTES + 64 * lane);
-                off += flatten_step<DELTAS>(S_prev[s], blockpos, p.out, off, p.out_cap, prev_last, overflow, stage);
+                off += flatten_step<DELTAS>(S_prev[s], blockpos, p.out, off, p.out_cap, prev_last, overflow, stage,
+                                            S1_SLAB_BYTES / 4);
             }
             if (overflow && lane == 0) atomicOr(&p.result->overflow, 1u);
         }

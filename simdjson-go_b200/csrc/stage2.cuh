@@ -127,7 +127,6 @@ struct Stage2Params {
     // scratch
     uint8_t* typ;        // [n]
     uint32_t* aux;       // [n] strings: dst_len | AUX_COPY
-    uint32_t* kb;        // [n] index of the nearest bracket strictly before i (or 0xffffffff)
     ScanVal* tile_sum;   // [ntiles]
     ScanVal* tile_pre;   // [ntiles] exclusive within its group of 1024 tiles
     ScanVal* grp_sum;    // [ngroups]
@@ -471,7 +470,6 @@ __global__ void __launch_bounds__(S2_THREADS) s2_emit_kernel(const Stage2Params 
     e = sv_add(e, sv_add(p.tile_pre[tile], p.grp_pre[tile >> 10]));
     const uint64_t tp = 1 + (uint64_t)e.w;  // slot 0 is the first root word
     bool live = i < p.n;
-    if (live) p.kb[i] = e.brk - 1;  // 0xffffffff when no bracket precedes
     if (live && tp + v.w > p.tape_cap) {
         if (v.w) atomicOr(&p.result->overflow, 1u);
         live = false;
@@ -658,13 +656,25 @@ __device__ __forceinline__ bool transition_ok(uint32_t ctx, uint32_t pp, uint32_
 }
 
 __global__ void __launch_bounds__(S2_THREADS) s2_grammar_kernel(const Stage2Params p) {
+    __shared__ uint32_t s_wcnt[S2_THREADS / 32];
     const uint32_t i = blockIdx.x * S2_THREADS + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t c = i < p.n ? p.typ[i] : (uint32_t)T_INVALID;
+    const bool is_brk = c >= T_OBJ_OPEN && c <= T_ARR_CLOSE;
+    // index of the nearest bracket strictly before i = (brackets in front of i) - 1: the tile
+    // prefix from K2b plus an in-block ballot count (no per-structural array needed)
+    const uint32_t bal = __ballot_sync(FULL, is_brk);
+    if (lane == 0) s_wcnt[warp] = __popc(bal);
+    __syncthreads();
+    uint32_t before = __popc(bal & lanemask_lt());
+#pragma unroll
+    for (int w2 = 0; w2 < S2_THREADS / 32; w2++)
+        if (w2 < (int)warp) before += s_wcnt[w2];
     if (i >= p.n) return;
-    const uint32_t c = p.typ[i];
+    before += p.tile_pre[blockIdx.x].brk + p.grp_pre[blockIdx.x >> 10].brk;
+    const uint32_t k = before - 1;  // 0xffffffff when no bracket precedes
     const uint32_t pv = i >= 1 ? p.typ[i - 1] : (uint32_t)T_START;
     const uint32_t ppv = i >= 2 ? p.typ[i - 2] : (uint32_t)T_START;
-    const uint32_t k = p.kb[i];  // nearest bracket strictly before i
-    const bool is_brk = c >= T_OBJ_OPEN && c <= T_ARR_CLOSE;
     int32_t enclosing = -1;  // bracket index of the innermost open scope before i
     if (is_brk) {
         enclosing = p.par[k + 1];  // own bracket index is k + 1

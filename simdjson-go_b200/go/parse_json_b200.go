@@ -1,0 +1,90 @@
+//go:build cgo && b200
+
+// Package simdjson: drop-in replacement for parse_json_amd64.go of minio/simdjson-go.
+//
+// This file is the ONLY Go code the B200 path needs: it replaces
+// (*internalParsedJson).parseMessage (reference parse_json_amd64.go:52) with one cgo call into
+// libsimdjson_b200.so.  Parse / ParseND / ParseNDStream (simdjson_amd64.go:66,82,116) and every
+// tape consumer (Iter, Object, Array, Serializer) stay as they are: the {Message, Tape,
+// Strings.B} triple written here is bit-exact with the assembly path.
+//
+// NOTE: the build image of this repository has no Go toolchain, so this file is not compiled
+// by the test-suite; the identical call sequence is exercised through the ctypes binding
+// (simdjson-go_b200/simdjson_b200/__init__.py: Context.parse).  Build it inside a checkout of
+// the reference with:  go build -tags b200   (and drop parse_json_amd64.go's build tag).
+package simdjson
+
+/*
+#cgo CFLAGS: -I${SRCDIR}/../../include
+#cgo LDFLAGS: -L${SRCDIR}/.. -lsimdjson_b200 -Wl,-rpath,${SRCDIR}/..
+#include "simdjson_b200.h"
+*/
+import "C"
+
+import (
+	"errors"
+	"sync"
+	"unsafe"
+)
+
+// one sj_ctx (CUDA stream + device scratch) per concurrent parse, recycled like the
+// reference recycles *ParsedJson internals (simdjson_amd64.go:46-51)
+var b200Pool = sync.Pool{New: func() any {
+	var h *C.sj_ctx
+	if rc := C.sj_ctx_create(-1, &h); rc != C.SJ_OK {
+		return (*C.sj_ctx)(nil)
+	}
+	return h
+}}
+
+// SupportedCPU reports whether the B200 path can run (simdjson_amd64.go:37).
+func SupportedCPU() bool { return C.sj_supported() != 0 }
+
+func (pj *internalParsedJson) parseMessage(msg []byte, ndjson bool) error {
+	h, _ := b200Pool.Get().(*C.sj_ctx)
+	if h == nil {
+		return errors.New("Host CPU does not meet target specs") // simdjson_amd64.go:43
+	}
+	defer b200Pool.Put(h)
+
+	var flags C.uint32_t
+	if ndjson {
+		flags |= C.SJ_FLAG_NDJSON
+	}
+	if pj.copyStrings {
+		flags |= C.SJ_FLAG_COPY_STRINGS
+	}
+	var tapeCap, strCap C.size_t
+	C.sj_bounds(C.size_t(len(msg)), &tapeCap, &strCap)
+	if cap(pj.Tape) < int(tapeCap) {
+		pj.Tape = make([]uint64, 0, tapeCap)
+	}
+	if pj.Strings == nil || cap(pj.Strings.B) < int(strCap) {
+		pj.Strings = &TStrings{make([]byte, 0, strCap)}
+	}
+	var tapeLen, strLen, off, n C.size_t
+	var p *C.uint8_t
+	if len(msg) > 0 {
+		p = (*C.uint8_t)(unsafe.Pointer(&msg[0]))
+	}
+	tape := pj.Tape[:cap(pj.Tape)]
+	strs := pj.Strings.B[:cap(pj.Strings.B)]
+	rc := C.sj_parse(h, p, C.size_t(len(msg)), flags,
+		(*C.uint64_t)(unsafe.Pointer(unsafe.SliceData(tape))), tapeCap, &tapeLen,
+		(*C.uint8_t)(unsafe.Pointer(unsafe.SliceData(strs))), strCap, &strLen,
+		&off, &n)
+	pj.Message = msg[off : off+n] // bytes.TrimSpace window (parse_json_amd64.go:55)
+	switch rc {
+	case C.SJ_OK:
+		pj.Tape = tape[:tapeLen]
+		pj.Strings.B = strs[:strLen]
+		pj.isvalid = true
+		return nil
+	case C.SJ_ERR_STAGE1:
+		return errors.New("Failed to find all structural indices for stage 1") // parse_json_amd64.go:93
+	case C.SJ_ERR_STAGE2:
+		return errors.New("Bad parsing while executing stage 2") // parse_json_amd64.go:81
+	default:
+		return errors.New(C.GoString(C.sj_error_string(rc)))
+	}
+}
