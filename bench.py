@@ -91,12 +91,20 @@ class ClockSampler(threading.Thread):
 # --------------------------------------------------------------------------------------
 # CPU arm: the oracle port, ParseNDStream-shaped (simdjson_amd64.go:116-215)
 # --------------------------------------------------------------------------------------
+_cpu_pool = None
+_cpu_local = threading.local()
+
+
 def cpu_parse_stream(buf, threads, chunk=10 << 20):
-    """Parse `buf` as NDJSON in newline-aligned ~10 MiB chunks on `threads` host threads.
-    Returns (seconds, bytes parsed)."""
+    """Parse `buf` as NDJSON in newline-aligned ~10 MiB chunks on `threads` host threads
+    (persistent workers with reused output buffers, like the reference's `reuse` channel,
+    simdjson_amd64.go:116).  Returns (seconds, bytes parsed)."""
+    global _cpu_pool
     from concurrent.futures import ThreadPoolExecutor
     from oracle.pyoracle import FLAG_COPY_STRINGS, FLAG_NDJSON, Oracle
     o = Oracle("native")
+    if _cpu_pool is None or _cpu_pool._max_workers != threads:
+        _cpu_pool = ThreadPoolExecutor(max_workers=threads)
     arr = np.frombuffer(buf, dtype=np.uint8)
     cuts = [0]
     while cuts[-1] < len(buf):
@@ -106,15 +114,15 @@ def cpu_parse_stream(buf, threads, chunk=10 << 20):
             break
         j = buf.find(b"\n", nxt)
         cuts.append(len(buf) if j < 0 else j + 1)
-    local = threading.local()
+    local = _cpu_local
 
     def work(i):
         a, b = cuts[i], cuts[i + 1]
         n = b - a
         if not hasattr(local, "tape") or local.cap < n:
-            local.cap = n
-            local.tape = np.empty(2 * n + 64, dtype=np.uint64)
-            local.strs = np.empty(n + 64, dtype=np.uint8)
+            local.cap = n + (n >> 2)
+            local.tape = np.empty(2 * local.cap + 64, dtype=np.uint64)
+            local.strs = np.empty(local.cap + 64, dtype=np.uint8)
         tl, sl, mo, ml = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0), C.c_size_t(0)
         rc = o.lib.sjo_parse(arr[a:b].ctypes.data, n, FLAG_NDJSON | FLAG_COPY_STRINGS, local.tape.ctypes.data,
                              local.tape.size, C.byref(tl), local.strs.ctypes.data, local.strs.size, C.byref(sl),
@@ -123,8 +131,7 @@ def cpu_parse_stream(buf, threads, chunk=10 << 20):
         return n
 
     t0 = time.perf_counter()
-    with ThreadPoolExecutor(max_workers=threads) as ex:
-        total = sum(ex.map(work, range(len(cuts) - 1)))
+    total = sum(_cpu_pool.map(work, range(len(cuts) - 1)))
     return time.perf_counter() - t0, total
 
 
@@ -138,6 +145,7 @@ def run_reference(args, rank, world):
     warm = warm[: warm.rfind(b"\n")]
     for _ in range(args.warmup):
         cpu_parse_stream(warm, threads)
+    cpu_parse_stream(sample, threads)  # first touch of every worker's buffers stays outside the timed steps
     secs = 0.0
     nbytes = 0
     for _ in range(args.steps):
@@ -329,6 +337,7 @@ def main():
         sample = sample[: sample.rfind(b"\n")]
         warm = sample[: 32 << 20]
         cpu_parse_stream(warm[: warm.rfind(b"\n")], threads)
+        cpu_parse_stream(sample, threads)  # first touch of every worker's buffers stays outside the timed region
         secs, nb = cpu_parse_stream(sample, threads)
         reps = 1
         while secs < 5.0 and reps < 8:  # stretch tiny timings to a few seconds of CPU work

@@ -229,3 +229,36 @@ def test_g20_fuzz_corpus_differential(ctx, oracle_native, which, limit):
             _same_parse(ctx, oracle_native, data, ndjson=nd)
         n += 1
     assert n > 100
+
+
+def test_concurrent_contexts(oracle_native):
+    """parse_json_amd64.go is re-entrant on distinct ParsedJson values (ParseNDStream runs several
+    parses at once, simdjson_amd64.go:132): distinct contexts must be usable from distinct threads"""
+    import threading
+    import simdjson_b200 as sj
+    names = ["twitter", "canada", "citm_catalog", "random"]
+    want = {n: oracle_native.parse(load_fixture(n)) for n in names}
+    errs = []
+
+    def work(name):
+        try:
+            c = sj.Context(0)
+            for _ in range(4):
+                rc, tape, strs, _ = c.parse(load_fixture(name))
+                assert rc == 0 and np.array_equal(tape, want[name][1]) and strs == want[name][2]
+            c.close()
+        except Exception as e:  # noqa: BLE001
+            errs.append((name, repr(e)))
+
+    ts = [threading.Thread(target=work, args=(n,)) for n in names]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs
+
+
+def test_too_large_and_empty(ctx):
+    import ctypes as C
+    tl, sl, mo, ml = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0), C.c_size_t(0)
+    rc = ctx.L.sj_parse(ctx.h, None, 0, 0, None, 0, C.byref(tl), None, 0, C.byref(sl), C.byref(mo), C.byref(ml))
+    assert rc == 1  # empty input: stage-1 failure, like the reference
+    assert ctx.L.sj_stage1_launch(ctx.h, 16, (1 << 31) + 5, 0, 0, 16, 0) == 5  # SJ_ERR_TOO_LARGE before touching memory
