@@ -48,6 +48,24 @@ def make_batch(nbytes):
     return buf
 
 
+def host_threads():
+    """threads for the CPU arm: the logical CPUs this process may use, capped by a cgroup quota"""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    quota = ""
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            q, period = f.read().split()
+        quota = "cpu.max=%s/%s" % (q, period)
+        if q != "max":
+            n = max(1, min(n, -(-int(q) // int(period))))
+    except Exception:
+        pass
+    return n, quota
+
+
 def read_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -139,7 +157,7 @@ def run_reference(args, rank, world):
     """--impl reference: the CPU implementation of the path on the box's host cores."""
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads, quota = host_threads()
     sample = make_batch(max(args.batch_mib, 1024) << 20)  # >= 100 chunks of 10 MiB so every host thread has work
     warm = sample[: 64 << 20]
     warm = warm[: warm.rfind(b"\n")]
@@ -161,7 +179,7 @@ def run_reference(args, rank, world):
         "config": {"workload": "synthetic NDJSON stream (parking-citations-shaped records), ParseNDStream-style 10 MiB chunks",
                    "batch_bytes": len(sample)},
         "cpu_baseline": {"value": round(gbs, 4), "unit": "GB/s", "cores": threads, "kind": "port",
-                         "sample": "%d MiB per step, oracle port (C restatement, AVX2+PCLMUL stage 1; the Go reference cannot be built: no Go toolchain)" % (len(sample) >> 20)},
+                         "sample": "%d MiB per step, oracle port (C restatement, AVX2+PCLMUL stage 1; the Go reference cannot be built: no Go toolchain) %s" % (len(sample) >> 20, quota)},
         "e2e": {"value": round(gbs, 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -329,7 +347,7 @@ def main():
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same stream ----
     cpu = None
     if rank == 0 and world == 1:
-        threads = os.cpu_count() or 1
+        threads, quota = host_threads()
         sample = batch
         while len(sample) < (args.cpu_sample_mib << 20):
             sample = sample + b"\n" + batch
@@ -346,7 +364,7 @@ def main():
             nb += n2
             reps += 1
         cpu = {"value": round(nb / secs / 1e9, 4), "unit": "GB/s", "cores": threads, "kind": "port",
-               "sample": "%d x %d MiB of the same NDJSON stream, 10 MiB chunks on all host threads (oracle port; the Go reference cannot be built here)" % (reps, len(sample) >> 20)}
+               "sample": "%d x %d MiB of the same NDJSON stream, 10 MiB chunks on all host threads (oracle port; the Go reference cannot be built here) %s" % (reps, len(sample) >> 20, quota)}
 
     if rank == 0:
         total_bytes = n * world * args.steps

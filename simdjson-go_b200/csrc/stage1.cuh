@@ -41,7 +41,13 @@ constexpr int S1_STEP_BYTES = 32 * 64;
 constexpr int S1_SLAB_BYTES = S1_STEPS * S1_STEP_BYTES;  // 8 KiB per warp
 constexpr int S1_TILE_BYTES = S1_WARPS * S1_SLAB_BYTES;  // one look-back per tile
 constexpr int S1_BUFS = 2;
-constexpr size_t S1_SMEM_BYTES = (size_t)S1_BUFS * S1_TILE_BYTES + 64;
+#ifdef SJ_CLASSIFY_LUT
+constexpr int S1_LUT_COPIES = 8;                         // table copies (lane & 7) to thin out bank conflicts
+constexpr size_t S1_LUT_BYTES = 2 * 256 * S1_LUT_COPIES * 4;  // two class tables
+#else
+constexpr size_t S1_LUT_BYTES = 0;
+#endif
+constexpr size_t S1_SMEM_BYTES = (size_t)S1_BUFS * S1_TILE_BYTES + 64 + S1_LUT_BYTES;
 
 struct Stage1Result {
     uint32_t n_idx;           // total structurals found
@@ -462,6 +468,65 @@ __device__ __forceinline__ uint32_t backslash_run_before(const uint8_t* __restri
     }
 }
 
+#ifdef SJ_CLASSIFY_LUT
+// ---------------------------------------------------------------------------------
+// Table-driven classification.  The SWAR compares keep the ALU pipe busy; a 256-entry class
+// table in shared memory moves the work to the load/store unit and the FMA pipe (IMAD):
+//   entry(b) = one flag per BYTE LANE (bit 0, 8, 16, 24) for four classes;
+//   acc = acc * 2 + entry(b)  over 8 consecutive input bytes leaves, in every byte lane, the
+//   8 flags of one class -- ready-made mask bytes that PRMT assembles into 64-bit masks.
+// table 1: {quote, structural, whitespace, rare = backslash or control}    (always)
+// table 2: {backslash, control (< 0x20), newline, -}                        (only if a step has a rare byte)
+// Each table exists in 8 copies indexed by (lane & 7): [byte][copy] -> bank 8*(byte%4)+copy.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t lut1_entry(uint32_t b) {
+    uint32_t e = 0;
+    if (b == '"') e |= 1u;
+    if (b == '{' || b == '}' || b == '[' || b == ']' || b == ':' || b == ',') e |= 1u << 8;
+    if (b == 0x20 || b == 0x09 || b == 0x0a || b == 0x0d) e |= 1u << 16;
+    if (b == '\\' || b < 0x20) e |= 1u << 24;
+    return e;
+}
+__device__ __forceinline__ uint32_t lut2_entry(uint32_t b) {
+    uint32_t e = 0;
+    if (b == '\\') e |= 1u;
+    if (b < 0x20) e |= 1u << 8;
+    if (b == 0x0a) e |= 1u << 16;
+    return e;
+}
+__device__ __forceinline__ void lut_init(uint32_t* lut) {  // all threads of the CTA
+    for (uint32_t i = threadIdx.x; i < 256 * S1_LUT_COPIES; i += blockDim.x) {
+        uint32_t b = i / S1_LUT_COPIES;
+        lut[i] = lut1_entry(b);
+        lut[256 * S1_LUT_COPIES + i] = lut2_entry(b);
+    }
+}
+// flags of the 8 bytes (w0 = bytes 0..3, w1 = bytes 4..7): bit i of every byte lane <-> byte i
+__device__ __forceinline__ uint32_t lut_group(const uint32_t* t, uint32_t w0, uint32_t w1) {
+    uint32_t acc = t[__byte_perm(w1, 0, 0x4443) * S1_LUT_COPIES];
+    acc = acc * 2 + t[__byte_perm(w1, 0, 0x4442) * S1_LUT_COPIES];
+    acc = acc * 2 + t[__byte_perm(w1, 0, 0x4441) * S1_LUT_COPIES];
+    acc = acc * 2 + t[__byte_perm(w1, 0, 0x4440) * S1_LUT_COPIES];
+    acc = acc * 2 + t[__byte_perm(w0, 0, 0x4443) * S1_LUT_COPIES];
+    acc = acc * 2 + t[__byte_perm(w0, 0, 0x4442) * S1_LUT_COPIES];
+    acc = acc * 2 + t[__byte_perm(w0, 0, 0x4441) * S1_LUT_COPIES];
+    acc = acc * 2 + t[__byte_perm(w0, 0, 0x4440) * S1_LUT_COPIES];
+    return acc;
+}
+// byte lane c of A[0..7] -> 64-bit mask (A[g] covers bytes 8g..8g+7 of the block)
+template <int C>
+__device__ __forceinline__ uint64_t lut_mask(const uint32_t (&A)[8]) {
+    constexpr uint32_t sel = C | ((4 + C) << 4);  // byte C of the first, byte C of the second operand
+    uint32_t t01 = __byte_perm(A[0], A[1], sel), t23 = __byte_perm(A[2], A[3], sel);
+    uint32_t t45 = __byte_perm(A[4], A[5], sel), t67 = __byte_perm(A[6], A[7], sel);
+    return mk64(__byte_perm(t01, t23, 0x5410), __byte_perm(t45, t67, 0x5410));
+}
+__device__ __forceinline__ void lut_classify(const uint32_t* t, const uint32_t (&w)[16], uint32_t (&A)[8]) {
+#pragma unroll
+    for (int g = 0; g < 8; g++) A[g] = lut_group(t, w[2 * g], w[2 * g + 1]);
+}
+#endif  // SJ_CLASSIFY_LUT
+
 #ifdef SJ_PROFILE_PHASES
 // development aid: per-phase cycle totals (lane 0 of every warp), summed into prof[0..7]
 #define SJ_PROF_DECL unsigned long long prof_t0 = clock64(), prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -540,6 +605,12 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S1_BUFS * S1_TILE_BYTES);
     const uint64_t len16 = (p.len + 15) & ~15ull;
     const int G = (int)gridDim.x;
+#ifdef SJ_CLASSIFY_LUT
+    uint32_t* lut = reinterpret_cast<uint32_t*>(smem + (size_t)S1_BUFS * S1_TILE_BYTES + 64);
+    lut_init(lut);  // visible after the __syncthreads below
+    const uint32_t* lut1 = lut + (lane & (S1_LUT_COPIES - 1));
+    const uint32_t* lut2 = lut1 + 256 * S1_LUT_COPIES;
+#endif
 
     // Tiles are dealt round-robin to the CTAs of a COOPERATIVE launch (all CTAs co-resident), so
     // every predecessor a look-back waits for is owned by a running CTA; thread 0 issues one TMA
@@ -603,27 +674,62 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
 #pragma unroll
         for (int s = 0; s < S1_STEPS; s++) qb[s] = st[s] = ws[s] = ct[s] = nl[s] = 0;
         if (active) {
+            // pass 1: pure per-lane classification of all steps -- no warp-synchronous operation in
+            // this loop, so the compiler is free to overlap the steps' instruction streams
+            uint64_t bsm[S1_STEPS];
+            uint32_t anyct_l[S1_STEPS];
 #pragma unroll
             for (int s = 0; s < S1_STEPS; s++) {
                 uint32_t w[16];
                 load_block_words(buf + s * S1_STEP_BYTES, lane, w);
                 const uint64_t blockpos = slab_start + (uint64_t)s * S1_STEP_BYTES + 64 * lane;
                 mask_tail(w, lane, blockpos, p.len);
-                BlockMasks m = classify_block(w);
                 const uint32_t r = (lane >> 1) & 3;
-                uint64_t bs = rotl16x(m.bs, r), qt = rotl16x(m.qt, r);
+#ifdef SJ_CLASSIFY_LUT
+                uint32_t A[8];
+                lut_classify(lut1, w, A);
+                qb[s] = rotl16x(lut_mask<0>(A), r);  // raw quotes; escaped ones are removed in pass 2
+                st[s] = rotl16x(lut_mask<1>(A), r);
+                ws[s] = rotl16x(lut_mask<2>(A), r);
+                const uint64_t rare = lut_mask<3>(A);
+                anyct_l[s] = ((uint32_t)rare | (uint32_t)(rare >> 32)) != 0;
+                bsm[s] = 0;
+#else
+                BlockMasks m = classify_block(w);
+                bsm[s] = rotl16x(m.bs, r);
+                qb[s] = rotl16x(m.qt, r);  // raw quotes; escaped ones are removed in pass 2
                 st[s] = rotl16x(m.st, r);
                 ws[s] = rotl16x(m.sp, r);
-                if (__any_sync(FULL, m.anyct != 0)) {  // warp-uniform: tab / LF / CR / other control characters
+                anyct_l[s] = m.anyct;
+#endif
+            }
+            // pass 2: everything that needs votes across the warp
+#pragma unroll
+            for (int s = 0; s < S1_STEPS; s++) {
+                if (__any_sync(FULL, anyct_l[s] != 0)) {  // warp-uniform: backslash / tab / LF / CR / control bytes
+                    uint32_t w[16];
+                    load_block_words(buf + s * S1_STEP_BYTES, lane, w);
+                    const uint64_t blockpos = slab_start + (uint64_t)s * S1_STEP_BYTES + 64 * lane;
+                    mask_tail(w, lane, blockpos, p.len);
+                    const uint32_t r = (lane >> 1) & 3;
+#ifdef SJ_CLASSIFY_LUT
+                    uint32_t A[8];
+                    lut_classify(lut2, w, A);
+                    bsm[s] = rotl16x(lut_mask<0>(A), r);
+                    ct[s] = rotl16x(lut_mask<1>(A), r);
+                    if (NDJSON) nl[s] = rotl16x(lut_mask<2>(A), r);
+#else
                     SlowMasks sm = classify_block_slow(w);
                     ws[s] |= rotl16x(sm.wsc, r);
                     ct[s] = rotl16x(sm.ct, r);
                     if (NDJSON) nl[s] = rotl16x(sm.nl, r);
+#endif
                 }
-
+                const uint64_t bs = bsm[s];
                 // odd-backslash carry into each lane's block (warp-uniform fast path: no backslashes at all)
                 uint64_t odd_ends = 0;
-                if (__any_sync(FULL, bs != 0) || bs_carry) {
+                const uint32_t hasbs = __ballot_sync(FULL, bs != 0);
+                if (hasbs || bs_carry) {
                     uint32_t allbs = bs == ~0ull;
                     uint32_t trail_odd = (bs == ~0ull) ? 0 : (__clzll(~bs) & 1);
                     uint32_t A = __ballot_sync(FULL, allbs);
@@ -634,13 +740,10 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
                     bs_carry = nonpass ? (F >> (31 - __clz(nonpass))) & 1 : bs_carry;
                     odd_ends = odd_backslash_ends(bs, cin, nullptr);
                 }
-                qb[s] = qt & ~odd_ends;
+                qb[s] &= ~odd_ends;
                 uint32_t P = __ballot_sync(FULL, (__popcll(qb[s]) & 1) != 0);
                 slab_par ^= __popc(P) & 1;
-                if (p.bsmap) {
-                    uint32_t hasbs = __ballot_sync(FULL, bs != 0);
-                    if (lane == 0) p.bsmap[slab * S1_STEPS + s] = hasbs;
-                }
+                if (p.bsmap && lane == 0) p.bsmap[slab * S1_STEPS + s] = hasbs;
             }
         }
         if (lane == 0) s_par[warp] = slab_par;

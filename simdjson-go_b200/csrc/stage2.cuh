@@ -81,10 +81,12 @@ __device__ __forceinline__ ScanVal sv_shfl(const ScanVal& a, int src) {
 }
 
 // block-wide exclusive scan (blockDim.x = NT, a multiple of 32, <= 1024); returns the
-// exclusive prefix of the calling thread and the block total
+// exclusive prefix of the calling thread and the block total.  Warp totals are scanned by the
+// first warp so every thread reads just two entries of shared memory.
 template <int NT>
 __device__ __forceinline__ ScanVal block_exclusive_scan(ScanVal v, ScanVal& total) {
-    __shared__ ScanVal warp_tot[NT / 32];
+    constexpr int NW = NT / 32;
+    __shared__ ScanVal warp_pre[NW + 1];  // [w] = sum of warps < w, [NW] = block total
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     ScanVal inc = v;
 #pragma unroll
@@ -92,19 +94,27 @@ __device__ __forceinline__ ScanVal block_exclusive_scan(ScanVal v, ScanVal& tota
         ScanVal t = sv_shfl_up(inc, d);
         if (lane >= d) inc = sv_add(inc, t);
     }
-    if (lane == 31) warp_tot[warp] = inc;
+    if (lane == 31) warp_pre[warp + 1] = inc;  // provisional: the warp's own total
     __syncthreads();
-    ScanVal wpre = sv_zero(), tot = sv_zero();
+    if (warp == 0) {
+        ScanVal w = lane < NW ? warp_pre[lane + 1] : sv_zero();
 #pragma unroll
-    for (int i = 0; i < NT / 32; i++) {
-        if (i < warp) wpre = sv_add(wpre, warp_tot[i]);
-        tot = sv_add(tot, warp_tot[i]);
+        for (int d = 1; d < NW; d <<= 1) {
+            ScanVal t = sv_shfl_up(w, d);
+            if (lane >= d) w = sv_add(w, t);
+        }
+        __syncwarp();
+        if (lane < NW) warp_pre[lane + 1] = w;  // inclusive: sum of warps <= lane
+        if (lane == 0) warp_pre[0] = sv_zero();
     }
     __syncthreads();
-    total = tot;
+    total = warp_pre[NW];
+    ScanVal wpre = warp_pre[warp];
     ScanVal exc = sv_shfl_up(inc, 1);
     if (lane == 0) exc = sv_zero();
-    return sv_add(wpre, exc);
+    ScanVal r = sv_add(wpre, exc);
+    __syncthreads();  // the shared array may be reused by the next call
+    return r;
 }
 
 struct Stage2Result {
@@ -495,6 +505,10 @@ __global__ void __launch_bounds__(S2_THREADS) s2_emit_kernel(const Stage2Params 
                     if (aux & AUX_ESC) {
                         StrCursor s{p.msg + pos + 1, p.len - pos - 1};
                         string_copy(s, p.strings + e.str);
+                    } else if (dl <= 12) {  // short: cheaper than a slot in the cooperative copy
+                        const uint8_t* src = p.msg + pos + 1;
+                        uint8_t* dst = p.strings + e.str;
+                        for (uint32_t q = 0; q < dl; q++) dst[q] = src[q];
                     } else {
                         fast_len = dl;
                     }
