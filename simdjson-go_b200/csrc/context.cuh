@@ -46,11 +46,11 @@ struct sj_ctx {
     // stage 1
     DevBuf msg;      // device copy of the (trimmed) message, padded
     DevBuf idx;      // structural positions (uint32)
-    DevBuf desc;     // look-back descriptors (3 x nslabs x u64)
+    DevBuf desc;     // K1 look-back descriptors (17 bytes per tile)
     DevBuf result;   // Stage1Result + Stage2Result
     void* host_result = nullptr;  // pinned mirror
     // stage 2
-    DevBuf s2a, s2b, s2c, s2d, s2e, s2f, s2g;
+    DevBuf s2a, s2b, s2c, s2d, s2e, s2f, s2g;  // s2a/s2b: stage-2 scratch (before / after the totals are known), s2c: backslash block map
     DevBuf tape, strings;  // device outputs for the host-buffer API
     DevBuf test_in, test_out, test_aux;
 };

@@ -55,9 +55,7 @@ struct Stage1Result {
     uint32_t ends_in_string;  // message ends inside an unterminated string
     uint32_t last_pos;        // position of the last structural (valid if n_idx > 0)
     uint32_t overflow;        // index buffer too small (n_idx is still exact)
-    uint32_t ticket;          // next unclaimed slab (dynamic assignment keeps the look-back deadlock-free
-                              // even when not every CTA of the grid is resident)
-    uint32_t pad[2];
+    uint32_t pad[3];
 };
 
 // ---------------------------------------------------------------------------------

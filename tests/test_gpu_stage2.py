@@ -262,3 +262,28 @@ def test_too_large_and_empty(ctx):
     rc = ctx.L.sj_parse(ctx.h, None, 0, 0, None, 0, C.byref(tl), None, 0, C.byref(sl), C.byref(mo), C.byref(ml))
     assert rc == 1  # empty input: stage-1 failure, like the reference
     assert ctx.L.sj_stage1_launch(ctx.h, 16, (1 << 31) + 5, 0, 0, 16, 0) == 5  # SJ_ERR_TOO_LARGE before touching memory
+
+
+def test_parse_nd_stream(oracle_native):
+    """ParseNDStream (simdjson_amd64.go:116): newline-aligned chunks, several in flight, results in
+    input order, each an independent ParsedJson; ndjson_test.go:250 countWhere(Make == HOND) = 116 per copy"""
+    import io
+    from simdjson_b200.stream import ParseNDStream
+    pk = load_fixture("parking-citations").strip()
+    copies = 7
+    stream = b"\n".join([pk] * copies) + b"\n"
+    hond = roots = 0
+    pos = 0
+    for pj in ParseNDStream(io.BytesIO(stream), chunk_bytes=300_000, inflight=3):
+        # the chunk this result came from is the next newline-aligned window of the stream
+        chunk_len = len(pj.Message)
+        start = stream.index(pj.Message[:64], pos)
+        rc, tape, strs, _ = oracle_native.parse(stream[start:start + chunk_len], ndjson=True)
+        assert rc == 0 and np.array_equal(pj.Tape, tape) and pj.Strings == strs
+        pos = start + chunk_len
+        it = pj.Iter()
+        hond += it.count_where("Make", "HOND")
+        roots += sum(1 for _ in it.roots())
+    assert roots == 1000 * copies and hond == 116 * copies
+    with pytest.raises(Exception):
+        list(ParseNDStream(io.BytesIO(b'{"a":1}\n{"b":\n'), chunk_bytes=1 << 20))

@@ -60,6 +60,20 @@ def test_two_rank_sharded_parse_equals_whole(tmp_path, oracle_native, copy):
     assert gstr == strings
 
 
+def test_stream_chunker_is_newline_aligned():
+    """host logic of ParseNDStream (simdjson_amd64.go:157-174): chunks end at a record boundary"""
+    import io
+    sys.path.insert(0, os.path.join(ROOT, "simdjson-go_b200"))
+    from simdjson_b200.stream import _chunks
+    recs = [b'{"i":%d,"pad":"%s"}' % (i, b"x" * (i % 97)) for i in range(5000)]
+    stream = b"\n".join(recs)
+    for size in (100, 1000, 4096, 1 << 20):
+        parts = list(_chunks(io.BytesIO(stream), size))
+        assert b"".join(parts) == stream
+        assert all(p.endswith(b"\n") for p in parts[:-1])
+    assert list(_chunks(io.BytesIO(b""), 10)) == []
+
+
 def test_split_at_newlines_covers_and_aligns():
     sys.path.insert(0, os.path.join(ROOT, "simdjson-go_b200"))
     from simdjson_b200.parallel import split_at_newlines
