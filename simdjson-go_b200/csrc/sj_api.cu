@@ -25,8 +25,7 @@ __global__ void test_block_masks_kernel(const uint8_t* blocks, size_t nblocks, c
     const uint32_t* src = reinterpret_cast<const uint32_t*>(blocks + 64 * i);
 #pragma unroll
     for (int k = 0; k < 16; k++) w[k] = src[k];
-    BlockMasks m = classify_block(w);
-    SlowMasks sm = classify_block_slow(w);
+    PlaneMasks m = classify_block_planes(w);
     uint32_t prev_odd = (uint32_t)carry_in[4 * i + 0];
     uint64_t prev_inside = carry_in[4 * i + 1];
     uint32_t prev_pseudo = (uint32_t)carry_in[4 * i + 2];
@@ -35,12 +34,20 @@ __global__ void test_block_masks_kernel(const uint8_t* blocks, size_t nblocks, c
     uint64_t odd_ends = odd_backslash_ends(m.bs, prev_odd, &odd_carry);
     uint64_t qb = m.qt & ~odd_ends;
     uint64_t qm = prefix_xor64(qb) ^ prev_inside;
-    uint64_t err = sm.ct & qm;
-    uint64_t ws = m.sp | sm.wsc;
+    uint64_t err = m.ct & qm;
+    uint64_t ws = m.ws;
     uint32_t pp_out;
     uint64_t fin = finalize_structurals(m.st, ws, qm, qb, prev_pseudo, &pp_out);
-    uint64_t nl = sm.nl;  // raw newline mask; the fused result applies & ~quote_mask
+    uint64_t nl = m.nl;  // raw newline mask; the fused result applies & ~quote_mask
     if (ndjson) fin |= nl & ~qm;
+    // cross-check: the word-wise SWAR classifier must agree with the bit-sliced one
+    {
+        BlockMasks f = classify_block(w);
+        SlowMasks sl = classify_block_slow(w);
+        if (f.bs != m.bs || f.qt != m.qt || f.st != m.st || (f.sp | sl.wsc) != m.ws || sl.ct != m.ct || sl.nl != m.nl ||
+            ((f.anyct != 0) != (m.ct != 0)))
+            err = ~0ull;
+    }
     uint64_t* o = out + 12 * i;
     o[0] = odd_ends;
     o[1] = qm;
@@ -53,7 +60,7 @@ __global__ void test_block_masks_kernel(const uint8_t* blocks, size_t nblocks, c
     o[8] = odd_carry;
     o[9] = (uint64_t)((int64_t)qm >> 63);
     o[10] = pp_out;
-    o[11] = m.anyct;
+    o[11] = m.ct != 0;
 }
 
 __global__ void test_finalize_kernel(const uint64_t* in, size_t n, uint64_t* out) {
