@@ -416,4 +416,9 @@ extern "C" int sj_debug_read_prof(sj_ctx* c, unsigned long long* out, int clear)
     if (clear) SJ_CUDA_CHECK(cudaMemset(d, 0, 128));
     return SJ_OK;
 }
+extern "C" int sj_debug_read_timeline(sj_ctx* c, unsigned long long* out) {
+    SJ_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    SJ_CUDA_CHECK(cudaMemcpyFromSymbol(out, sj::g_timeline, sizeof(unsigned long long) * 8 * 256 * 4));
+    return SJ_OK;
+}
 #endif

@@ -4,41 +4,49 @@
 // Replaces, per 64-byte block:
 //   find_odd_backslash_sequences     find_odd_backslash_sequences_amd64.s:24-61
 //   find_quote_mask_and_bits         find_quote_mask_and_bits_amd64.s:49-84   (CLMUL -> shift/xor prefix + warp ballot parity)
-//   find_whitespace_and_structurals  find_whitespace_and_structurals_amd64.s:62-103 (VPSHUFB LUTs -> SWAR compares)
+//   find_whitespace_and_structurals  find_whitespace_and_structurals_amd64.s:62-103 (VPSHUFB LUTs -> bit planes)
 //   finalize_structurals             finalize_structurals_amd64.s:19-36
 //   find_newline_delimiters          find_newline_delimiters_amd64.s:16-28    (NDJSON)
 //   flatten_bits_incremental         flatten_bits_amd64.s:26-60               (serial tzcnt -> popcount + warp scan compaction)
 // and the driver loop of stage1_find_marks_amd64.go:41-148.
 //
-// Shape: persistent grid (1 CTA per SM), S1_WARPS warps per CTA, each warp owns one
-// 8 KiB slab at a time (round-robin over the message).  A slab is staged HBM -> shared
-// memory by one 1-D TMA bulk copy per warp into a per-warp double buffer (the next slab
-// streams in while the current one is processed); lane L of the warp owns the 64-byte
-// block L of each of the slab's four 2 KiB steps and reads it with four conflict-free
-// 16-byte LDS.  Carries across blocks use ballots inside a warp; carries across slabs use
-// two decoupled look-back chains (in-string parity, then structural count / last
-// position); the odd-backslash and pseudo-predecessor carries are recovered from the 32
-// bytes in front of the slab.
+// Shape: persistent cooperative grid (1 CTA per SM).  A CTA is S1_WARPS worker warps plus one
+// scan warp and works on one 96 KiB TILE at a time (tiles are dealt round-robin to the CTAs);
+// the tile is staged HBM -> shared memory by one 1-D TMA bulk copy into a double buffer (the
+// next tile streams in while the current one is processed).  Each worker warp owns one 6 KiB
+// slab of the tile; lane L owns the 64-byte block L of each of the slab's 2 KiB steps and reads
+// it with four conflict-free 16-byte LDS.  Carries across blocks use ballots inside a warp;
+// carries across slabs go through shared memory; carries across tiles use two decoupled
+// look-back chains (in-string parity, then structural count) that the scan warp runs while the
+// workers classify / flatten, so a look-back never stalls them; the odd-backslash and
+// pseudo-predecessor carries are recovered from the 32 bytes in front of the slab (prefetched
+// one tile ahead).  The 64-byte masks come from a bit-sliced classifier (byte transpose + bit
+// planes + Boolean class functions) instead of per-byte compares.
 #pragma once
 #include "common.cuh"
 
 namespace sj {
 
 #ifndef SJ_S1_WARPS
-#define SJ_S1_WARPS 12
+#define SJ_S1_WARPS 16
+#endif
+// Pause between two polls of a look-back (ns).  148 scan warps polling back to back slow the
+// publishers down (measured: 1.17 ms per GiB without a pause, 0.77 ms with 0.4-1.5 us).
+#ifndef SJ_SPIN_SLEEP
+#define SJ_SPIN_SLEEP 1000
 #endif
 #ifndef SJ_S1_CTAS_PER_SM
 #define SJ_S1_CTAS_PER_SM 1
 #endif
 constexpr int S1_WARPS = SJ_S1_WARPS;            // warps per CTA = slabs per tile
 constexpr int S1_CTAS_PER_SM = SJ_S1_CTAS_PER_SM;
-constexpr int S1_THREADS = S1_WARPS * 32;
+constexpr int S1_THREADS = (S1_WARPS + 1) * 32;  // worker warps + one scan warp (the look-backs)
 #ifndef SJ_S1_STEPS
-#define SJ_S1_STEPS 4
+#define SJ_S1_STEPS 3
 #endif
 constexpr int S1_STEPS = SJ_S1_STEPS;            // 2 KiB steps per slab
 constexpr int S1_STEP_BYTES = 32 * 64;
-constexpr int S1_SLAB_BYTES = S1_STEPS * S1_STEP_BYTES;  // 8 KiB per warp
+constexpr int S1_SLAB_BYTES = S1_STEPS * S1_STEP_BYTES;  // 6 KiB per warp
 constexpr int S1_TILE_BYTES = S1_WARPS * S1_SLAB_BYTES;  // one look-back per tile
 constexpr int S1_BUFS = 2;
 #ifdef SJ_CLASSIFY_LUT
@@ -339,6 +347,16 @@ __device__ __forceinline__ uint64_t finalize_structurals(uint64_t st, uint64_t w
 // ---------------------------------------------------------------------------------
 // `stage` (optional): stage_cap x uint32 of shared memory private to the warp; the lanes drop their
 // entries there and the warp then streams them out with fully coalesced 128-byte stores.
+#ifndef SJ_FLATTEN_UNROLL
+#define SJ_FLATTEN_UNROLL 2
+#endif
+// st.shared.u32 [addr], val  predicated on cond != 0
+__device__ __forceinline__ void sts_if(uint32_t addr, uint32_t val, uint32_t cond) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.u32 [%0], %1;\n\t}" ::"r"(addr), "r"(val), "r"(cond)
+        : "memory");
+}
+
 template <bool DELTAS>
 __device__ __forceinline__ uint32_t flatten_step(uint64_t S, uint32_t blockpos, uint32_t* __restrict__ out,
                                                  uint64_t base, uint64_t cap, uint32_t& prev_last, uint32_t& overflow,
@@ -371,6 +389,37 @@ __device__ __forceinline__ uint32_t flatten_step(uint64_t S, uint32_t blockpos, 
     }
     uint32_t pos0 = blockpos;
     if (stage && total <= stage_cap) {  // warp-uniform
+#ifndef SJ_FLATTEN_SERIAL
+        // the two 32-bit halves are extracted side by side (two independent dependency chains,
+        // half the trip count of the divergent loop); bit-reversed so that one FLO finds the
+        // next position
+        uint32_t alo = (uint32_t)__cvta_generic_to_shared(stage + (inc - c));
+        uint32_t ahi = alo + 4 * __popc(lo);
+        uint32_t prev_hi = lo ? pos0 + 31 - __clz(lo) : prev;
+        const uint32_t pos1 = pos0 + 32;
+        // branch-free body: an exhausted half keeps running on a zero mask with its store
+        // predicated off (inline PTX: the compiler would branch around the four instructions)
+        // (an exhausted half never uses its cursor again, so the cursors advance unconditionally)
+        while (lo | hi) {
+#pragma unroll
+            for (int u = 0; u < SJ_FLATTEN_UNROLL; u++) {
+                {
+                    const uint32_t p = pos0 + (__ffs(lo) - 1);
+                    sts_if(alo + 4 * u, DELTAS ? p - prev : p, lo);
+                    prev = p;
+                    lo &= lo - 1;
+                }
+                {
+                    const uint32_t p = pos1 + (__ffs(hi) - 1);
+                    sts_if(ahi + 4 * u, DELTAS ? p - prev_hi : p, hi);
+                    prev_hi = p;
+                    hi &= hi - 1;
+                }
+            }
+            alo += 4 * SJ_FLATTEN_UNROLL;
+            ahi += 4 * SJ_FLATTEN_UNROLL;
+        }
+#else
         uint32_t so = inc - c;
         while (lo) {
             uint32_t b = __ffs(lo) - 1;
@@ -387,6 +436,7 @@ __device__ __forceinline__ uint32_t flatten_step(uint64_t S, uint32_t blockpos, 
             stage[so++] = DELTAS ? p - prev : p;
             prev = p;
         }
+#endif
         __syncwarp();
         for (uint32_t k = lane; k < total; k += 32) out[base + k] = stage[k];
         __syncwarp();
@@ -451,19 +501,20 @@ __device__ __forceinline__ uint32_t gather_bit16(const uint4& q, int k) {
 __device__ __forceinline__ uint32_t lookback_parity(const uint8_t* dpar, int slab, unsigned long long* prof = nullptr) {
     const int lane = threadIdx.x & 31;
     uint32_t par = 0;
+#ifdef SJ_PROFILE_PHASES
+    unsigned long long nspin = 0, nround = 0;
+#endif
     for (int g = slab >> 4;; g -= 32) {  // lane L inspects the 16-slab group g - L
         const int grp = g - lane;
         uint32_t V, I, P;
 #ifdef SJ_PROFILE_PHASES
-        if (prof && lane == 0) atomicAdd(prof + 10, 1ull);
+        nround++;
 #endif
         do {
 #ifdef SJ_PROFILE_PHASES
-            if (prof && lane == 0) atomicAdd(prof + 9, 1ull);
+            nspin++;
 #endif
-#ifdef SJ_SPIN_SLEEP
-            __nanosleep(SJ_SPIN_SLEEP);
-#endif
+            if (SJ_SPIN_SLEEP) __nanosleep(SJ_SPIN_SLEEP);
             if (grp >= 0) {
                 uint4 q = ld_relaxed_v4(dpar + (size_t)grp * 16);
                 V = gather_bit16(q, 0);
@@ -489,6 +540,9 @@ __device__ __forceinline__ uint32_t lookback_parity(const uint8_t* dpar, int sla
         else if (lane == f)
             contrib = __popc(P >> (31 - __clz(I))) & 1;  // the inclusive slab and every slab after it
         par ^= __popc(__ballot_sync(FULL, contrib)) & 1;
+#ifdef SJ_PROFILE_PHASES
+        if (has && prof && lane == 0) atomicAdd(prof + 9, nspin), atomicAdd(prof + 10, nround);
+#endif
         if (has) return par;
     }
 }
@@ -498,20 +552,21 @@ __device__ __forceinline__ uint64_t lookback_count(const uint32_t* dagg, const u
                                                unsigned long long* prof = nullptr) {
     const int lane = threadIdx.x & 31;
     uint64_t total = 0;
+#ifdef SJ_PROFILE_PHASES
+    unsigned long long nspin = 0, nround = 0;
+#endif
     for (int g = tile >> 2;; g -= 32) {  // lane L inspects the 4-tile group g - L
         const int grp = g - lane;
         uint32_t sum = 0, valid = 1;
         uint64_t inc = 0;
 #ifdef SJ_PROFILE_PHASES
-        if (prof && lane == 0) atomicAdd(prof + 13, 1ull);
+        nround++;
 #endif
         do {
 #ifdef SJ_PROFILE_PHASES
-            if (prof && lane == 0) atomicAdd(prof + 12, 1ull);
+            nspin++;
 #endif
-#ifdef SJ_SPIN_SLEEP
-            __nanosleep(SJ_SPIN_SLEEP);
-#endif
+            if (SJ_SPIN_SLEEP) __nanosleep(SJ_SPIN_SLEEP);
             if (grp >= 0) {
                 uint4 q = ld_relaxed_v4(dagg + (size_t)grp * 4);
                 inc = grp > 0 ? ld_relaxed_u64(dinc + (size_t)grp * 4 - 1) : DI_VALID;
@@ -537,6 +592,9 @@ __device__ __forceinline__ uint64_t lookback_count(const uint32_t* dagg, const u
         for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
         total += v;
         if (has) {
+#ifdef SJ_PROFILE_PHASES
+            if (prof && lane == 0) atomicAdd(prof + 12, nspin), atomicAdd(prof + 13, nround);
+#endif
             uint64_t pre = __shfl_sync(FULL, inc, f) & ~DI_VALID;
             return total + pre;
         }
@@ -637,6 +695,29 @@ __device__ __forceinline__ void lut_classify(const uint32_t* t, const uint32_t (
 #define SJ_PROF_FLUSH
 #endif
 
+#ifdef SJ_PROFILE_PHASES
+// timeline of the scan warp of 8 CTAs (globaltimer ns): [cta][iteration][event]
+// events: 0 = chain 2 done, 1 = barrier (1) passed, 2 = chain 1 done, 3 = barrier (3) passed
+__device__ unsigned long long g_timeline[8][256][4];
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ int timeline_slot() {
+    const int c = blockIdx.x, G = gridDim.x;
+    if (c < 3) return c;
+    if (c == G / 2 - 1) return 3;
+    if (c == G / 2) return 4;
+    if (c >= G - 3) return 5 + (c - (G - 3));
+    return -1;
+}
+#define SJ_TL(ev)                                                                            \
+    if (lane == 0 && tl_slot >= 0 && tl_it < 256) g_timeline[tl_slot][tl_it][ev] = globaltimer_ns();
+#else
+#define SJ_TL(ev)
+#endif
+
 struct Stage1Params {
     const uint8_t* msg;  // 16-byte aligned, readable up to round_up(len, 16)
     uint64_t len;
@@ -717,17 +798,105 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
     };
 
     int tile = blockIdx.x;
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == S1_WARPS * 32) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
         mbar_fence_init();
         issue(tile, 0);
     }
     __syncthreads();
+    int b = 0;
+
+    // ---------------------------------------------------------------------------------------
+    // Scan warp: owns both decoupled look-backs and the TMA issue, so that neither chain ever
+    // stalls the worker warps.  Per iteration (tile T_i, previous tile T_(i-1) of this CTA):
+    //   while the workers classify T_i     : chain 2 (output offset) of T_(i-1)  -> s_base
+    //   barrier (1)
+    //   while the workers flatten T_(i-1)  : chain 1 (quote parity) of T_i       -> s_parin
+    //   barrier (2), barrier (3)
+    //   publish T_i's structural count (chain-2 aggregate)
+    // ---------------------------------------------------------------------------------------
+    if (warp == S1_WARPS) {
+        bool have_prev = false;
+        int prev_tile = 0;
+        uint32_t prev_tile_count = 0, prev_par_out = 0;
+#ifdef SJ_PROFILE_PHASES
+        const int tl_slot = timeline_slot();
+        int tl_it = -1;
+#endif
+        while (tile < p.ntiles || have_prev) {
+            const bool cur = tile < p.ntiles;  // CTA-uniform
+            uint64_t tb = 0;
+#ifdef SJ_PROFILE_PHASES
+            tl_it++;
+#endif
+            if (have_prev) {  // every tile in front of prev_tile published its count one iteration ago
+#ifdef SJ_PROFILE_PHASES
+                unsigned long long lb_t1 = clock64();
+                if (prev_tile > 0) tb = lookback_count(p.dagg, p.dinc, prev_tile, p.prof);
+                if (lane == 0) atomicAdd(p.prof + 11, clock64() - lb_t1);
+#else
+                if (prev_tile > 0) tb = lookback_count(p.dagg, p.dinc, prev_tile);
+#endif
+                if (lane == 0) {
+                    st_relaxed_u64(p.dinc + prev_tile, DI_VALID | (tb + prev_tile_count));
+                    if (prev_tile == p.ntiles - 1) {
+                        p.result->n_idx = (uint32_t)(tb + prev_tile_count);
+                        p.result->ends_in_string = prev_par_out;
+                    }
+                }
+            }
+            if (lane == 0) s_base = tb;
+            SJ_TL(0)
+            __syncthreads();  // (1)
+            SJ_TL(1)
+            if (lane == 0) issue(tile + G, b ^ 1);
+            uint32_t tile_par = 0;
+#pragma unroll
+            for (int w2 = 0; w2 < S1_WARPS; w2++) tile_par ^= s_par[w2];
+            uint32_t tin = 0;
+            if (cur) {
+                if (lane == 0)
+                    st_relaxed_u8(p.dpar + tile, DP_VALID | (tile == 0 ? DP_INCL : 0) | (tile_par ? DP_PAR : 0));
+                if (tile > 0) {
+#ifdef SJ_PROFILE_PHASES
+                    unsigned long long lb_t0 = clock64();
+                    tin = lookback_parity(p.dpar, tile, p.prof);
+                    if (lane == 0) atomicAdd(p.prof + 8, clock64() - lb_t0), atomicAdd(p.prof + 14, 1ull);
+#else
+                    tin = lookback_parity(p.dpar, tile);
+#endif
+                    if (lane == 0) st_relaxed_u8(p.dpar + tile, DP_VALID | DP_INCL | ((tile_par ^ tin) ? DP_PAR : 0));
+                }
+            }
+            if (lane == 0) s_parin = tin;
+            SJ_TL(2)
+            __syncthreads();  // (2)
+            __syncthreads();  // (3)
+            SJ_TL(3)
+            uint32_t tile_count = 0, tile_last1 = 0;
+#pragma unroll
+            for (int w2 = 0; w2 < S1_WARPS; w2++) {
+                uint32_t l1 = s_last[w2];
+                tile_count += s_cnt[w2];
+                if (l1) tile_last1 = l1;
+            }
+            if (cur && lane == 0) {  // chain-2 aggregate; its look-back runs one iteration later
+                p.lastp1[tile] = tile_last1;
+                st_relaxed_u32(p.dagg + tile, DA_VALID | tile_count);
+            }
+            have_prev = cur;
+            prev_tile = tile;
+            prev_tile_count = tile_count;
+            prev_par_out = tin ^ tile_par;
+            tile += G;
+            b ^= 1;
+        }
+        return;
+    }
 
     SJ_PROF_DECL
     uint32_t phasebits = 0;
-    int b = 0;
 
     // software pipeline: iteration i runs phase A / chain 1 / phase B of tile T_i and the chain-2
     // look-back + flatten of tile T_(i-1); one drain iteration flattens the last tile
@@ -736,7 +905,14 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
 #pragma unroll
     for (int s = 0; s < S1_STEPS; s++) S_prev[s] = 0;
     int prev_tile = 0;
-    uint32_t prev_warp_base = 0, prev_tile_count = 0, prev_in_tile1 = 0, prev_par_out = 0;
+    uint32_t prev_warp_base = 0, prev_in_tile1 = 0;
+
+    // bytes in front of a warp's slab of tile t (0x20 = "nothing there": first slab, or no such slab)
+    auto peek_load = [&](int t) -> uint32_t {
+        const uint64_t ss = ((uint64_t)t * S1_WARPS + warp) * S1_SLAB_BYTES;
+        return (t < p.ntiles && ss < p.len && ss > lane) ? (uint32_t)p.msg[ss - 1 - lane] : 0x20u;
+    };
+    uint32_t peekc = peek_load(tile);
 
     while (tile < p.ntiles || have_prev) {
         const bool cur = tile < p.ntiles;  // CTA-uniform
@@ -746,12 +922,18 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
         const bool active = cur && slab_start < p.len;  // warps past the end of the message only keep the barriers
         const uint8_t* buf = smem + (size_t)b * S1_TILE_BYTES + (size_t)warp * S1_SLAB_BYTES;
 
-        // carries that depend only on raw bytes in front of the slab
-        uint32_t bs_carry = 0, prevc = 0x20, prevc_esc = 0;
-        if (active && slab > 0) {
-            bs_carry = backslash_run_before(p.msg, slab_start) & 1;
-            prevc = p.msg[slab_start - 1];
-            if (prevc == '"') prevc_esc = backslash_run_before(p.msg, slab_start - 1) & 1;  // warp-uniform
+        // carries that depend only on raw bytes in front of the slab: lane L holds byte
+        // slab_start - 1 - L (loaded one iteration ago, under the flatten of the previous tile)
+        uint32_t bs_carry, prevc_esc = 0;
+        const uint32_t peek_bs = __ballot_sync(FULL, peekc == '\\');
+        const uint32_t prevc = __shfl_sync(FULL, peekc, 0);
+        if (peek_bs == FULL)
+            bs_carry = backslash_run_before(p.msg, slab_start) & 1;  // a run of 32 or more: walk it
+        else
+            bs_carry = (__ffs(~peek_bs) - 1) & 1;
+        if (prevc == '"') {  // warp-uniform; is that quote escaped?
+            const uint32_t n = __ffs(~(peek_bs >> 1)) - 1;
+            prevc_esc = n == 31 ? backslash_run_before(p.msg, slab_start - 1) & 1 : n & 1;
         }
         SJ_PROF_MARK(1)
         if (cur) {
@@ -856,56 +1038,13 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
         SJ_PROF_MARK(3)
         __syncthreads();  // (1) slab parities visible; buffer b is dead (nothing re-reads the bytes) and
                           //     buffer b^1 is free (the previous iteration's staging is finished)
-        if (threadIdx.x == 0) issue(tile + G, b ^ 1);
-
-        // ---------------- chains (warp 0): parity of this tile, output offset of the previous one ----------------
-        uint32_t warp_pre = 0, tile_par = 0;
+        // the scan warp issues the TMA of the next tile into b^1 and runs chain 1 of this tile now
+        const uint32_t peek_next = peek_load(tile + G);
+        uint32_t warp_pre = 0;
 #pragma unroll
-        for (int w2 = 0; w2 < S1_WARPS; w2++) {
-            uint32_t v = s_par[w2];
-            tile_par ^= v;
-            if (w2 < (int)warp) warp_pre ^= v;
-        }
-        if (warp == 0) {
-            if (cur && lane == 0)
-                st_relaxed_u8(p.dpar + tile, DP_VALID | (tile == 0 ? DP_INCL : 0) | (tile_par ? DP_PAR : 0));
-            uint64_t tb = 0;
-            if (have_prev) {  // every tile in front of prev_tile published its count one iteration ago
-#ifdef SJ_PROFILE_PHASES
-                unsigned long long lb_t1 = clock64();
-                if (prev_tile > 0) tb = lookback_count(p.dagg, p.dinc, prev_tile, p.prof);
-                if (lane == 0) atomicAdd(p.prof + 11, clock64() - lb_t1);
-#else
-                if (prev_tile > 0) tb = lookback_count(p.dagg, p.dinc, prev_tile);
-#endif
-                if (lane == 0) {
-                    st_relaxed_u64(p.dinc + prev_tile, DI_VALID | (tb + prev_tile_count));
-                    if (prev_tile == p.ntiles - 1) {
-                        p.result->n_idx = (uint32_t)(tb + prev_tile_count);
-                        p.result->ends_in_string = prev_par_out;
-                    }
-                }
-            }
-            uint32_t tin = 0;
-            if (cur && tile > 0) {
-#ifdef SJ_PROFILE_PHASES
-                unsigned long long lb_t0 = clock64();
-                tin = lookback_parity(p.dpar, tile, p.prof);
-                if (lane == 0) atomicAdd(p.prof + 8, clock64() - lb_t0), atomicAdd(p.prof + 14, 1ull);
-#else
-                tin = lookback_parity(p.dpar, tile);
-#endif
-                if (lane == 0) st_relaxed_u8(p.dpar + tile, DP_VALID | DP_INCL | ((tile_par ^ tin) ? DP_PAR : 0));
-            }
-            if (lane == 0) {
-                s_parin = tin;
-                s_base = tb;
-            }
-        }
+        for (int w2 = 0; w2 < S1_WARPS; w2++)
+            if (w2 < (int)warp) warp_pre ^= s_par[w2];
         SJ_PROF_MARK(4)
-        __syncthreads();  // (2)
-        const uint32_t tile_par_in = s_parin;
-        const uint32_t par_in = tile_par_in ^ warp_pre;
 
         // ---------------- flatten of the previous tile ----------------
         if (have_prev) {
@@ -914,7 +1053,7 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
             uint32_t prev_last = prev_in_tile1 - 1;  // 0xffffffff when nothing precedes inside the tile
             uint32_t overflow = 0;
             uint64_t off = s_base + prev_warp_base;
-            // the warp's own 8 KiB slab of buffer b is dead after phase A: reuse it as the staging area
+            // the warp's own slab of buffer b is dead after phase A: reuse it as the staging area
             uint32_t* stage = reinterpret_cast<uint32_t*>(smem + (size_t)b * S1_TILE_BYTES + (size_t)warp * S1_SLAB_BYTES);
             const uint64_t pslab_start = ((uint64_t)prev_tile * S1_WARPS + warp) * S1_SLAB_BYTES;
 #pragma unroll
@@ -926,6 +1065,9 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
             if (overflow && lane == 0) atomicOr(&p.result->overflow, 1u);
         }
         SJ_PROF_MARK(5)
+        __syncthreads();  // (2) quote parity in front of the tile (scan warp, chain 1)
+        const uint32_t par_in = s_parin ^ warp_pre;
+        SJ_PROF_MARK(0)
 
         // pseudo-structural predecessor carry into the slab (finalize_structurals_amd64.s:24-27;
         // initial value 1: stage1_find_marks_amd64.go:54)
@@ -984,27 +1126,20 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
         SJ_PROF_MARK(6)
         __syncthreads();  // (3) slab counts of the tile are visible
 
-        uint32_t warp_base = 0, tile_count = 0, tile_last1 = 0, in_tile1 = 0;
+        uint32_t warp_base = 0, in_tile1 = 0;
 #pragma unroll
         for (int w2 = 0; w2 < S1_WARPS; w2++) {
-            uint32_t cnt = s_cnt[w2], l1 = s_last[w2];
-            tile_count += cnt;
-            if (l1) tile_last1 = l1;
             if (w2 < (int)warp) {
-                warp_base += cnt;
+                uint32_t l1 = s_last[w2];
+                warp_base += s_cnt[w2];
                 if (l1) in_tile1 = l1;
             }
-        }
-        if (cur && threadIdx.x == 0) {  // chain-2 aggregate; its look-back runs one iteration later
-            p.lastp1[tile] = tile_last1;
-            st_relaxed_u32(p.dagg + tile, DA_VALID | tile_count);
         }
         have_prev = cur;
         prev_tile = tile;
         prev_warp_base = warp_base;
-        prev_tile_count = tile_count;
         prev_in_tile1 = in_tile1;
-        prev_par_out = tile_par_in ^ tile_par;
+        peekc = peek_next;
         tile += G;
         b ^= 1;
     }

@@ -68,8 +68,18 @@ for lib in libs:
         if has_prof:
             L.sj_debug_read_prof(h, buf, 1)
             tot = float(sum(buf[:8]))
-            names = ["ticket+issue", "peek", "tma wait", "phaseA", "lookback1", "phaseB", "lookback2", "flatten"]
+            names = ["wait(2)", "peek", "tma wait", "phaseA", "wait(1)", "flatten", "phaseB", "wait(3)+tail"]
             print("   " + "  ".join("%s %.1f%%" % (nm, 100 * v / tot) for nm, v in zip(names, buf)))
+            if hasattr(L, "sj_debug_read_timeline") and deltas == 0:
+                tl = (C.c_ulonglong * (8 * 256 * 4))()
+                L.sj_debug_read_timeline.argtypes = [vp, C.c_void_p]
+                L.sj_debug_read_timeline(h, tl)
+                import numpy as np
+                a = np.ctypeslib.as_array(tl).reshape(8, 256, 4).astype(np.int64)
+                t0 = a[:, 0, 1].min()
+                print("   timeline (us since first barrier(1)); per CTA slot: it: chain2done bar1 chain1done bar3")
+                for it in (0, 1, 2, 10, 11, 30, 31, 60, 61):
+                    print("   it %2d: " % it + " | ".join("%7.1f %7.1f %7.1f %7.1f" % tuple((a[c, it, :] - t0) / 1e3) for c in (0, 1, 3, 4, 6, 7)))
             nt = max(1, buf[14])
             print("   per tile: LB1 %.0f cyc, %.1f spins, %.2f rounds | LB2 %.0f cyc, %.1f spins, %.2f rounds | tiles %d" % (
                 buf[8] / nt, buf[9] / nt, buf[10] / nt, buf[11] / nt, buf[12] / nt, buf[13] / nt, buf[14]))
