@@ -350,6 +350,12 @@ __device__ __forceinline__ uint64_t finalize_structurals(uint64_t st, uint64_t w
 #ifndef SJ_FLATTEN_UNROLL
 #define SJ_FLATTEN_UNROLL 2
 #endif
+// index of the highest set bit (0xffffffff for 0): one FLO
+__device__ __forceinline__ uint32_t bfind(uint32_t x) {
+    uint32_t b;
+    asm("bfind.u32 %0, %1;" : "=r"(b) : "r"(x));
+    return b;
+}
 // st.shared.u32 [addr], val  predicated on cond != 0
 __device__ __forceinline__ void sts_if(uint32_t addr, uint32_t val, uint32_t cond) {
     asm volatile(
@@ -458,6 +464,80 @@ __device__ __forceinline__ uint32_t flatten_step(uint64_t S, uint32_t blockpos, 
         prev = p;
     }
     return total;
+}
+
+// Flatten of a whole slab through the warp's staging area.  Positions are extracted from the top
+// bit down (one FLO per structural, no bit reversal) by two independent chains (the two 32-bit
+// halves of the lane's mask) with predicated stores; the copy-out is coalesced and forms the
+// deltas (flatten_bits_amd64.s:38-40) from neighbouring staged positions, so the divergent
+// extraction loop carries no delta arithmetic at all.
+//   slabpos   = message offset of the slab,  dst = out + (output offset of the slab)
+//   prev_last = position of the last structural in front of the slab (0xffffffff: none yet)
+template <bool DELTAS, int STEPS>
+__device__ __forceinline__ void flatten_slab_staged(const uint64_t (&S)[STEPS], uint32_t slabpos, uint32_t* __restrict__ dst,
+                                                    uint32_t prev_last, uint32_t* stage, uint32_t stage_cap) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(stage);
+    uint32_t so = 0;  // entries staged and not yet copied out (warp-uniform)
+    // coalesced copy-out of the staged positions (as deltas if asked for)
+    auto flush = [&]() {
+        __syncwarp();
+#pragma unroll 4
+        for (uint32_t k = lane; k < so; k += 32) {
+            uint32_t v = stage[k];
+            if (DELTAS) v -= k ? stage[k - 1] : prev_last;
+            dst[k] = v;
+        }
+        if (DELTAS && so) prev_last = stage[so - 1];
+        dst += so;
+        so = 0;
+        __syncwarp();
+    };
+#pragma unroll
+    for (int s = 0; s < STEPS; s++) {
+        uint32_t lo = (uint32_t)S[s], hi = (uint32_t)(S[s] >> 32);
+        const uint32_t ch = __popc(hi);
+        const uint32_t c = __popc(lo) + ch;
+        uint32_t inc = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t t = __shfl_up_sync(FULL, inc, d);
+            if (lane >= d) inc += t;
+        }
+        const uint32_t total = __shfl_sync(FULL, inc, 31);
+        const uint32_t pos0 = slabpos + s * S1_STEP_BYTES + 64 * lane, pos1 = pos0 + 32;
+        if (so + total > stage_cap) {  // warp-uniform; only inputs with > 1 structural per 4 bytes get here
+            flush();
+            if (total > stage_cap) {  // this step alone does not fit: straight to global memory
+                uint32_t overflow = 0;
+                flatten_step<DELTAS>(S[s], pos0, dst, 0, ~0ull, prev_last, overflow);
+                dst += total;
+                continue;
+            }
+        }
+        // cursors on the LAST slot of each half
+        uint32_t ahi = sbase + 4 * (so + inc) - 4;
+        uint32_t alo = ahi - 4 * ch;
+        while (lo | hi) {
+#pragma unroll
+            for (int u = 0; u < SJ_FLATTEN_UNROLL; u++) {
+                {
+                    const uint32_t b = bfind(lo);
+                    sts_if(alo - 4 * u, pos0 + b, lo);
+                    lo &= ~(1u << (b & 31));
+                }
+                {
+                    const uint32_t b = bfind(hi);
+                    sts_if(ahi - 4 * u, pos1 + b, hi);
+                    hi &= ~(1u << (b & 31));
+                }
+            }
+            alo -= 4 * SJ_FLATTEN_UNROLL;
+            ahi -= 4 * SJ_FLATTEN_UNROLL;
+        }
+        so += total;
+    }
+    flush();
 }
 
 // ---------------------------------------------------------------------------------
@@ -771,9 +851,12 @@ __device__ __forceinline__ void mask_tail(uint32_t (&w)[16], uint32_t lane, uint
 template <bool NDJSON, bool DELTAS>
 __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_kernel(const Stage1Params p) {
     extern __shared__ __align__(128) uint8_t smem[];
+    // workers -> scan warp: quote parity, structural count, last structural (+1) of each slab
     __shared__ uint32_t s_par[S1_WARPS], s_cnt[S1_WARPS], s_last[S1_WARPS];
-    __shared__ uint32_t s_parin;
-    __shared__ unsigned long long s_base;
+    // scan warp -> workers: in-string state in front of each slab of the current tile; output
+    // offset and last structural (+1) in front of each slab of the previous tile
+    __shared__ uint32_t s_parin[S1_WARPS], s_wlast[S1_WARPS];
+    __shared__ unsigned long long s_off[S1_WARPS];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S1_BUFS * S1_TILE_BYTES);
     const uint64_t len16 = (p.len + 15) & ~15ull;
@@ -810,7 +893,7 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
     // ---------------------------------------------------------------------------------------
     // Scan warp: owns both decoupled look-backs and the TMA issue, so that neither chain ever
     // stalls the worker warps.  Per iteration (tile T_i, previous tile T_(i-1) of this CTA):
-    //   while the workers classify T_i     : chain 2 (output offset) of T_(i-1)  -> s_base
+    //   while the workers classify T_i     : chain 2 (output offset) of T_(i-1)  -> s_off
     //   barrier (1)
     //   while the workers flatten T_(i-1)  : chain 1 (quote parity) of T_i       -> s_parin
     //   barrier (2), barrier (3)
@@ -820,6 +903,7 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
         bool have_prev = false;
         int prev_tile = 0;
         uint32_t prev_tile_count = 0, prev_par_out = 0;
+        uint32_t prev_wbase = 0, prev_wlast = 0;  // lane w: structurals / last structural (+1) in the slabs below slab w
 #ifdef SJ_PROFILE_PHASES
         const int tl_slot = timeline_slot();
         int tl_it = -1;
@@ -846,14 +930,16 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
                     }
                 }
             }
-            if (lane == 0) s_base = tb;
+            if (lane < S1_WARPS) {
+                s_off[lane] = tb + prev_wbase;
+                s_wlast[lane] = prev_wlast;
+            }
             SJ_TL(0)
             __syncthreads();  // (1)
             SJ_TL(1)
             if (lane == 0) issue(tile + G, b ^ 1);
-            uint32_t tile_par = 0;
-#pragma unroll
-            for (int w2 = 0; w2 < S1_WARPS; w2++) tile_par ^= s_par[w2];
+            const uint32_t parbits = __ballot_sync(FULL, lane < S1_WARPS && s_par[lane < S1_WARPS ? lane : 0] != 0);
+            const uint32_t tile_par = __popc(parbits) & 1;
             uint32_t tin = 0;
             if (cur) {
                 if (lane == 0)
@@ -869,18 +955,26 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
                     if (lane == 0) st_relaxed_u8(p.dpar + tile, DP_VALID | DP_INCL | ((tile_par ^ tin) ? DP_PAR : 0));
                 }
             }
-            if (lane == 0) s_parin = tin;
+            if (lane < S1_WARPS) s_parin[lane] = tin ^ (__popc(parbits & lanemask_lt()) & 1);
             SJ_TL(2)
             __syncthreads();  // (2)
-            __syncthreads();  // (3)
+            named_bar_sync(1, S1_THREADS);  // (3): the workers arrive without waiting
             SJ_TL(3)
-            uint32_t tile_count = 0, tile_last1 = 0;
+            // per-slab prefixes of the tile just finished (consumed by its flatten, next iteration)
+            const uint32_t cnt = lane < S1_WARPS ? s_cnt[lane] : 0, l1 = lane < S1_WARPS ? s_last[lane] : 0;
+            uint32_t incl = cnt;
 #pragma unroll
-            for (int w2 = 0; w2 < S1_WARPS; w2++) {
-                uint32_t l1 = s_last[w2];
-                tile_count += s_cnt[w2];
-                if (l1) tile_last1 = l1;
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t t = __shfl_up_sync(FULL, incl, d);
+                if (lane >= d) incl += t;
             }
+            const uint32_t tile_count = __shfl_sync(FULL, incl, 31);
+            const uint32_t nonempty = __ballot_sync(FULL, l1 != 0);
+            const uint32_t below = nonempty & lanemask_lt();
+            const uint32_t got = __shfl_sync(FULL, l1, below ? 31 - __clz(below) : 0);
+            const uint32_t tile_last1 = __shfl_sync(FULL, l1, nonempty ? 31 - __clz(nonempty) : 0);
+            prev_wbase = incl - cnt;
+            prev_wlast = below ? got : 0;
             if (cur && lane == 0) {  // chain-2 aggregate; its look-back runs one iteration later
                 p.lastp1[tile] = tile_last1;
                 st_relaxed_u32(p.dagg + tile, DA_VALID | tile_count);
@@ -905,7 +999,7 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
 #pragma unroll
     for (int s = 0; s < S1_STEPS; s++) S_prev[s] = 0;
     int prev_tile = 0;
-    uint32_t prev_warp_base = 0, prev_in_tile1 = 0;
+    uint32_t prev_slab_count = 0;
 
     // bytes in front of a warp's slab of tile t (0x20 = "nothing there": first slab, or no such slab)
     auto peek_load = [&](int t) -> uint32_t {
@@ -920,6 +1014,7 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
         const int slab = tile * S1_WARPS + (int)warp;
         const uint64_t slab_start = (uint64_t)slab * S1_SLAB_BYTES;
         const bool active = cur && slab_start < p.len;  // warps past the end of the message only keep the barriers
+        const bool tail_tile = tile >= p.ntiles - 1;
         const uint8_t* buf = smem + (size_t)b * S1_TILE_BYTES + (size_t)warp * S1_SLAB_BYTES;
 
         // carries that depend only on raw bytes in front of the slab: lane L holds byte
@@ -957,7 +1052,7 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
                 uint32_t w[16];
                 load_block_words(buf + s * S1_STEP_BYTES, lane, w);
                 const uint64_t blockpos = slab_start + (uint64_t)s * S1_STEP_BYTES + 64 * lane;
-                mask_tail(w, lane, blockpos, p.len);
+                if (tail_tile) mask_tail(w, lane, blockpos, p.len);  // CTA-uniform: only the last tile has a tail
                 const uint32_t r = (lane >> 1) & 3;
 #if !defined(SJ_CLASSIFY_LUT) && !defined(SJ_CLASSIFY_SWAR)
                 PlaneMasks m = classify_block_planes(w);
@@ -1040,33 +1135,26 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
                           //     buffer b^1 is free (the previous iteration's staging is finished)
         // the scan warp issues the TMA of the next tile into b^1 and runs chain 1 of this tile now
         const uint32_t peek_next = peek_load(tile + G);
-        uint32_t warp_pre = 0;
-#pragma unroll
-        for (int w2 = 0; w2 < S1_WARPS; w2++)
-            if (w2 < (int)warp) warp_pre ^= s_par[w2];
         SJ_PROF_MARK(4)
 
         // ---------------- flatten of the previous tile ----------------
         if (have_prev) {
             // deltas: the first structural of a tile is written as pos + 1 here and rebased on the
             // previous tile's last structural by stage1_finish_kernel
-            uint32_t prev_last = prev_in_tile1 - 1;  // 0xffffffff when nothing precedes inside the tile
-            uint32_t overflow = 0;
-            uint64_t off = s_base + prev_warp_base;
+            const uint32_t prev_last = s_wlast[warp] - 1;  // 0xffffffff when nothing precedes inside the tile
+            const uint64_t off = s_off[warp];
             // the warp's own slab of buffer b is dead after phase A: reuse it as the staging area
             uint32_t* stage = reinterpret_cast<uint32_t*>(smem + (size_t)b * S1_TILE_BYTES + (size_t)warp * S1_SLAB_BYTES);
             const uint64_t pslab_start = ((uint64_t)prev_tile * S1_WARPS + warp) * S1_SLAB_BYTES;
-#pragma unroll
-            for (int s = 0; s < S1_STEPS; s++) {
-                uint32_t blockpos = (uint32_t)(pslab_start + (uint64_t)s * S1_STEP_BYTES + 64 * lane);
-                off += flatten_step<DELTAS>(S_prev[s], blockpos, p.out, off, p.out_cap, prev_last, overflow, stage,
-                                            S1_SLAB_BYTES / 4);
+            if (off + prev_slab_count > p.out_cap) {  // warp-uniform
+                if (lane == 0) atomicOr(&p.result->overflow, 1u);
+            } else {
+                flatten_slab_staged<DELTAS, S1_STEPS>(S_prev, (uint32_t)pslab_start, p.out + off, prev_last, stage, S1_SLAB_BYTES / 4);
             }
-            if (overflow && lane == 0) atomicOr(&p.result->overflow, 1u);
         }
         SJ_PROF_MARK(5)
         __syncthreads();  // (2) quote parity in front of the tile (scan warp, chain 1)
-        const uint32_t par_in = s_parin ^ warp_pre;
+        const uint32_t par_in = s_parin[warp];
         SJ_PROF_MARK(0)
 
         // pseudo-structural predecessor carry into the slab (finalize_structurals_amd64.s:24-27;
@@ -1124,21 +1212,12 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
             s_last[warp] = own_last1;
         }
         SJ_PROF_MARK(6)
-        __syncthreads();  // (3) slab counts of the tile are visible
+        // (3) slab counts of the tile are visible to the scan warp; the workers only signal
+        named_bar_arrive(1, S1_THREADS);
 
-        uint32_t warp_base = 0, in_tile1 = 0;
-#pragma unroll
-        for (int w2 = 0; w2 < S1_WARPS; w2++) {
-            if (w2 < (int)warp) {
-                uint32_t l1 = s_last[w2];
-                warp_base += s_cnt[w2];
-                if (l1) in_tile1 = l1;
-            }
-        }
         have_prev = cur;
         prev_tile = tile;
-        prev_warp_base = warp_base;
-        prev_in_tile1 = in_tile1;
+        prev_slab_count = slab_count;
         peekc = peek_next;
         tile += G;
         b ^= 1;

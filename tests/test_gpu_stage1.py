@@ -199,3 +199,18 @@ def test_control_char_error(ctx, oracle_native):
     for c in (0, 1, 9, 10, 13, 31):
         _check(ctx, oracle_native, b'{"a":"x' + bytes([c]) + b'y"}', False)
         _check(ctx, oracle_native, b'{"a" ' + bytes([c]) + b' :"xy"}', False)
+
+
+def test_dense_structurals(ctx, oracle_native):
+    """more than one structural per 4 bytes: the flatten's staging area (slab / 4 entries) overflows,
+    so the mid-slab flush and the straight-to-global path are exercised (positions and deltas)"""
+    docs = [
+        b"[" * 150000 + b"]" * 150000,                      # every byte structural
+        b"[" + b"[1," * 60000 + b"1" + b"]" * 60000 + b"]",  # 2 of 3 bytes
+        b"[" + b",".join([b"[]"] * 90000) + b"]",             # all structural, no values
+        b"[" + b",".join([b'{"a":[1,2],"b":{}}'] * 20000) + b"]",
+        b"[" + b"1," * 30000 + b"[" * 5000 + b"]" * 5000 + b"," + b'"x"' * 1 + b"]",  # sparse then dense then sparse
+    ]
+    for d in docs:
+        _check(ctx, oracle_native, d, False)
+        _check(ctx, oracle_native, d, True)
