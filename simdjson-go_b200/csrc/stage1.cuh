@@ -35,6 +35,10 @@ namespace sj {
 #ifndef SJ_SPIN_SLEEP
 #define SJ_SPIN_SLEEP 1000
 #endif
+#ifndef SJ_SPIN_FIRST
+#define SJ_SPIN_FIRST 1  // pause before the first poll as well: polling while the other CTAs publish
+                         // into the same descriptor lines slows everybody down (0.56 -> 0.96 ms per GiB)
+#endif
 #ifndef SJ_S1_CTAS_PER_SM
 #define SJ_S1_CTAS_PER_SM 1
 #endif
@@ -123,6 +127,22 @@ __device__ __forceinline__ uint64_t mk64(uint32_t lo, uint32_t hi) { return ((ui
 
 // rotate a 64-bit mask left by 16*r bits (r = 0..3): undoes the bank-conflict-free
 // chunk rotation used when a lane reads its 64 bytes from shared memory
+// The same rotation as two PRMTs: the four 16-bit pieces of (lo, hi) are re-ordered by per-lane
+// selectors (rot_selectors) computed once per thread.
+struct RotSel {
+    uint32_t lo, hi;
+};
+__device__ __forceinline__ RotSel rot_selectors(uint32_t r) {
+    // result piece k = source piece (k - r) & 3 ; piece q = bytes 2q, 2q+1 of the 8-byte pool {lo, hi}
+    auto two = [](uint32_t q0, uint32_t q1) { return (2 * q0) | ((2 * q0 + 1) << 4) | ((2 * q1) << 8) | ((2 * q1 + 1) << 12); };
+    RotSel s;
+    s.lo = two((0 - r) & 3, (1 - r) & 3);
+    s.hi = two((2 - r) & 3, (3 - r) & 3);
+    return s;
+}
+__device__ __forceinline__ uint64_t rotl16x(uint32_t lo, uint32_t hi, const RotSel& s) {
+    return mk64(__byte_perm(lo, hi, s.lo), __byte_perm(lo, hi, s.hi));
+}
 __device__ __forceinline__ uint64_t rotl16x(uint64_t m, uint32_t r) {
     uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
     if (r & 2) {
@@ -222,9 +242,22 @@ __device__ __forceinline__ void transpose4x4(uint32_t a, uint32_t b, uint32_t c,
 
 // one merge step: hi keeps the m-bits of X in place and moves the m-bits of Y down by s;
 // lo moves the ~m-bits of X up by s and keeps the ~m-bits of Y     (m >> s == ~m)
+// (a & m) | (b & ~m) as ONE LOP3 (the compiler emits an AND and an OR-AND for the C expression
+// because m and ~m are different immediates)
+__device__ __forceinline__ uint32_t bitsel(uint32_t m, uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(d) : "r"(a), "r"(b), "r"(m));
+    return d;
+}
 __device__ __forceinline__ void s2p_pair(uint32_t X, uint32_t Y, uint32_t m, int s, uint32_t& hi, uint32_t& lo) {
-    hi = (X & m) | ((Y >> s) & ~m);
-    lo = ((X << s) & m) | (Y & ~m);
+#ifndef SJ_S2P_SHIFT
+    // Y >> s as IMAD.HI: the classifier is bound by the ALU pipe (LOP3 / SHF / PRMT issue every
+    // other cycle), the FMA pipe is nearly idle -- measured 4 % faster than the SHF form
+    hi = bitsel(m, X, __umulhi(Y, 1u << (32 - s)));
+#else
+    hi = bitsel(m, X, Y >> s);
+#endif
+    lo = bitsel(m, X << s, Y);
 }
 
 // bit planes of 32 bytes held in 8 words (word k = bytes 4k..4k+3): pl[k] bit i = bit k of byte i
@@ -466,6 +499,62 @@ __device__ __forceinline__ uint32_t flatten_step(uint64_t S, uint32_t blockpos, 
     return total;
 }
 
+// Positions of the structurals of one 2 KiB step, staged into `chunk` (the step's own, already
+// consumed, input bytes: 512 entries).  Extraction runs from the top bit down (one FLO per
+// structural, no bit reversal) as two independent chains (the two 32-bit halves of the lane's
+// mask) with predicated stores.  Returns the step's count (warp-uniform); nothing is staged if it
+// exceeds `cap` (more than one structural per 4 bytes).
+__device__ __forceinline__ uint32_t extract_step(uint64_t S, uint32_t pos0, uint32_t* chunk, uint32_t cap) {
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t lo = (uint32_t)S, hi = (uint32_t)(S >> 32);
+    const uint32_t ch = __popc(hi);
+    const uint32_t c = __popc(lo) + ch;
+    uint32_t inc = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(FULL, inc, d);
+        if (lane >= d) inc += t;
+    }
+    const uint32_t total = __shfl_sync(FULL, inc, 31);
+    if (total > cap) return total;
+    // cursors on the LAST slot of each half
+    uint32_t ahi = (uint32_t)__cvta_generic_to_shared(chunk) + 4 * inc - 4;
+    uint32_t alo = ahi - 4 * ch;
+    const uint32_t pos1 = pos0 + 32;
+    while (lo | hi) {
+#pragma unroll
+        for (int u = 0; u < SJ_FLATTEN_UNROLL; u++) {
+            {
+                const uint32_t b = bfind(lo);
+                sts_if(alo - 4 * u, pos0 + b, lo);
+                lo &= ~(1u << (b & 31));
+            }
+            {
+                const uint32_t b = bfind(hi);
+                sts_if(ahi - 4 * u, pos1 + b, hi);
+                hi &= ~(1u << (b & 31));
+            }
+        }
+        alo -= 4 * SJ_FLATTEN_UNROLL;
+        ahi -= 4 * SJ_FLATTEN_UNROLL;
+    }
+    return total;
+}
+
+// Coalesced copy-out of one staged step; deltas (flatten_bits_amd64.s:38-40) are formed here from
+// neighbouring staged positions, so the divergent extraction loop carries no delta arithmetic.
+template <bool DELTAS>
+__device__ __forceinline__ void copy_out_step(const uint32_t* chunk, uint32_t n, uint32_t* __restrict__ dst, uint32_t& prev_last) {
+    const uint32_t lane = threadIdx.x & 31;
+#pragma unroll 4
+    for (uint32_t k = lane; k < n; k += 32) {
+        uint32_t v = chunk[k];
+        if (DELTAS) v -= k ? chunk[k - 1] : prev_last;
+        dst[k] = v;
+    }
+    if (DELTAS && n) prev_last = chunk[n - 1];
+}
+
 // Flatten of a whole slab through the warp's staging area.  Positions are extracted from the top
 // bit down (one FLO per structural, no bit reversal) by two independent chains (the two 32-bit
 // halves of the lane's mask) with predicated stores; the copy-out is coalesced and forms the
@@ -587,6 +676,7 @@ __device__ __forceinline__ uint32_t lookback_parity(const uint8_t* dpar, int sla
     for (int g = slab >> 4;; g -= 32) {  // lane L inspects the 16-slab group g - L
         const int grp = g - lane;
         uint32_t V, I, P;
+        bool again = false;
 #ifdef SJ_PROFILE_PHASES
         nround++;
 #endif
@@ -594,7 +684,8 @@ __device__ __forceinline__ uint32_t lookback_parity(const uint8_t* dpar, int sla
 #ifdef SJ_PROFILE_PHASES
             nspin++;
 #endif
-            if (SJ_SPIN_SLEEP) __nanosleep(SJ_SPIN_SLEEP);
+            if (SJ_SPIN_SLEEP && (again || SJ_SPIN_FIRST)) __nanosleep(SJ_SPIN_SLEEP);
+            again = true;
             if (grp >= 0) {
                 uint4 q = ld_relaxed_v4(dpar + (size_t)grp * 16);
                 V = gather_bit16(q, 0);
@@ -639,6 +730,7 @@ __device__ __forceinline__ uint64_t lookback_count(const uint32_t* dagg, const u
         const int grp = g - lane;
         uint32_t sum = 0, valid = 1;
         uint64_t inc = 0;
+        bool again = false;
 #ifdef SJ_PROFILE_PHASES
         nround++;
 #endif
@@ -646,7 +738,8 @@ __device__ __forceinline__ uint64_t lookback_count(const uint32_t* dagg, const u
 #ifdef SJ_PROFILE_PHASES
             nspin++;
 #endif
-            if (SJ_SPIN_SLEEP) __nanosleep(SJ_SPIN_SLEEP);
+            if (SJ_SPIN_SLEEP && (again || SJ_SPIN_FIRST)) __nanosleep(SJ_SPIN_SLEEP);
+            again = true;
             if (grp >= 0) {
                 uint4 q = ld_relaxed_v4(dagg + (size_t)grp * 4);
                 inc = grp > 0 ? ld_relaxed_u64(dinc + (size_t)grp * 4 - 1) : DI_VALID;
@@ -859,6 +952,12 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
     __shared__ unsigned long long s_off[S1_WARPS];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S1_BUFS * S1_TILE_BYTES);
+    // hand-shakes between the worker warps and the scan warp (one phase per iteration).  Workers
+    // never wait for each other directly: they signal P / R and wait for the scan warp's S / Q.
+    uint64_t* const bar_P = bars + 2;  // workers -> scan: slab parities of the tile are written   (count = workers)
+    uint64_t* const bar_R = bars + 3;  // workers -> scan: slab counts of the tile are written     (count = workers)
+    uint64_t* const bar_S = bars + 4;  // scan -> workers: output offsets of the previous tile     (count = 1)
+    uint64_t* const bar_Q = bars + 5;  // scan -> workers: in-string state in front of every slab  (count = 1)
     const uint64_t len16 = (p.len + 15) & ~15ull;
     const int G = (int)gridDim.x;
 #ifdef SJ_CLASSIFY_LUT
@@ -875,6 +974,8 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
         if (t < p.ntiles) {
             uint64_t start = (uint64_t)t * S1_TILE_BYTES;
             uint32_t bytes = (uint32_t)min((uint64_t)S1_TILE_BYTES, len16 - start);
+            // the buffer was last written through the generic proxy (staged positions)
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_expect_tx(&bars[b], bytes);
             tma_load_1d(smem + (size_t)b * S1_TILE_BYTES, p.msg + start, bytes, &bars[b]);
         }
@@ -884,6 +985,10 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
     if (threadIdx.x == S1_WARPS * 32) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
+        mbar_init(bar_P, S1_WARPS);
+        mbar_init(bar_R, S1_WARPS);
+        mbar_init(bar_S, 1);
+        mbar_init(bar_Q, 1);
         mbar_fence_init();
         issue(tile, 0);
     }
@@ -904,6 +1009,7 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
         int prev_tile = 0;
         uint32_t prev_tile_count = 0, prev_par_out = 0;
         uint32_t prev_wbase = 0, prev_wlast = 0;  // lane w: structurals / last structural (+1) in the slabs below slab w
+        uint32_t itpar = 0;                        // parity of the iteration = phase of the hand-shake barriers
 #ifdef SJ_PROFILE_PHASES
         const int tl_slot = timeline_slot();
         int tl_it = -1;
@@ -934,8 +1040,10 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
                 s_off[lane] = tb + prev_wbase;
                 s_wlast[lane] = prev_wlast;
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_S);
             SJ_TL(0)
-            __syncthreads();  // (1)
+            mbar_wait(bar_P, itpar);  // every worker has classified its slab: buffer b^1 (tile i-1) is dead
             SJ_TL(1)
             if (lane == 0) issue(tile + G, b ^ 1);
             const uint32_t parbits = __ballot_sync(FULL, lane < S1_WARPS && s_par[lane < S1_WARPS ? lane : 0] != 0);
@@ -956,9 +1064,11 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
                 }
             }
             if (lane < S1_WARPS) s_parin[lane] = tin ^ (__popc(parbits & lanemask_lt()) & 1);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_Q);
             SJ_TL(2)
-            __syncthreads();  // (2)
-            named_bar_sync(1, S1_THREADS);  // (3): the workers arrive without waiting
+            mbar_wait(bar_R, itpar);
+            itpar ^= 1;
             SJ_TL(3)
             // per-slab prefixes of the tile just finished (consumed by its flatten, next iteration)
             const uint32_t cnt = lane < S1_WARPS ? s_cnt[lane] : 0, l1 = lane < S1_WARPS ? s_last[lane] : 0;
@@ -991,6 +1101,8 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
 
     SJ_PROF_DECL
     uint32_t phasebits = 0;
+    uint32_t itpar = 0;  // parity of the iteration = phase of the hand-shake barriers
+    const RotSel rsel = rot_selectors((lane >> 1) & 3);  // undoes the bank-conflict-free chunk order of load_block_words
 
     // software pipeline: iteration i runs phase A / chain 1 / phase B of tile T_i and the chain-2
     // look-back + flatten of tile T_(i-1); one drain iteration flattens the last tile
@@ -1030,7 +1142,7 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
             const uint32_t n = __ffs(~(peek_bs >> 1)) - 1;
             prevc_esc = n == 31 ? backslash_run_before(p.msg, slab_start - 1) & 1 : n & 1;
         }
-        SJ_PROF_MARK(1)
+        SJ_PROF_MARK(7)
         if (cur) {
             mbar_wait(&bars[b], (phasebits >> b) & 1);
             phasebits ^= 1u << b;
@@ -1038,76 +1150,48 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
         SJ_PROF_MARK(2)
 
         // ---------------- phase A: classify, escape analysis, slab quote parity ----------------
-        uint64_t qb[S1_STEPS], st[S1_STEPS], ws[S1_STEPS], ct[S1_STEPS], nl[S1_STEPS];
+        // ... interleaved, step by step, with the EXTRACTION of the previous tile's structurals: the
+        // classification is all ALU-pipe work, the extraction is FLO / shared-store work, and warps
+        // drift apart inside this region (the extraction loop's trip count differs per warp), so
+        // the two instruction mixes overlap on the SM instead of alternating.  The positions of
+        // step s are staged over the input bytes of step s of this tile, which are dead as soon as
+        // every lane of the warp has loaded them.
+        uint64_t qb[S1_STEPS], st[S1_STEPS], ws[S1_STEPS], ct[S1_STEPS], nl[S1_STEPS], bsm[S1_STEPS];
+        uint32_t tot_prev[S1_STEPS];  // structurals per step of the previous tile's slab (warp-uniform)
+        uint32_t dense = 0;           // a step of the previous tile did not fit its staging chunk
         uint32_t slab_par = 0;
+        uint32_t* const stage = reinterpret_cast<uint32_t*>(smem + (size_t)b * S1_TILE_BYTES + (size_t)warp * S1_SLAB_BYTES);
+        const uint32_t pslab_pos = (uint32_t)(((uint64_t)prev_tile * S1_WARPS + warp) * S1_SLAB_BYTES);
 #pragma unroll
-        for (int s = 0; s < S1_STEPS; s++) qb[s] = st[s] = ws[s] = ct[s] = nl[s] = 0;
-        if (active) {
-            // pass 1: pure per-lane classification of all steps -- no warp-synchronous operation in
-            // this loop, so the compiler is free to overlap the steps' instruction streams
-            uint64_t bsm[S1_STEPS];
-            uint32_t anyct_l[S1_STEPS];
-#pragma unroll
-            for (int s = 0; s < S1_STEPS; s++) {
-                uint32_t w[16];
-                load_block_words(buf + s * S1_STEP_BYTES, lane, w);
+        for (int s = 0; s < S1_STEPS; s++) {
+            qb[s] = st[s] = ws[s] = ct[s] = nl[s] = bsm[s] = 0;
+            tot_prev[s] = 0;
+            uint32_t w[16];
+            if (active) load_block_words(buf + s * S1_STEP_BYTES, lane, w);
+#ifdef SJ_INTERLEAVE  // extraction of the previous tile step by step between the classifications
+            if (have_prev) {
+                __syncwarp();  // every lane holds its bytes of step s: the chunk may be overwritten
+                tot_prev[s] = extract_step(S_prev[s], pslab_pos + s * S1_STEP_BYTES + 64 * lane, stage + s * (S1_STEP_BYTES / 4),
+                                           S1_STEP_BYTES / 4);
+                dense |= tot_prev[s] > S1_STEP_BYTES / 4;
+            }
+#endif
+            if (active) {
                 const uint64_t blockpos = slab_start + (uint64_t)s * S1_STEP_BYTES + 64 * lane;
                 if (tail_tile) mask_tail(w, lane, blockpos, p.len);  // CTA-uniform: only the last tile has a tail
-                const uint32_t r = (lane >> 1) & 3;
-#if !defined(SJ_CLASSIFY_LUT) && !defined(SJ_CLASSIFY_SWAR)
                 PlaneMasks m = classify_block_planes(w);
-                bsm[s] = rotl16x(m.bs, r);
-                qb[s] = rotl16x(m.qt, r);  // raw quotes; escaped ones are removed in pass 2
-                st[s] = rotl16x(m.st, r);
-                ws[s] = rotl16x(m.ws, r);
-                ct[s] = rotl16x(m.ct, r);
-                if (NDJSON) nl[s] = rotl16x(m.nl, r);
-                anyct_l[s] = 0;
-#elif defined(SJ_CLASSIFY_LUT)
-                uint32_t A[8];
-                lut_classify(lut1, w, A);
-                qb[s] = rotl16x(lut_mask<0>(A), r);  // raw quotes; escaped ones are removed in pass 2
-                st[s] = rotl16x(lut_mask<1>(A), r);
-                ws[s] = rotl16x(lut_mask<2>(A), r);
-                const uint64_t rare = lut_mask<3>(A);
-                anyct_l[s] = ((uint32_t)rare | (uint32_t)(rare >> 32)) != 0;
-                bsm[s] = 0;
-#else
-                BlockMasks m = classify_block(w);
-                bsm[s] = rotl16x(m.bs, r);
-                qb[s] = rotl16x(m.qt, r);  // raw quotes; escaped ones are removed in pass 2
-                st[s] = rotl16x(m.st, r);
-                ws[s] = rotl16x(m.sp, r);
-                anyct_l[s] = m.anyct;
-#endif
+                bsm[s] = rotl16x((uint32_t)m.bs, (uint32_t)(m.bs >> 32), rsel);
+                qb[s] = rotl16x((uint32_t)m.qt, (uint32_t)(m.qt >> 32), rsel);  // raw quotes; escaped ones are removed in pass 2
+                st[s] = rotl16x((uint32_t)m.st, (uint32_t)(m.st >> 32), rsel);
+                ws[s] = rotl16x((uint32_t)m.ws, (uint32_t)(m.ws >> 32), rsel);
+                ct[s] = rotl16x((uint32_t)m.ct, (uint32_t)(m.ct >> 32), rsel);
+                if (NDJSON) nl[s] = rotl16x((uint32_t)m.nl, (uint32_t)(m.nl >> 32), rsel);
             }
+        }
+        if (active) {
             // pass 2: everything that needs votes across the warp
 #pragma unroll
             for (int s = 0; s < S1_STEPS; s++) {
-#if defined(SJ_CLASSIFY_LUT) || defined(SJ_CLASSIFY_SWAR)
-                if (__any_sync(FULL, anyct_l[s] != 0))
-#else
-                if (false)
-#endif
-                {  // warp-uniform second classification pass of the LUT / SWAR variants
-                    uint32_t w[16];
-                    load_block_words(buf + s * S1_STEP_BYTES, lane, w);
-                    const uint64_t blockpos = slab_start + (uint64_t)s * S1_STEP_BYTES + 64 * lane;
-                    mask_tail(w, lane, blockpos, p.len);
-                    const uint32_t r = (lane >> 1) & 3;
-#ifdef SJ_CLASSIFY_LUT
-                    uint32_t A[8];
-                    lut_classify(lut2, w, A);
-                    bsm[s] = rotl16x(lut_mask<0>(A), r);
-                    ct[s] = rotl16x(lut_mask<1>(A), r);
-                    if (NDJSON) nl[s] = rotl16x(lut_mask<2>(A), r);
-#else
-                    SlowMasks sm = classify_block_slow(w);
-                    ws[s] |= rotl16x(sm.wsc, r);
-                    ct[s] = rotl16x(sm.ct, r);
-                    if (NDJSON) nl[s] = rotl16x(sm.nl, r);
-#endif
-                }
                 const uint64_t bs = bsm[s];
                 // odd-backslash carry into each lane's block (warp-uniform fast path: no backslashes at all)
                 uint64_t odd_ends = 0;
@@ -1129,31 +1213,56 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
                 if (p.bsmap && lane == 0) p.bsmap[slab * S1_STEPS + s] = hasbs;
             }
         }
-        if (lane == 0) s_par[warp] = slab_par;
+        // P: the slab's parity is written and the warp is done with buffer b^1.  When the last worker
+        // has signalled, the scan warp issues the TMA of the next tile into b^1 and starts chain 1 of
+        // this tile; nobody waits here, so the warps drift apart and the ALU-bound classification of
+        // late warps overlaps the FLO / store-bound extraction of early ones.
+        if (lane == 0) {
+            s_par[warp] = slab_par;
+            mbar_arrive(bar_P);
+        }
         SJ_PROF_MARK(3)
-        __syncthreads();  // (1) slab parities visible; buffer b is dead (nothing re-reads the bytes) and
-                          //     buffer b^1 is free (the previous iteration's staging is finished)
-        // the scan warp issues the TMA of the next tile into b^1 and runs chain 1 of this tile now
         const uint32_t peek_next = peek_load(tile + G);
+#ifndef SJ_INTERLEAVE
+        // ---------------- extraction of the previous tile's structurals ----------------
+        // positions of step s are staged over the input bytes of step s of the warp's own slab
+        // (dead: this warp alone read them, in phase A above)
+        if (have_prev) {
+            __syncwarp();
+#pragma unroll
+            for (int s = 0; s < S1_STEPS; s++) {
+                tot_prev[s] = extract_step(S_prev[s], pslab_pos + s * S1_STEP_BYTES + 64 * lane, stage + s * (S1_STEP_BYTES / 4),
+                                           S1_STEP_BYTES / 4);
+                dense |= tot_prev[s] > S1_STEP_BYTES / 4;
+            }
+        }
+#endif
         SJ_PROF_MARK(4)
+        mbar_wait(bar_S, itpar);  // output offsets of the previous tile (chain 2, run by the scan warp under phase A)
+        SJ_PROF_MARK(1)
+        __syncwarp();             // staged positions of all lanes are visible
 
-        // ---------------- flatten of the previous tile ----------------
+        // ---------------- copy-out of the previous tile's staged structurals ----------------
         if (have_prev) {
             // deltas: the first structural of a tile is written as pos + 1 here and rebased on the
             // previous tile's last structural by stage1_finish_kernel
-            const uint32_t prev_last = s_wlast[warp] - 1;  // 0xffffffff when nothing precedes inside the tile
+            uint32_t prev_last = s_wlast[warp] - 1;  // 0xffffffff when nothing precedes inside the tile
             const uint64_t off = s_off[warp];
-            // the warp's own slab of buffer b is dead after phase A: reuse it as the staging area
-            uint32_t* stage = reinterpret_cast<uint32_t*>(smem + (size_t)b * S1_TILE_BYTES + (size_t)warp * S1_SLAB_BYTES);
-            const uint64_t pslab_start = ((uint64_t)prev_tile * S1_WARPS + warp) * S1_SLAB_BYTES;
             if (off + prev_slab_count > p.out_cap) {  // warp-uniform
                 if (lane == 0) atomicOr(&p.result->overflow, 1u);
-            } else {
-                flatten_slab_staged<DELTAS, S1_STEPS>(S_prev, (uint32_t)pslab_start, p.out + off, prev_last, stage, S1_SLAB_BYTES / 4);
+            } else if (!dense) {
+                uint32_t* dst = p.out + off;
+#pragma unroll
+                for (int s = 0; s < S1_STEPS; s++) {
+                    copy_out_step<DELTAS>(stage + s * (S1_STEP_BYTES / 4), tot_prev[s], dst, prev_last);
+                    dst += tot_prev[s];
+                }
+            } else {  // more than one structural per 4 bytes somewhere in the slab: unstaged path
+                flatten_slab_staged<DELTAS, S1_STEPS>(S_prev, pslab_pos, p.out + off, prev_last, stage, S1_SLAB_BYTES / 4);
             }
         }
         SJ_PROF_MARK(5)
-        __syncthreads();  // (2) quote parity in front of the tile (scan warp, chain 1)
+        mbar_wait(bar_Q, itpar);  // quote parity in front of the tile (chain 1, run by the scan warp meanwhile)
         const uint32_t par_in = s_parin[warp];
         SJ_PROF_MARK(0)
 
@@ -1212,8 +1321,9 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
             s_last[warp] = own_last1;
         }
         SJ_PROF_MARK(6)
-        // (3) slab counts of the tile are visible to the scan warp; the workers only signal
-        named_bar_arrive(1, S1_THREADS);
+        // R: slab counts of the tile are written (the same lane 0 wrote them)
+        if (lane == 0) mbar_arrive(bar_R);
+        itpar ^= 1;
 
         have_prev = cur;
         prev_tile = tile;

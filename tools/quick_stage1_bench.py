@@ -68,7 +68,7 @@ for lib in libs:
         if has_prof:
             L.sj_debug_read_prof(h, buf, 1)
             tot = float(sum(buf[:8]))
-            names = ["wait(2)", "peek", "tma wait", "phaseA", "wait(1)", "flatten", "phaseB", "wait(3)+tail"]
+            names = ["wait Q", "wait S", "tma wait", "phaseA", "extract", "copy-out", "phaseB", "top+peek"]
             print("   " + "  ".join("%s %.1f%%" % (nm, 100 * v / tot) for nm, v in zip(names, buf)))
             if hasattr(L, "sj_debug_read_timeline") and deltas == 0:
                 tl = (C.c_ulonglong * (8 * 256 * 4))()
