@@ -217,10 +217,10 @@ static int launch_stage1(sj_ctx* c, const uint8_t* d_msg, size_t len, bool ndjso
     if (len == 0 || len > SJ_MAX_MESSAGE) return SJ_ERR_TOO_LARGE;
     if ((reinterpret_cast<uintptr_t>(d_msg) & 15) != 0) return SJ_ERR_ARGUMENT;
     const int ntiles = (int)((len + S1_TILE_BYTES - 1) / S1_TILE_BYTES);
-    // descriptor block: [dinc u64][lastp1 u32][dagg u32][dpar u8], every part 16-byte aligned
+    // descriptor block: [lastp1 u32][chain-1 slots][chain-2 slots]; a slot per tile and chain
     const size_t n16 = ((size_t)ntiles + 15) & ~(size_t)15;
-    const size_t off_inc = 0, off_last = off_inc + n16 * 8, off_agg = off_last + n16 * 4, off_par = off_agg + n16 * 4;
-    const size_t desc_bytes = off_par + n16 + 16;
+    const size_t off_last = 0, off_par = (n16 * 4 + 127) & ~(size_t)127, off_cnt = off_par + (size_t)ntiles * S1_DESC_STRIDE;
+    const size_t desc_bytes = off_cnt + (size_t)ntiles * S1_DESC_STRIDE;
     int rc = c->desc.reserve(desc_bytes);
     if (rc) return rc;
     SJ_CUDA_CHECK(cudaMemsetAsync(c->desc.p, 0, desc_bytes, c->stream));
@@ -230,10 +230,9 @@ static int launch_stage1(sj_ctx* c, const uint8_t* d_msg, size_t len, bool ndjso
     p.len = len;
     p.out = d_out;
     p.out_cap = cap;
-    p.dinc = reinterpret_cast<uint64_t*>(c->desc.as<uint8_t>() + off_inc);
     p.lastp1 = reinterpret_cast<uint32_t*>(c->desc.as<uint8_t>() + off_last);
-    p.dagg = reinterpret_cast<uint32_t*>(c->desc.as<uint8_t>() + off_agg);
     p.dpar = c->desc.as<uint8_t>() + off_par;
+    p.dcnt = c->desc.as<uint8_t>() + off_cnt;
     p.result = c->result.as<Stage1Result>();
     p.ntiles = ntiles;
     p.bsmap = d_bsmap;

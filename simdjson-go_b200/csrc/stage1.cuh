@@ -30,14 +30,15 @@ namespace sj {
 #ifndef SJ_S1_WARPS
 #define SJ_S1_WARPS 16
 #endif
-// Pause between two polls of a look-back (ns).  148 scan warps polling back to back slow the
-// publishers down (measured: 1.17 ms per GiB without a pause, 0.77 ms with 0.4-1.5 us).
+// Pause between two polls of a look-back (ns), and whether to pause before the first poll too.
+// With one descriptor slot per L2 line the chains are insensitive to both (0.50 ms per GiB with
+// no pause, 100 ns or 400 ns); with the descriptors of 128 tiles packed in one line a poll issued
+// while the other CTAs published cost microseconds (1.0 ms unless every look-back slept 1 us first).
 #ifndef SJ_SPIN_SLEEP
-#define SJ_SPIN_SLEEP 1000
+#define SJ_SPIN_SLEEP 100
 #endif
 #ifndef SJ_SPIN_FIRST
-#define SJ_SPIN_FIRST 1  // pause before the first poll as well: polling while the other CTAs publish
-                         // into the same descriptor lines slows everybody down (0.56 -> 0.96 ms per GiB)
+#define SJ_SPIN_FIRST 0
 #endif
 #ifndef SJ_S1_CTAS_PER_SM
 #define SJ_S1_CTAS_PER_SM 1
@@ -630,16 +631,23 @@ __device__ __forceinline__ void flatten_slab_staged(const uint64_t (&S)[STEPS], 
 }
 
 // ---------------------------------------------------------------------------------
-// look-back chains.  A look-back can only advance one window of predecessors per L2
-// round trip, so the windows are made wide with narrow descriptors:
-//   chain 1 (in-string parity): one BYTE per tile  {bit0 valid, bit1 inclusive, bit2 parity};
-//           a lane reads 16 descriptors with one 16-byte load -> 512 tiles per round
-//   chain 2 (structural count): one uint32 aggregate per tile {bit31 valid, count}
-//           -> 4 per lane, 128 tiles per round -- plus one uint64 inclusive prefix per tile
-//           {bit63 valid}; a lane checks the prefix just in front of its group.
-// The unit of both chains is a TILE (all slabs of one CTA iteration): only one warp per CTA
-// polls, which keeps the descriptor lines from becoming an L2 hot spot.
+// look-back chains over TILES (all slabs of one CTA iteration; only the scan warp of a CTA
+// publishes and polls).  Every tile owns one descriptor SLOT per chain, and the slots are
+// S1_DESC_STRIDE bytes apart, i.e. in different L2 lines: with the descriptors of 128 tiles packed
+// into one line (the previous layout) 148 CTAs published into and polled the same line at the
+// same moment, and a poll issued during that burst took microseconds.
+//   chain 1 (in-string parity): uint32 {bit0 valid, bit1 inclusive, bit2 parity}
+//   chain 2 (structural count): 16 bytes {uint32 aggregate | bit31 valid, pad, uint64 inclusive
+//            prefix | bit63 valid}
+// A lane inspects S1_LB_PER_LANE predecessors per round (distance lane + 32 j), all loads in
+// flight at once; with a grid of at most 32 * S1_LB_PER_LANE CTAs the tile this CTA published
+// one iteration ago (always inclusive) is inside the first round.
 // ---------------------------------------------------------------------------------
+#ifndef SJ_S1_DESC_STRIDE
+#define SJ_S1_DESC_STRIDE 128
+#endif
+constexpr int S1_DESC_STRIDE = SJ_S1_DESC_STRIDE;
+constexpr int S1_LB_PER_LANE = 5;
 constexpr uint32_t DP_VALID = 1, DP_INCL = 2, DP_PAR = 4;
 constexpr uint32_t DA_VALID = 0x80000000u;
 constexpr uint64_t DI_VALID = 1ull << 63;
@@ -652,31 +660,22 @@ __device__ __forceinline__ uint4 ld_relaxed_v4(const void* p) {
                  : "memory");
     return v;
 }
-__device__ __forceinline__ void st_relaxed_u8(uint8_t* p, uint32_t v) {
-    asm volatile("st.relaxed.gpu.global.u8 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ uint32_t* par_slot(uint8_t* dpar, int tile) {
+    return reinterpret_cast<uint32_t*>(dpar + (size_t)tile * S1_DESC_STRIDE);
 }
+__device__ __forceinline__ uint8_t* cnt_slot(uint8_t* dcnt, int tile) { return dcnt + (size_t)tile * S1_DESC_STRIDE; }
 
-// bit k of each of the 16 bytes of q -> 16-bit mask (byte i -> bit i)
-__device__ __forceinline__ uint32_t gather_bit16(const uint4& q, int k) {
-    const uint32_t M = 0x10204080u;  // flags at bits 0,8,16,24 -> bits 28..31
-    uint32_t a = (((q.x >> k) & 0x01010101u) * M) >> 28;
-    uint32_t b = (((q.y >> k) & 0x01010101u) * M) >> 28;
-    uint32_t c = (((q.z >> k) & 0x01010101u) * M) >> 28;
-    uint32_t d = (((q.w >> k) & 0x01010101u) * M) >> 28;
-    return a | (b << 4) | (c << 8) | (d << 12);
-}
-
-// exclusive in-string parity at the entry of `slab` (slab > 0)
-__device__ __forceinline__ uint32_t lookback_parity(const uint8_t* dpar, int slab, unsigned long long* prof = nullptr) {
+// quote parity of everything in front of `tile` (tile > 0)
+__device__ __forceinline__ uint32_t lookback_parity(uint8_t* dpar, int tile, unsigned long long* prof = nullptr) {
     const int lane = threadIdx.x & 31;
     uint32_t par = 0;
 #ifdef SJ_PROFILE_PHASES
     unsigned long long nspin = 0, nround = 0;
 #endif
-    for (int g = slab >> 4;; g -= 32) {  // lane L inspects the 16-slab group g - L
-        const int grp = g - lane;
-        uint32_t V, I, P;
+    for (int base = tile - 1;; base -= 32 * S1_LB_PER_LANE) {
+        uint32_t d[S1_LB_PER_LANE];
         bool again = false;
+        uint32_t ok;
 #ifdef SJ_PROFILE_PHASES
         nround++;
 #endif
@@ -686,51 +685,44 @@ __device__ __forceinline__ uint32_t lookback_parity(const uint8_t* dpar, int sla
 #endif
             if (SJ_SPIN_SLEEP && (again || SJ_SPIN_FIRST)) __nanosleep(SJ_SPIN_SLEEP);
             again = true;
-            if (grp >= 0) {
-                uint4 q = ld_relaxed_v4(dpar + (size_t)grp * 16);
-                V = gather_bit16(q, 0);
-                I = gather_bit16(q, 1);
-                P = gather_bit16(q, 2);
-                if (grp == (slab >> 4)) {  // own group: only slabs in front of `slab` count
-                    uint32_t keep = (1u << (slab & 15)) - 1;
-                    V |= ~keep & 0xffffu;
-                    I &= keep;
-                    P &= keep;
-                }
-            } else {  // before the message: an inclusive prefix of parity 0
-                V = 0xffffu;
-                I = 0x8000u;
-                P = 0;
+            ok = 1;
+#pragma unroll
+            for (int j = 0; j < S1_LB_PER_LANE; j++) {
+                const int t = base - lane - 32 * j;
+                d[j] = t >= 0 ? ld_relaxed_u32(par_slot(dpar, t)) : (DP_VALID | DP_INCL);  // before the message: parity 0
+                ok &= d[j];
             }
-        } while (__any_sync(FULL, V != 0xffffu));
-        uint32_t has = __ballot_sync(FULL, I != 0);
-        int f = has ? __ffs(has) - 1 : 32;
-        uint32_t contrib = 0;
-        if (lane < f)
-            contrib = __popc(P) & 1;
-        else if (lane == f)
-            contrib = __popc(P >> (31 - __clz(I))) & 1;  // the inclusive slab and every slab after it
-        par ^= __popc(__ballot_sync(FULL, contrib)) & 1;
+        } while (__any_sync(FULL, !(ok & DP_VALID)));
+#pragma unroll
+        for (int j = 0; j < S1_LB_PER_LANE; j++) {  // nearest predecessors first
+            const uint32_t I = __ballot_sync(FULL, (d[j] & DP_INCL) != 0);
+            const uint32_t P = __ballot_sync(FULL, (d[j] & DP_PAR) != 0);
+            if (I == 0) {
+                par ^= __popc(P) & 1;
+            } else {  // the nearest inclusive descriptor: it and everything nearer
+                const uint32_t f = __ffs(I) - 1;
+                par ^= __popc(P & (0xffffffffu >> (31 - f))) & 1;
 #ifdef SJ_PROFILE_PHASES
-        if (has && prof && lane == 0) atomicAdd(prof + 9, nspin), atomicAdd(prof + 10, nround);
+                if (prof && lane == 0) atomicAdd(prof + 9, nspin), atomicAdd(prof + 10, nround);
 #endif
-        if (has) return par;
+                return par;
+            }
+        }
     }
 }
 
 // number of structurals in all tiles in front of `tile` (tile > 0)
-__device__ __forceinline__ uint64_t lookback_count(const uint32_t* dagg, const uint64_t* dinc, int tile,
-                                               unsigned long long* prof = nullptr) {
+__device__ __forceinline__ uint64_t lookback_count(uint8_t* dcnt, int tile, unsigned long long* prof = nullptr) {
     const int lane = threadIdx.x & 31;
     uint64_t total = 0;
 #ifdef SJ_PROFILE_PHASES
     unsigned long long nspin = 0, nround = 0;
 #endif
-    for (int g = tile >> 2;; g -= 32) {  // lane L inspects the 4-tile group g - L
-        const int grp = g - lane;
-        uint32_t sum = 0, valid = 1;
-        uint64_t inc = 0;
+    for (int base = tile - 1;; base -= 32 * S1_LB_PER_LANE) {
+        uint32_t agg[S1_LB_PER_LANE];
+        uint64_t inc[S1_LB_PER_LANE];
         bool again = false;
+        uint32_t ok;
 #ifdef SJ_PROFILE_PHASES
         nround++;
 #endif
@@ -740,36 +732,36 @@ __device__ __forceinline__ uint64_t lookback_count(const uint32_t* dagg, const u
 #endif
             if (SJ_SPIN_SLEEP && (again || SJ_SPIN_FIRST)) __nanosleep(SJ_SPIN_SLEEP);
             again = true;
-            if (grp >= 0) {
-                uint4 q = ld_relaxed_v4(dagg + (size_t)grp * 4);
-                inc = grp > 0 ? ld_relaxed_u64(dinc + (size_t)grp * 4 - 1) : DI_VALID;
-                uint32_t w[4] = {q.x, q.y, q.z, q.w};
-                if (grp == (tile >> 2)) {  // own group: drop tiles >= tile (pretend valid, count 0)
-                    const int keep = tile & 3;
+            ok = DA_VALID;
 #pragma unroll
-                    for (int i = 0; i < 4; i++)
-                        if (i >= keep) w[i] = DA_VALID;
+            for (int j = 0; j < S1_LB_PER_LANE; j++) {
+                const int t = base - lane - 32 * j;
+                if (t >= 0) {
+                    const uint4 q = ld_relaxed_v4(cnt_slot(dcnt, t));
+                    agg[j] = q.x;
+                    inc[j] = ((uint64_t)q.w << 32) | q.z;
+                } else {  // before the message: prefix 0
+                    agg[j] = DA_VALID;
+                    inc[j] = DI_VALID;
                 }
-                valid = (w[0] & w[1] & w[2] & w[3] & DA_VALID) != 0;
-                sum = (w[0] & ~DA_VALID) + (w[1] & ~DA_VALID) + (w[2] & ~DA_VALID) + (w[3] & ~DA_VALID);
-            } else {
-                valid = 1;
-                sum = 0;
-                inc = DI_VALID;  // before the message: prefix 0
+                ok &= agg[j];
             }
-        } while (__any_sync(FULL, !valid));
-        uint32_t has = __ballot_sync(FULL, (inc & DI_VALID) != 0);
-        int f = has ? __ffs(has) - 1 : 31;
-        uint64_t v = lane <= f ? sum : 0;
+        } while (__any_sync(FULL, !(ok & DA_VALID)));
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
-        total += v;
-        if (has) {
+        for (int j = 0; j < S1_LB_PER_LANE; j++) {  // nearest predecessors first
+            const uint32_t I = __ballot_sync(FULL, (inc[j] & DI_VALID) != 0);
+            const uint32_t f = I ? __ffs(I) - 1 : 32;  // nearest tile with an inclusive prefix
+            uint32_t v = (uint32_t)lane < f ? (agg[j] & ~DA_VALID) : 0;
+#pragma unroll
+            for (int dd = 16; dd > 0; dd >>= 1) v += __shfl_xor_sync(FULL, v, dd);
+            total += v;
+            if (I) {
+                const uint32_t lo = __shfl_sync(FULL, (uint32_t)inc[j], f), hi = __shfl_sync(FULL, (uint32_t)(inc[j] >> 32), f);
 #ifdef SJ_PROFILE_PHASES
-            if (prof && lane == 0) atomicAdd(prof + 12, nspin), atomicAdd(prof + 13, nround);
+                if (prof && lane == 0) atomicAdd(prof + 12, nspin), atomicAdd(prof + 13, nround);
 #endif
-            uint64_t pre = __shfl_sync(FULL, inc, f) & ~DI_VALID;
-            return total + pre;
+                return total + ((((uint64_t)hi << 32) | lo) & ~DI_VALID);
+            }
         }
     }
 }
@@ -896,9 +888,8 @@ struct Stage1Params {
     uint64_t len;
     uint32_t* out;       // positions (or deltas)
     uint64_t out_cap;
-    uint8_t* dpar;       // [ntiles rounded up to 16] zeroed: chain-1 descriptors
-    uint32_t* dagg;      // [ntiles rounded up to 4] zeroed: chain-2 aggregates
-    uint64_t* dinc;      // [ntiles] zeroed: chain-2 inclusive prefixes
+    uint8_t* dpar;       // [ntiles * S1_DESC_STRIDE] zeroed: chain-1 descriptor slots
+    uint8_t* dcnt;       // [ntiles * S1_DESC_STRIDE] zeroed: chain-2 descriptor slots
     uint32_t* lastp1;    // [ntiles] position + 1 of the tile's last structural (0 = none)
     uint32_t* bsmap;     // optional: bit k = 64-byte block k contains a backslash (lets stage 2 skip the string scan)
     Stage1Result* result;
@@ -1023,13 +1014,13 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
             if (have_prev) {  // every tile in front of prev_tile published its count one iteration ago
 #ifdef SJ_PROFILE_PHASES
                 unsigned long long lb_t1 = clock64();
-                if (prev_tile > 0) tb = lookback_count(p.dagg, p.dinc, prev_tile, p.prof);
+                if (prev_tile > 0) tb = lookback_count(p.dcnt, prev_tile, p.prof);
                 if (lane == 0) atomicAdd(p.prof + 11, clock64() - lb_t1);
 #else
-                if (prev_tile > 0) tb = lookback_count(p.dagg, p.dinc, prev_tile);
+                if (prev_tile > 0) tb = lookback_count(p.dcnt, prev_tile);
 #endif
                 if (lane == 0) {
-                    st_relaxed_u64(p.dinc + prev_tile, DI_VALID | (tb + prev_tile_count));
+                    st_relaxed_u64(reinterpret_cast<uint64_t*>(cnt_slot(p.dcnt, prev_tile) + 8), DI_VALID | (tb + prev_tile_count));
                     if (prev_tile == p.ntiles - 1) {
                         p.result->n_idx = (uint32_t)(tb + prev_tile_count);
                         p.result->ends_in_string = prev_par_out;
@@ -1051,7 +1042,7 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
             uint32_t tin = 0;
             if (cur) {
                 if (lane == 0)
-                    st_relaxed_u8(p.dpar + tile, DP_VALID | (tile == 0 ? DP_INCL : 0) | (tile_par ? DP_PAR : 0));
+                    st_relaxed_u32(par_slot(p.dpar, tile), DP_VALID | (tile == 0 ? DP_INCL : 0) | (tile_par ? DP_PAR : 0));
                 if (tile > 0) {
 #ifdef SJ_PROFILE_PHASES
                     unsigned long long lb_t0 = clock64();
@@ -1060,7 +1051,7 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
 #else
                     tin = lookback_parity(p.dpar, tile);
 #endif
-                    if (lane == 0) st_relaxed_u8(p.dpar + tile, DP_VALID | DP_INCL | ((tile_par ^ tin) ? DP_PAR : 0));
+                    if (lane == 0) st_relaxed_u32(par_slot(p.dpar, tile), DP_VALID | DP_INCL | ((tile_par ^ tin) ? DP_PAR : 0));
                 }
             }
             if (lane < S1_WARPS) s_parin[lane] = tin ^ (__popc(parbits & lanemask_lt()) & 1);
@@ -1087,7 +1078,7 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
             prev_wlast = below ? got : 0;
             if (cur && lane == 0) {  // chain-2 aggregate; its look-back runs one iteration later
                 p.lastp1[tile] = tile_last1;
-                st_relaxed_u32(p.dagg + tile, DA_VALID | tile_count);
+                st_relaxed_u32(reinterpret_cast<uint32_t*>(cnt_slot(p.dcnt, tile)), DA_VALID | tile_count);
             }
             have_prev = cur;
             prev_tile = tile;
@@ -1353,8 +1344,8 @@ __global__ void stage1_finish_kernel(const Stage1Params p) {
     uint32_t prev = p.lastp1[t];
     while (prev == 0 && t > 0) prev = p.lastp1[--t];
     if (prev == 0) return;  // no structural in front: the first delta stays pos + 1
-    const uint64_t incl = p.dinc[s] & ~DI_VALID;
-    const uint64_t first = incl - (p.dagg[s] & ~DA_VALID);
+    const uint64_t incl = *reinterpret_cast<const uint64_t*>(cnt_slot(p.dcnt, s) + 8) & ~DI_VALID;
+    const uint64_t first = incl - (*reinterpret_cast<const uint32_t*>(cnt_slot(p.dcnt, s)) & ~DA_VALID);
     if (first < p.out_cap) p.out[first] -= prev;  // (pos + 1) - (prev_pos + 1)
 }
 
