@@ -500,8 +500,7 @@ __device__ __forceinline__ uint32_t flatten_step(uint64_t S, uint32_t blockpos, 
     return total;
 }
 
-// Positions of the structurals of one 2 KiB step, staged into `chunk` (the step's own, already
-// consumed, input bytes: 512 entries).  Extraction runs from the top bit down (one FLO per
+// Positions of the structurals of one 2 KiB step, staged into `chunk` (room for `cap` entries).  Extraction runs from the top bit down (one FLO per
 // structural, no bit reversal) as two independent chains (the two 32-bit halves of the lane's
 // mask) with predicated stores.  Returns the step's count (warp-uniform); nothing is staged if it
 // exceeds `cap` (more than one structural per 4 bytes).
@@ -545,15 +544,24 @@ __device__ __forceinline__ uint32_t extract_step(uint64_t S, uint32_t pos0, uint
 // Coalesced copy-out of one staged step; deltas (flatten_bits_amd64.s:38-40) are formed here from
 // neighbouring staged positions, so the divergent extraction loop carries no delta arithmetic.
 template <bool DELTAS>
-__device__ __forceinline__ void copy_out_step(const uint32_t* chunk, uint32_t n, uint32_t* __restrict__ dst, uint32_t& prev_last) {
+__device__ __forceinline__ void copy_out(const uint32_t* stage, uint32_t n, uint32_t* __restrict__ dst, uint32_t prev_last) {
     const uint32_t lane = threadIdx.x & 31;
-#pragma unroll 4
-    for (uint32_t k = lane; k < n; k += 32) {
-        uint32_t v = chunk[k];
-        if (DELTAS) v -= k ? chunk[k - 1] : prev_last;
+    uint32_t k = lane;
+    for (; k + 96 < n; k += 128) {  // four coalesced 128-byte rows per trip
+        uint32_t v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            v[u] = stage[k + 32 * u];
+            if (DELTAS) v[u] -= (k + 32 * u) ? stage[k + 32 * u - 1] : prev_last;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) dst[k + 32 * u] = v[u];
+    }
+    for (; k < n; k += 32) {
+        uint32_t v = stage[k];
+        if (DELTAS) v -= k ? stage[k - 1] : prev_last;
         dst[k] = v;
     }
-    if (DELTAS && n) prev_last = chunk[n - 1];
 }
 
 // Flatten of a whole slab through the warp's staging area.  Positions are extracted from the top
@@ -913,25 +921,6 @@ __device__ __forceinline__ void load_block_words(const uint8_t* buf, uint32_t la
 }
 
 // bytes at or beyond `len` read as 0x20 (find_structural_bits_amd64.s:134-155)
-__device__ __forceinline__ void mask_tail(uint32_t (&w)[16], uint32_t lane, uint64_t blockpos, uint64_t len) {
-    if (blockpos + 64 <= len) return;
-    const uint32_t r = (lane >> 1) & 3;
-#pragma unroll
-    for (int k = 0; k < 16; k++) {
-        uint32_t chunk = ((k >> 2) + r) & 3;
-        uint64_t wpos = blockpos + chunk * 16 + (k & 3) * 4;
-        uint32_t v = w[k];
-        if (wpos >= len) {
-            v = 0x20202020u;
-        } else if (wpos + 4 > len) {
-            uint32_t keep = (uint32_t)(len - wpos);  // 1..3 valid bytes
-            uint32_t m = (1u << (8 * keep)) - 1;
-            v = (v & m) | (0x20202020u & ~m);
-        }
-        w[k] = v;
-    }
-}
-
 template <bool NDJSON, bool DELTAS>
 __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_kernel(const Stage1Params p) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -1140,36 +1129,25 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
         }
         SJ_PROF_MARK(2)
 
+        // the last tile: bytes past the end of the message read as spaces (find_structural_bits_amd64.s:167);
+        // padded in shared memory so that the hot loop carries no tail handling at all
+        if (tail_tile && active && p.len - slab_start < S1_SLAB_BYTES) {
+            uint8_t* wbuf = smem + (size_t)b * S1_TILE_BYTES + (size_t)warp * S1_SLAB_BYTES;
+            for (uint32_t o = (uint32_t)(p.len - slab_start) + lane; o < S1_SLAB_BYTES; o += 32) wbuf[o] = 0x20;
+            __syncwarp();
+        }
+
         // ---------------- phase A: classify, escape analysis, slab quote parity ----------------
-        // ... interleaved, step by step, with the EXTRACTION of the previous tile's structurals: the
-        // classification is all ALU-pipe work, the extraction is FLO / shared-store work, and warps
-        // drift apart inside this region (the extraction loop's trip count differs per warp), so
-        // the two instruction mixes overlap on the SM instead of alternating.  The positions of
-        // step s are staged over the input bytes of step s of this tile, which are dead as soon as
-        // every lane of the warp has loaded them.
         uint64_t qb[S1_STEPS], st[S1_STEPS], ws[S1_STEPS], ct[S1_STEPS], nl[S1_STEPS], bsm[S1_STEPS];
-        uint32_t tot_prev[S1_STEPS];  // structurals per step of the previous tile's slab (warp-uniform)
-        uint32_t dense = 0;           // a step of the previous tile did not fit its staging chunk
         uint32_t slab_par = 0;
         uint32_t* const stage = reinterpret_cast<uint32_t*>(smem + (size_t)b * S1_TILE_BYTES + (size_t)warp * S1_SLAB_BYTES);
         const uint32_t pslab_pos = (uint32_t)(((uint64_t)prev_tile * S1_WARPS + warp) * S1_SLAB_BYTES);
 #pragma unroll
         for (int s = 0; s < S1_STEPS; s++) {
             qb[s] = st[s] = ws[s] = ct[s] = nl[s] = bsm[s] = 0;
-            tot_prev[s] = 0;
-            uint32_t w[16];
-            if (active) load_block_words(buf + s * S1_STEP_BYTES, lane, w);
-#ifdef SJ_INTERLEAVE  // extraction of the previous tile step by step between the classifications
-            if (have_prev) {
-                __syncwarp();  // every lane holds its bytes of step s: the chunk may be overwritten
-                tot_prev[s] = extract_step(S_prev[s], pslab_pos + s * S1_STEP_BYTES + 64 * lane, stage + s * (S1_STEP_BYTES / 4),
-                                           S1_STEP_BYTES / 4);
-                dense |= tot_prev[s] > S1_STEP_BYTES / 4;
-            }
-#endif
             if (active) {
-                const uint64_t blockpos = slab_start + (uint64_t)s * S1_STEP_BYTES + 64 * lane;
-                if (tail_tile) mask_tail(w, lane, blockpos, p.len);  // CTA-uniform: only the last tile has a tail
+                uint32_t w[16];
+                load_block_words(buf + s * S1_STEP_BYTES, lane, w);
                 PlaneMasks m = classify_block_planes(w);
                 bsm[s] = rotl16x((uint32_t)m.bs, (uint32_t)(m.bs >> 32), rsel);
                 qb[s] = rotl16x((uint32_t)m.qt, (uint32_t)(m.qt >> 32), rsel);  // raw quotes; escaped ones are removed in pass 2
@@ -1214,20 +1192,23 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
         }
         SJ_PROF_MARK(3)
         const uint32_t peek_next = peek_load(tile + G);
-#ifndef SJ_INTERLEAVE
         // ---------------- extraction of the previous tile's structurals ----------------
-        // positions of step s are staged over the input bytes of step s of the warp's own slab
-        // (dead: this warp alone read them, in phase A above)
+        // the positions are staged over the warp's own slab of this tile (dead: this warp alone read
+        // it, in phase A above)
+        uint32_t staged = 0;  // entries staged (warp-uniform)
+        uint32_t dense = 0;   // more than one structural per 4 bytes: the slab does not fit its own staging area
         if (have_prev) {
             __syncwarp();
 #pragma unroll
             for (int s = 0; s < S1_STEPS; s++) {
-                tot_prev[s] = extract_step(S_prev[s], pslab_pos + s * S1_STEP_BYTES + 64 * lane, stage + s * (S1_STEP_BYTES / 4),
-                                           S1_STEP_BYTES / 4);
-                dense |= tot_prev[s] > S1_STEP_BYTES / 4;
+                if (!dense) {
+                    const uint32_t n = extract_step(S_prev[s], pslab_pos + s * S1_STEP_BYTES + 64 * lane, stage + staged,
+                                                    S1_SLAB_BYTES / 4 - staged);
+                    dense = n > S1_SLAB_BYTES / 4 - staged;
+                    staged += n;
+                }
             }
         }
-#endif
         SJ_PROF_MARK(4)
         mbar_wait(bar_S, itpar);  // output offsets of the previous tile (chain 2, run by the scan warp under phase A)
         SJ_PROF_MARK(1)
@@ -1242,12 +1223,7 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
             if (off + prev_slab_count > p.out_cap) {  // warp-uniform
                 if (lane == 0) atomicOr(&p.result->overflow, 1u);
             } else if (!dense) {
-                uint32_t* dst = p.out + off;
-#pragma unroll
-                for (int s = 0; s < S1_STEPS; s++) {
-                    copy_out_step<DELTAS>(stage + s * (S1_STEP_BYTES / 4), tot_prev[s], dst, prev_last);
-                    dst += tot_prev[s];
-                }
+                copy_out<DELTAS>(stage, staged, p.out + off, prev_last);
             } else {  // more than one structural per 4 bytes somewhere in the slab: unstaged path
                 flatten_slab_staged<DELTAS, S1_STEPS>(S_prev, pslab_pos, p.out + off, prev_last, stage, S1_SLAB_BYTES / 4);
             }
