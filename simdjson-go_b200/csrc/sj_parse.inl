@@ -212,7 +212,7 @@ static int run_stage2(sj_ctx* c, const uint8_t* d_msg, size_t len, const uint32_
             lvl_total += sz;
         }
     }
-    size_t need2 = Carver::need({nb * 4, nb * 4, nb * 4, nb * 4, (lvl_total + 8) * 4, ((size_t)tot.n_records + 2) * 4});
+    size_t need2 = Carver::need({nb * 4, nb * 4, nb * 4, nb * 4, nb * 4, nb, (lvl_total + 8) * 4, ((size_t)tot.n_records + 2) * 4});
     rc = c->s2b.reserve(need2);
     if (rc) return rc;
     Carver k2(c->s2b.p);
@@ -220,6 +220,8 @@ static int run_stage2(sj_ctx* c, const uint8_t* d_msg, size_t len, const uint32_
     p.brk_tp = k2.take<uint32_t>(nb);
     p.brk_depth = k2.take<int32_t>(nb);
     p.par = k2.take<int32_t>(nb);
+    p.enc_after = k2.take<int32_t>(nb);
+    p.ctx_after = k2.take<uint8_t>(nb);
     int32_t* lvl_mem = k2.take<int32_t>(lvl_total + 8);
     p.rootpos = k2.take<uint32_t>((size_t)tot.n_records + 2);
 
@@ -246,7 +248,8 @@ static int run_stage2(sj_ctx* c, const uint8_t* d_msg, size_t len, const uint32_
             sz = nsz;
         }
         s2_ansv_kernel<<<(unsigned)((nb + S2_THREADS - 1) / S2_THREADS), S2_THREADS, 0, c->stream>>>(L, p.par);
-        c->launches++;
+        s2_scope_kernel<<<(unsigned)((nb + S2_THREADS - 1) / S2_THREADS), S2_THREADS, 0, c->stream>>>(p, (uint32_t)nb);
+        c->launches += 2;
     }
     s2_grammar_kernel<<<ntiles, S2_THREADS, 0, c->stream>>>(p);
     {

@@ -42,6 +42,10 @@ constexpr uint32_t AUX_COPY = 0x80000000u;              // string goes to the st
 constexpr uint32_t AUX_ESC = 0x40000000u;               // string contains escapes (source length != unescaped length)
 constexpr uint32_t AUX_LEN = 0x3fffffffu;
 constexpr int S2_THREADS = 256;
+#ifndef SJ_S2_SHORT_STRING
+#define SJ_S2_SHORT_STRING 24
+#endif
+constexpr uint32_t S2_SHORT_STRING = SJ_S2_SHORT_STRING;  // strings up to this length are copied by their own thread
 
 struct ScanVal {
     uint32_t w;     // tape words
@@ -117,6 +121,74 @@ __device__ __forceinline__ ScanVal block_exclusive_scan(ScanVal v, ScanVal& tota
     return r;
 }
 
+// The same scan for the per-structural contributions of ONE block (K2a, K2c): every field but
+// `str` is tiny (w <= 2, brk, rec <= 1, depth in {-1,0,1} per structural), so four of the five
+// fields travel as 16-bit lanes of one 64-bit word (depth biased by +1 per thread) and the scan
+// moves 3 registers per step instead of 5.  NT <= 8192 keeps every lane below 2^16.
+template <int NT>
+__device__ __forceinline__ ScanVal block_exclusive_scan_small(const ScanVal& v, ScanVal& total) {
+    constexpr int NW = NT / 32;
+    __shared__ unsigned long long wp_pk[NW + 1];
+    __shared__ uint32_t wp_str[NW + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned long long own = (unsigned long long)v.w | ((unsigned long long)v.brk << 16) | ((unsigned long long)v.rec << 32) |
+                                   ((unsigned long long)(uint32_t)(v.depth + 1) << 48);
+    unsigned long long pk = own;
+    uint32_t st = v.str;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long tp = __shfl_up_sync(FULL, pk, d);
+        const uint32_t ts = __shfl_up_sync(FULL, st, d);
+        if (lane >= d) {
+            pk += tp;
+            st += ts;
+        }
+    }
+    if (lane == 31) {
+        wp_pk[warp + 1] = pk;
+        wp_str[warp + 1] = st;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long a = lane < NW ? wp_pk[lane + 1] : 0ull;
+        uint32_t b = lane < NW ? wp_str[lane + 1] : 0u;
+#pragma unroll
+        for (int d = 1; d < NW; d <<= 1) {
+            const unsigned long long ta = __shfl_up_sync(FULL, a, d);
+            const uint32_t tb = __shfl_up_sync(FULL, b, d);
+            if (lane >= d) {
+                a += ta;
+                b += tb;
+            }
+        }
+        __syncwarp();
+        if (lane < NW) {
+            wp_pk[lane + 1] = a;  // inclusive: sum of warps <= lane
+            wp_str[lane + 1] = b;
+        }
+        if (lane == 0) {
+            wp_pk[0] = 0;
+            wp_str[0] = 0;
+        }
+    }
+    __syncthreads();
+    const unsigned long long tot = wp_pk[NW];
+    total.w = (uint32_t)(tot & 0xffff);
+    total.brk = (uint32_t)((tot >> 16) & 0xffff);
+    total.rec = (uint32_t)((tot >> 32) & 0xffff);
+    total.depth = (int32_t)(tot >> 48) - NT;
+    total.str = wp_str[NW];
+    const unsigned long long ex = wp_pk[warp] + pk - own;  // exclusive prefix of this thread
+    ScanVal r;
+    r.w = (uint32_t)(ex & 0xffff);
+    r.brk = (uint32_t)((ex >> 16) & 0xffff);
+    r.rec = (uint32_t)((ex >> 32) & 0xffff);
+    r.depth = (int32_t)(ex >> 48) - (int32_t)threadIdx.x;
+    r.str = wp_str[warp] + st - v.str;
+    __syncthreads();  // the shared arrays may be reused by the next call
+    return r;
+}
+
 struct Stage2Result {
     uint64_t tape_len;     // total tape words (including both root words of the last record)
     uint64_t strings_len;  // bytes of the string buffer
@@ -147,6 +219,8 @@ struct Stage2Params {
     uint32_t* brk_tp;    // [nb] tape slot
     int32_t* brk_depth;  // [nb] depth before the bracket  (= level 0 of the min hierarchy)
     int32_t* par;        // [nb] nearest previous bracket with smaller depth (-1 none)
+    int32_t* enc_after;  // [nb] innermost scope that is open right AFTER bracket k (bracket index, -1 = top level)
+    uint8_t* ctx_after;  // [nb] its kind (CTX_ROOT / CTX_OBJ / CTX_ARR)
     uint32_t* rootpos;   // [records + 1] tape slot of each record's root-open word
     // outputs
     uint64_t* tape;
@@ -387,12 +461,14 @@ __global__ void __launch_bounds__(S2_THREADS) s2_classify_measure_kernel(const S
                     e--;
                 }
                 if (e > pos && p.msg[e] == '"') {
-                    fast = true;
-                    for (uint64_t blk = (pos + 1) >> 6; blk <= (e >> 6); blk++)
-                        if ((p.bsmap[blk >> 5] >> (blk & 31)) & 1) {
-                            fast = false;
-                            break;
-                        }
+                    // any backslash block among blocks [b0, b1] of K1's map?  (one word in practice)
+                    const uint32_t b0 = (uint32_t)((pos + 1) >> 6), b1 = (uint32_t)(e >> 6);
+                    uint32_t hit = 0;
+                    for (uint32_t wd = b0 >> 5; wd <= (b1 >> 5) && !hit; wd++) {
+                        const uint32_t lo_bit = wd == (b0 >> 5) ? (b0 & 31) : 0, hi_bit = wd == (b1 >> 5) ? (b1 & 31) : 31;
+                        hit = p.bsmap[wd] & ((0xffffffffu >> (31 - hi_bit)) & (0xffffffffu << lo_bit));
+                    }
+                    fast = hit == 0;
                     if (fast) {
                         sl = dl = e - pos - 1;
                         ok = true;
@@ -422,7 +498,7 @@ __global__ void __launch_bounds__(S2_THREADS) s2_classify_measure_kernel(const S
         v = contribution(t, aux, next_t);
     }
     ScanVal total;
-    block_exclusive_scan<S2_THREADS>(v, total);
+    block_exclusive_scan_small<S2_THREADS>(v, total);
     if (threadIdx.x == 0) p.tile_sum[blockIdx.x] = total;
 }
 
@@ -475,7 +551,7 @@ __global__ void __launch_bounds__(S2_THREADS) s2_emit_kernel(const Stage2Params 
         v = contribution(t, aux, next_t);
     }
     ScanVal total;
-    ScanVal e = block_exclusive_scan<S2_THREADS>(v, total);
+    ScanVal e = block_exclusive_scan_small<S2_THREADS>(v, total);
     const uint32_t tile = blockIdx.x;
     e = sv_add(e, sv_add(p.tile_pre[tile], p.grp_pre[tile >> 10]));
     const uint64_t tp = 1 + (uint64_t)e.w;  // slot 0 is the first root word
@@ -505,10 +581,18 @@ __global__ void __launch_bounds__(S2_THREADS) s2_emit_kernel(const Stage2Params 
                     if (aux & AUX_ESC) {
                         StrCursor s{p.msg + pos + 1, p.len - pos - 1};
                         string_copy(s, p.strings + e.str);
-                    } else if (dl <= 12) {  // short: cheaper than a slot in the cooperative copy
+                    } else if (dl <= S2_SHORT_STRING) {  // short: cheaper than a slot in the cooperative copy
                         const uint8_t* src = p.msg + pos + 1;
                         uint8_t* dst = p.strings + e.str;
-                        for (uint32_t q = 0; q < dl; q++) dst[q] = src[q];
+                        uint32_t q = 0;
+                        for (; q + 4 <= dl; q += 4) {  // four loads in flight, immediate offsets
+                            const uint8_t c0 = src[q], c1 = src[q + 1], c2 = src[q + 2], c3 = src[q + 3];
+                            dst[q] = c0;
+                            dst[q + 1] = c1;
+                            dst[q + 2] = c2;
+                            dst[q + 3] = c3;
+                        }
+                        for (; q < dl; q++) dst[q] = src[q];
                     } else {
                         fast_len = dl;
                     }
@@ -669,6 +753,24 @@ __device__ __forceinline__ bool transition_ok(uint32_t ctx, uint32_t pp, uint32_
     return false;
 }
 
+// Scope that is open right after each bracket: one thread per BRACKET does the pointer chase
+// (bracket -> its open -> that open's parent) once, so that K2e -- one thread per structural, 10-40x
+// more threads -- needs a single load of the result instead of a chain of five dependent ones.
+__global__ void __launch_bounds__(S2_THREADS) s2_scope_kernel(const Stage2Params p, uint32_t nb) {
+    const uint32_t k = blockIdx.x * S2_THREADS + threadIdx.x;
+    if (k >= nb) return;
+    const uint32_t bt = p.typ[p.brk_i[k]];
+    int32_t enc;
+    if (bt == T_OBJ_OPEN || bt == T_ARR_OPEN) {
+        enc = (int32_t)k;
+    } else {
+        const int32_t m = p.par[k];  // the close's open
+        enc = m >= 0 ? p.par[m] : -1;
+    }
+    p.enc_after[k] = enc;
+    p.ctx_after[k] = enc >= 0 ? (p.typ[p.brk_i[enc]] == T_OBJ_OPEN ? CTX_OBJ : CTX_ARR) : CTX_ROOT;
+}
+
 __global__ void __launch_bounds__(S2_THREADS) s2_grammar_kernel(const Stage2Params p) {
     __shared__ uint32_t s_wcnt[S2_THREADS / 32];
     const uint32_t i = blockIdx.x * S2_THREADS + threadIdx.x;
@@ -689,20 +791,14 @@ __global__ void __launch_bounds__(S2_THREADS) s2_grammar_kernel(const Stage2Para
     const uint32_t k = before - 1;  // 0xffffffff when no bracket precedes
     const uint32_t pv = i >= 1 ? p.typ[i - 1] : (uint32_t)T_START;
     const uint32_t ppv = i >= 2 ? p.typ[i - 2] : (uint32_t)T_START;
-    int32_t enclosing = -1;  // bracket index of the innermost open scope before i
-    if (is_brk) {
-        enclosing = p.par[k + 1];  // own bracket index is k + 1
-    } else if (k != 0xffffffffu) {
-        const uint32_t bt = p.typ[p.brk_i[k]];
-        if (bt == T_OBJ_OPEN || bt == T_ARR_OPEN) {
-            enclosing = (int32_t)k;
-        } else {
-            const int32_t m = p.par[k];  // the close's open
-            enclosing = m >= 0 ? p.par[m] : -1;
-        }
-    }
+    // the scope this structural sits in = the scope open after the previous bracket (for a closing
+    // bracket that is the scope it closes: its open is the nearest bracket of smaller depth)
     uint32_t ctx = CTX_ROOT;
-    if (enclosing >= 0) ctx = p.typ[p.brk_i[enclosing]] == T_OBJ_OPEN ? CTX_OBJ : CTX_ARR;
+    int32_t enclosing = -1;
+    if (k != 0xffffffffu) {
+        ctx = p.ctx_after[k];
+        if (c == T_OBJ_CLOSE || c == T_ARR_CLOSE) enclosing = p.enc_after[k];
+    }
     if (!transition_ok(ctx, ppv, pv, c)) {
         atomicOr(&p.result->error, 1u);
         return;
