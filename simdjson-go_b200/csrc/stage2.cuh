@@ -581,20 +581,8 @@ __global__ void __launch_bounds__(S2_THREADS) s2_emit_kernel(const Stage2Params 
                     if (aux & AUX_ESC) {
                         StrCursor s{p.msg + pos + 1, p.len - pos - 1};
                         string_copy(s, p.strings + e.str);
-                    } else if (dl <= S2_SHORT_STRING) {  // short: cheaper than a slot in the cooperative copy
-                        const uint8_t* src = p.msg + pos + 1;
-                        uint8_t* dst = p.strings + e.str;
-                        uint32_t q = 0;
-                        for (; q + 4 <= dl; q += 4) {  // four loads in flight, immediate offsets
-                            const uint8_t c0 = src[q], c1 = src[q + 1], c2 = src[q + 2], c3 = src[q + 3];
-                            dst[q] = c0;
-                            dst[q + 1] = c1;
-                            dst[q + 2] = c2;
-                            dst[q + 3] = c3;
-                        }
-                        for (; q < dl; q++) dst[q] = src[q];
                     } else {
-                        fast_len = dl;
+                        fast_len = dl;  // copied by the warp below
                     }
                 } else {
                     atomicOr(&p.result->overflow, 1u);
@@ -622,28 +610,37 @@ __global__ void __launch_bounds__(S2_THREADS) s2_emit_kernel(const Stage2Params 
         default: break;
         }
     }
-    // ---- warp-cooperative copy of the warp's escape-free strings: byte k of their concatenation is
-    // moved by lane k mod 32, so both the reads and the writes of the warp are contiguous runs ----
-    uint32_t finc = fast_len;
+    // ---- warp-cooperative copy of the warp's escape-free strings.  A string's own thread would copy
+    // it byte by byte (one LSU transaction per byte and lane, trip count = the longest string of the
+    // warp).  Instead the strings are queued in shared memory; strings of up to 32 bytes are copied
+    // by groups of 8 lanes (four strings at a time, 8 consecutive bytes per group and step), longer
+    // ones by the whole warp one after another (32 consecutive bytes per step). ----
+    __shared__ uint4 s_q[S2_THREADS];
+    uint4* q = s_q + (threadIdx.x & ~31u);
+    const uint32_t shortm = __ballot_sync(FULL, fast_len != 0 && fast_len <= 32);
+    const uint32_t longm = __ballot_sync(FULL, fast_len > 32);
+    if (shortm | longm) {
+        if (fast_len != 0 && fast_len <= 32) q[__popc(shortm & lanemask_lt())] = make_uint4((uint32_t)pos + 1, e.str, fast_len, 0);
+        __syncwarp();
+        const uint32_t ns = __popc(shortm), g = lane >> 3, b = lane & 7;
+        for (uint32_t r = g; r < ns; r += 4) {
+            const uint4 d = q[r];
+            const uint8_t* src = p.msg + d.x;
+            uint8_t* dst = p.strings + d.y;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        uint32_t up = __shfl_up_sync(FULL, finc, d);
-        if (lane >= d) finc += up;
-    }
-    const uint32_t T = __shfl_sync(FULL, finc, 31);
-    const uint32_t fo = finc - fast_len;  // exclusive offset of this lane's string
-    const uint32_t src0 = (uint32_t)pos + 1, dst0 = e.str;
-    for (uint32_t base = 0; base < T; base += 32) {
-        const uint32_t k = base + lane;
-        int lo = 0, hi = 31;  // largest lane whose offset is <= k
-#pragma unroll
-        for (int step = 0; step < 5; step++) {
-            int mid = (lo + hi + 1) >> 1;
-            uint32_t vm = __shfl_sync(FULL, fo, mid);
-            if (vm <= k) lo = mid; else hi = mid - 1;
+            for (uint32_t o = 0; o < 32; o += 8)
+                if (o + b < d.z) dst[o + b] = src[o + b];
         }
-        const uint32_t so = __shfl_sync(FULL, fo, lo), ss = __shfl_sync(FULL, src0, lo), sd = __shfl_sync(FULL, dst0, lo);
-        if (k < T) p.strings[sd + (k - so)] = p.msg[ss + (k - so)];
+        uint32_t m = longm;
+        while (m) {
+            const int src_lane = __ffs(m) - 1;
+            m &= m - 1;
+            const uint32_t sp = __shfl_sync(FULL, (uint32_t)pos + 1, src_lane), dp = __shfl_sync(FULL, e.str, src_lane),
+                           ln = __shfl_sync(FULL, fast_len, src_lane);
+            const uint8_t* src = p.msg + sp;
+            uint8_t* dst = p.strings + dp;
+            for (uint32_t o = lane; o < ln; o += 32) dst[o] = src[o];
+        }
     }
 }
 
@@ -718,16 +715,16 @@ __global__ void __launch_bounds__(S2_THREADS) s2_ansv_kernel(AnsvLevels L, int32
 // ---------------------------------------------------------------------------------
 enum : uint32_t { CTX_ROOT = 0, CTX_OBJ = 1, CTX_ARR = 2 };
 
-__device__ __forceinline__ bool is_value_start(uint32_t c) {
+__host__ __device__ constexpr bool is_value_start(uint32_t c) {
     return c == T_STRING || c == T_NUMBER || c == T_TRUE || c == T_FALSE || c == T_NULL || c == T_OBJ_OPEN ||
            c == T_ARR_OPEN;
 }
-__device__ __forceinline__ bool is_scalar_or_close(uint32_t c) {
+__host__ __device__ constexpr bool is_scalar_or_close(uint32_t c) {
     return c == T_NUMBER || c == T_TRUE || c == T_FALSE || c == T_NULL || c == T_OBJ_CLOSE || c == T_ARR_CLOSE;
 }
 
 // stage2_build_tape_amd64.go:176-425, restated as "is c allowed after p (after pp) inside ctx"
-__device__ __forceinline__ bool transition_ok(uint32_t ctx, uint32_t pp, uint32_t p, uint32_t c) {
+__host__ __device__ constexpr bool transition_ok(uint32_t ctx, uint32_t pp, uint32_t p, uint32_t c) {
     if (c == T_INVALID) return false;
     if (ctx == CTX_OBJ) {
         if (p == T_OBJ_OPEN) return c == T_STRING || c == T_OBJ_CLOSE;                // object_begin :225-240
@@ -753,6 +750,32 @@ __device__ __forceinline__ bool transition_ok(uint32_t ctx, uint32_t pp, uint32_
     return false;
 }
 
+// transition_ok as a bit table, built at compile time: the previous-previous structural only
+// matters as "was the string before us a key" (pp is '{' or ','), so the index is
+// ((ctx * 2 + is_key) * 14 + p) * 14 + c  -- 1176 bits.  K2e copies it to shared memory and replaces
+// ~100 branchy instructions per structural by one LDS.
+constexpr uint32_t TRANS_NT = 14;  // T_INVALID .. T_START
+constexpr uint32_t TRANS_WORDS = (3 * 2 * TRANS_NT * TRANS_NT + 31) / 32;
+struct TransTable {
+    uint32_t w[TRANS_WORDS];
+};
+__host__ __device__ constexpr uint32_t trans_index(uint32_t ctx, uint32_t is_key, uint32_t p, uint32_t c) {
+    return ((ctx * 2 + is_key) * TRANS_NT + p) * TRANS_NT + c;
+}
+constexpr TransTable make_trans_table() {
+    TransTable t{};
+    for (uint32_t ctx = 0; ctx < 3; ctx++)
+        for (uint32_t k = 0; k < 2; k++)
+            for (uint32_t p = 0; p < TRANS_NT; p++)
+                for (uint32_t c = 0; c < TRANS_NT; c++)
+                    if (transition_ok(ctx, k ? (uint32_t)T_COMMA : (uint32_t)T_INVALID, p, c)) {
+                        const uint32_t i = trans_index(ctx, k, p, c);
+                        t.w[i >> 5] |= 1u << (i & 31);
+                    }
+    return t;
+}
+__constant__ TransTable c_trans = make_trans_table();
+
 // Scope that is open right after each bracket: one thread per BRACKET does the pointer chase
 // (bracket -> its open -> that open's parent) once, so that K2e -- one thread per structural, 10-40x
 // more threads -- needs a single load of the result instead of a chain of five dependent ones.
@@ -773,6 +796,8 @@ __global__ void __launch_bounds__(S2_THREADS) s2_scope_kernel(const Stage2Params
 
 __global__ void __launch_bounds__(S2_THREADS) s2_grammar_kernel(const Stage2Params p) {
     __shared__ uint32_t s_wcnt[S2_THREADS / 32];
+    __shared__ uint32_t s_tr[TRANS_WORDS];
+    if (threadIdx.x < TRANS_WORDS) s_tr[threadIdx.x] = c_trans.w[threadIdx.x];
     const uint32_t i = blockIdx.x * S2_THREADS + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t c = i < p.n ? p.typ[i] : (uint32_t)T_INVALID;
@@ -799,7 +824,8 @@ __global__ void __launch_bounds__(S2_THREADS) s2_grammar_kernel(const Stage2Para
         ctx = p.ctx_after[k];
         if (c == T_OBJ_CLOSE || c == T_ARR_CLOSE) enclosing = p.enc_after[k];
     }
-    if (!transition_ok(ctx, ppv, pv, c)) {
+    const uint32_t ti = trans_index(ctx, (ppv == T_OBJ_OPEN || ppv == T_COMMA) ? 1u : 0u, pv, c);
+    if (!((s_tr[ti >> 5] >> (ti & 31)) & 1)) {  // transition_ok(ctx, ppv, pv, c)
         atomicOr(&p.result->error, 1u);
         return;
     }
