@@ -251,7 +251,7 @@ static int run_stage2(sj_ctx* c, const uint8_t* d_msg, size_t len, const uint32_
         s2_scope_kernel<<<(unsigned)((nb + S2_THREADS - 1) / S2_THREADS), S2_THREADS, 0, c->stream>>>(p, (uint32_t)nb);
         c->launches += 2;
     }
-    s2_grammar_kernel<<<ntiles, S2_THREADS, 0, c->stream>>>(p);
+    s2_grammar_kernel<<<(ntiles + S2E_ITEMS - 1) / S2E_ITEMS, S2_THREADS, 0, c->stream>>>(p);
     {
         const uint64_t nrec = tot.n_records;
         const unsigned blocks = (unsigned)((nrec + 1 + 255) / 256);

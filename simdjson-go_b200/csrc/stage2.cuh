@@ -794,47 +794,67 @@ __global__ void __launch_bounds__(S2_THREADS) s2_scope_kernel(const Stage2Params
     p.ctx_after[k] = enc >= 0 ? (p.typ[p.brk_i[enc]] == T_OBJ_OPEN ? CTX_OBJ : CTX_ARR) : CTX_ROOT;
 }
 
+// Four consecutive structurals per thread (the per-structural work is a handful of instructions
+// behind two dependent loads, so one structural per thread is latency-bound): a block covers
+// 4 * S2_THREADS structurals = four K2b tiles, 64 threads (two warps) per tile.
+constexpr int S2E_ITEMS = 4;
 __global__ void __launch_bounds__(S2_THREADS) s2_grammar_kernel(const Stage2Params p) {
     __shared__ uint32_t s_wcnt[S2_THREADS / 32];
     __shared__ uint32_t s_tr[TRANS_WORDS];
     if (threadIdx.x < TRANS_WORDS) s_tr[threadIdx.x] = c_trans.w[threadIdx.x];
-    const uint32_t i = blockIdx.x * S2_THREADS + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t c = i < p.n ? p.typ[i] : (uint32_t)T_INVALID;
-    const bool is_brk = c >= T_OBJ_OPEN && c <= T_ARR_CLOSE;
-    // index of the nearest bracket strictly before i = (brackets in front of i) - 1: the tile
-    // prefix from K2b plus an in-block ballot count (no per-structural array needed)
-    const uint32_t bal = __ballot_sync(FULL, is_brk);
-    if (lane == 0) s_wcnt[warp] = __popc(bal);
-    __syncthreads();
-    uint32_t before = __popc(bal & lanemask_lt());
+    const uint32_t i0 = (blockIdx.x * S2_THREADS + threadIdx.x) * S2E_ITEMS;
+    // types of the thread's structurals and of the two in front of them
+    uint32_t c[S2E_ITEMS];
+    if (i0 + S2E_ITEMS <= p.n) {
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(p.typ + i0);
 #pragma unroll
-    for (int w2 = 0; w2 < S2_THREADS / 32; w2++)
-        if (w2 < (int)warp) before += s_wcnt[w2];
-    if (i >= p.n) return;
-    before += p.tile_pre[blockIdx.x].brk + p.grp_pre[blockIdx.x >> 10].brk;
-    const uint32_t k = before - 1;  // 0xffffffff when no bracket precedes
-    const uint32_t pv = i >= 1 ? p.typ[i - 1] : (uint32_t)T_START;
-    const uint32_t ppv = i >= 2 ? p.typ[i - 2] : (uint32_t)T_START;
-    // the scope this structural sits in = the scope open after the previous bracket (for a closing
-    // bracket that is the scope it closes: its open is the nearest bracket of smaller depth)
-    uint32_t ctx = CTX_ROOT;
-    int32_t enclosing = -1;
-    if (k != 0xffffffffu) {
-        ctx = p.ctx_after[k];
-        if (c == T_OBJ_CLOSE || c == T_ARR_CLOSE) enclosing = p.enc_after[k];
+        for (int j = 0; j < S2E_ITEMS; j++) c[j] = (w >> (8 * j)) & 0xff;
+    } else {
+#pragma unroll
+        for (int j = 0; j < S2E_ITEMS; j++) c[j] = i0 + j < p.n ? p.typ[i0 + j] : (uint32_t)T_INVALID;
     }
-    const uint32_t ti = trans_index(ctx, (ppv == T_OBJ_OPEN || ppv == T_COMMA) ? 1u : 0u, pv, c);
-    if (!((s_tr[ti >> 5] >> (ti & 31)) & 1)) {  // transition_ok(ctx, ppv, pv, c)
-        atomicOr(&p.result->error, 1u);
-        return;
-    }
-    if (c == T_OBJ_CLOSE || c == T_ARR_CLOSE) {  // scopeEnd, stage2...go:327-334
-        const uint32_t open_tp = p.brk_tp[enclosing], close_tp = p.brk_tp[k + 1];
-        if (close_tp < p.tape_cap) {
-            p.tape[open_tp] = ((uint64_t)(c == T_OBJ_CLOSE ? '{' : '[') << 56) | ((uint64_t)close_tp + 1);
-            p.tape[close_tp] = ((uint64_t)(c == T_OBJ_CLOSE ? '}' : ']') << 56) | open_tp;
+    uint32_t pv = T_START, ppv = T_START;
+    if (i0 >= 1 && i0 < p.n) pv = p.typ[i0 - 1];
+    if (i0 >= 2 && i0 < p.n) ppv = p.typ[i0 - 2];
+    // brackets of the tile in front of each structural: K2b's tile prefix + the other warp of the
+    // tile + lower lanes of this warp + the thread's own earlier structurals
+    uint32_t nbrk = 0;
+#pragma unroll
+    for (int j = 0; j < S2E_ITEMS; j++) nbrk += (c[j] >= T_OBJ_OPEN && c[j] <= T_ARR_CLOSE) ? 1u : 0u;
+    const uint32_t b0 = __ballot_sync(FULL, nbrk & 1), b1 = __ballot_sync(FULL, nbrk & 2), b2 = __ballot_sync(FULL, nbrk & 4);
+    const uint32_t lt = lanemask_lt();
+    uint32_t before = __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
+    if (lane == 0) s_wcnt[warp] = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+    __syncthreads();
+    if (i0 >= p.n) return;
+    if (warp & 1) before += s_wcnt[warp - 1];  // S2_THREADS / S2E_ITEMS = 64 threads per tile
+    const uint32_t tile = i0 / S2_THREADS;
+    before += p.tile_pre[tile].brk + p.grp_pre[tile >> 10].brk;
+#pragma unroll
+    for (int j = 0; j < S2E_ITEMS; j++) {
+        const uint32_t i = i0 + j;
+        if (i >= p.n) break;
+        const uint32_t cj = c[j];
+        const uint32_t k = before - 1;  // nearest bracket strictly before i; 0xffffffff when none
+        // the scope this structural sits in = the scope open after the previous bracket (for a closing
+        // bracket that is the scope it closes: its open is the nearest bracket of smaller depth)
+        uint32_t ctx = CTX_ROOT;
+        if (k != 0xffffffffu) ctx = p.ctx_after[k];
+        const uint32_t ti = trans_index(ctx, (ppv == T_OBJ_OPEN || ppv == T_COMMA) ? 1u : 0u, pv, cj);
+        if (!((s_tr[ti >> 5] >> (ti & 31)) & 1)) {  // transition_ok(ctx, ppv, pv, c)
+            atomicOr(&p.result->error, 1u);
+        } else if (cj == T_OBJ_CLOSE || cj == T_ARR_CLOSE) {  // scopeEnd, stage2...go:327-334
+            const int32_t enclosing = p.enc_after[k];  // k exists: a close cannot follow T_START in a valid transition
+            const uint32_t open_tp = p.brk_tp[enclosing], close_tp = p.brk_tp[k + 1];
+            if (close_tp < p.tape_cap) {
+                p.tape[open_tp] = ((uint64_t)(cj == T_OBJ_CLOSE ? '{' : '[') << 56) | ((uint64_t)close_tp + 1);
+                p.tape[close_tp] = ((uint64_t)(cj == T_OBJ_CLOSE ? '}' : ']') << 56) | open_tp;
+            }
         }
+        if (cj >= T_OBJ_OPEN && cj <= T_ARR_CLOSE) before++;
+        ppv = pv;
+        pv = cj;
     }
 }
 
