@@ -143,12 +143,12 @@ struct Carver {  // sub-allocates one DevBuf
 static int run_stage2(sj_ctx* c, const uint8_t* d_msg, size_t len, const uint32_t* d_idx, uint32_t n, uint32_t flags,
                       uint64_t* d_tape, size_t tape_cap, uint8_t* d_strings, size_t strings_cap, Stage2Result* out,
                       const uint32_t* d_bsmap) {
-    const uint32_t ntiles = (n + S2_THREADS - 1) / S2_THREADS;
+    const uint32_t ntiles = (n + S2_TILE - 1) / S2_TILE;
     const uint32_t ngroups = (ntiles + 1023) / 1024;
     // ---- phase 1 scratch ----
-    size_t need1 = Carver::need({(size_t)n, (size_t)n * 4, (size_t)ntiles * sizeof(ScanVal),
-                                 (size_t)ntiles * sizeof(ScanVal), (size_t)ngroups * sizeof(ScanVal),
-                                 (size_t)ngroups * sizeof(ScanVal)});
+    size_t need1 = Carver::need({(size_t)n + 16, ((size_t)n + 16) * 4, (size_t)ntiles * sizeof(ScanVal),
+                                 (size_t)ntiles * sizeof(ScanVal), (size_t)ntiles * S2_ITEMS * sizeof(ScanVal),
+                                 (size_t)ngroups * sizeof(ScanVal), (size_t)ngroups * sizeof(ScanVal)});
     int rc = c->s2a.reserve(need1);
     if (rc) return rc;
     Carver k1(c->s2a.p);
@@ -165,6 +165,7 @@ static int run_stage2(sj_ctx* c, const uint8_t* d_msg, size_t len, const uint32_
     p.aux = k1.take<uint32_t>(n);
     p.tile_sum = k1.take<ScanVal>(ntiles);
     p.tile_pre = k1.take<ScanVal>(ntiles);
+    p.sub_pre = k1.take<ScanVal>((size_t)ntiles * S2_ITEMS);
     p.grp_sum = k1.take<ScanVal>(ngroups);
     p.grp_pre = k1.take<ScanVal>(ngroups);
     p.ntiles = ntiles;
@@ -225,7 +226,7 @@ static int run_stage2(sj_ctx* c, const uint8_t* d_msg, size_t len, const uint32_
     int32_t* lvl_mem = k2.take<int32_t>(lvl_total + 8);
     p.rootpos = k2.take<uint32_t>((size_t)tot.n_records + 2);
 
-    s2_emit_kernel<<<ntiles, S2_THREADS, 0, c->stream>>>(p);
+    s2_emit_kernel<<<(n + S2_THREADS - 1) / S2_THREADS, S2_THREADS, 0, c->stream>>>(p);
     c->launches++;
     if (nb > 0) {
         AnsvLevels L;
@@ -251,7 +252,7 @@ static int run_stage2(sj_ctx* c, const uint8_t* d_msg, size_t len, const uint32_
         s2_scope_kernel<<<(unsigned)((nb + S2_THREADS - 1) / S2_THREADS), S2_THREADS, 0, c->stream>>>(p, (uint32_t)nb);
         c->launches += 2;
     }
-    s2_grammar_kernel<<<(ntiles + S2E_ITEMS - 1) / S2E_ITEMS, S2_THREADS, 0, c->stream>>>(p);
+    s2_grammar_kernel<<<ntiles, S2_THREADS, 0, c->stream>>>(p);
     {
         const uint64_t nrec = tot.n_records;
         const unsigned blocks = (unsigned)((nrec + 1 + 255) / 256);

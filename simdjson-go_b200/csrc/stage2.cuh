@@ -42,6 +42,8 @@ constexpr uint32_t AUX_COPY = 0x80000000u;              // string goes to the st
 constexpr uint32_t AUX_ESC = 0x40000000u;               // string contains escapes (source length != unescaped length)
 constexpr uint32_t AUX_LEN = 0x3fffffffu;
 constexpr int S2_THREADS = 256;
+constexpr int S2_ITEMS = 4;                       // consecutive structurals per thread in K2a / K2c / K2e
+constexpr int S2_TILE = S2_THREADS * S2_ITEMS;     // structurals per block = granularity of the K2b scan
 #ifndef SJ_S2_SHORT_STRING
 #define SJ_S2_SHORT_STRING 24
 #endif
@@ -123,16 +125,17 @@ __device__ __forceinline__ ScanVal block_exclusive_scan(ScanVal v, ScanVal& tota
 
 // The same scan for the per-structural contributions of ONE block (K2a, K2c): every field but
 // `str` is tiny (w <= 2, brk, rec <= 1, depth in {-1,0,1} per structural), so four of the five
-// fields travel as 16-bit lanes of one 64-bit word (depth biased by +1 per thread) and the scan
-// moves 3 registers per step instead of 5.  NT <= 8192 keeps every lane below 2^16.
-template <int NT>
+// fields travel as 16-bit lanes of one 64-bit word (depth biased by +BIAS per thread, BIAS = number
+// of structurals a thread contributes) and the scan moves 3 registers per step instead of 5.
+// NT * BIAS <= 8192 keeps every lane below 2^16.
+template <int NT, int BIAS>
 __device__ __forceinline__ ScanVal block_exclusive_scan_small(const ScanVal& v, ScanVal& total) {
     constexpr int NW = NT / 32;
     __shared__ unsigned long long wp_pk[NW + 1];
     __shared__ uint32_t wp_str[NW + 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned long long own = (unsigned long long)v.w | ((unsigned long long)v.brk << 16) | ((unsigned long long)v.rec << 32) |
-                                   ((unsigned long long)(uint32_t)(v.depth + 1) << 48);
+                                   ((unsigned long long)(uint32_t)(v.depth + BIAS) << 48);
     unsigned long long pk = own;
     uint32_t st = v.str;
 #pragma unroll
@@ -176,14 +179,14 @@ __device__ __forceinline__ ScanVal block_exclusive_scan_small(const ScanVal& v, 
     total.w = (uint32_t)(tot & 0xffff);
     total.brk = (uint32_t)((tot >> 16) & 0xffff);
     total.rec = (uint32_t)((tot >> 32) & 0xffff);
-    total.depth = (int32_t)(tot >> 48) - NT;
+    total.depth = (int32_t)(tot >> 48) - NT * BIAS;
     total.str = wp_str[NW];
     const unsigned long long ex = wp_pk[warp] + pk - own;  // exclusive prefix of this thread
     ScanVal r;
     r.w = (uint32_t)(ex & 0xffff);
     r.brk = (uint32_t)((ex >> 16) & 0xffff);
     r.rec = (uint32_t)((ex >> 32) & 0xffff);
-    r.depth = (int32_t)(ex >> 48) - (int32_t)threadIdx.x;
+    r.depth = (int32_t)(ex >> 48) - (int32_t)threadIdx.x * BIAS;
     r.str = wp_str[warp] + st - v.str;
     __syncthreads();  // the shared arrays may be reused by the next call
     return r;
@@ -211,6 +214,7 @@ struct Stage2Params {
     uint32_t* aux;       // [n] strings: dst_len | AUX_COPY
     ScanVal* tile_sum;   // [ntiles]
     ScanVal* tile_pre;   // [ntiles] exclusive within its group of 1024 tiles
+    ScanVal* sub_pre;    // [ntiles * S2_ITEMS] exclusive prefix of each quarter tile inside its tile (K2a)
     ScanVal* grp_sum;    // [ngroups]
     ScanVal* grp_pre;    // [ngroups] exclusive
     uint32_t ntiles, ngroups;
@@ -387,6 +391,12 @@ __device__ __forceinline__ void string_copy(const StrCursor& s, uint8_t* dst) {
     }
 }
 
+// element j (runtime index) of four registers
+template <typename T>
+__device__ __forceinline__ T sel4(const T (&a)[4], int j) {
+    return j == 0 ? a[0] : j == 1 ? a[1] : j == 2 ? a[2] : a[3];
+}
+
 // ---------------------------------------------------------------------------------
 // K2a
 // ---------------------------------------------------------------------------------
@@ -426,25 +436,48 @@ __device__ __forceinline__ ScanVal contribution(uint32_t t, uint32_t aux, uint32
     return v;
 }
 
+// Four consecutive structurals per thread: their positions come with one 16-byte load, their first
+// bytes are in flight together, and the block scan is paid once per four.
 __global__ void __launch_bounds__(S2_THREADS) s2_classify_measure_kernel(const Stage2Params p) {
-    const uint32_t i = blockIdx.x * S2_THREADS + threadIdx.x;
+    const uint32_t i0 = (blockIdx.x * S2_THREADS + threadIdx.x) * S2_ITEMS;
+    uint32_t pos[S2_ITEMS], nxt[S2_ITEMS], c[S2_ITEMS];  // position, position of the next structural, first byte
+    uint32_t cn = 0;                                       // first byte of the structural after the thread's last one
+    if (i0 + S2_ITEMS < p.n) {
+        const uint4 q = *reinterpret_cast<const uint4*>(p.idx + i0);
+        pos[0] = q.x, pos[1] = q.y, pos[2] = q.z, pos[3] = q.w;
+        nxt[0] = q.y, nxt[1] = q.z, nxt[2] = q.w, nxt[3] = p.idx[i0 + 4];
+    } else {
+#pragma unroll
+        for (int j = 0; j < S2_ITEMS; j++) {
+            pos[j] = i0 + j < p.n ? p.idx[i0 + j] : 0;
+            nxt[j] = i0 + j + 1 < p.n ? p.idx[i0 + j + 1] : pos[j];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < S2_ITEMS; j++) c[j] = i0 + j < p.n ? p.msg[pos[j]] : 0;
+    if (i0 + S2_ITEMS < p.n) cn = p.msg[nxt[S2_ITEMS - 1]];
     ScanVal v = sv_zero();
-    if (i < p.n) {
-        const uint64_t pos = p.idx[i];
-        const uint32_t c = p.msg[pos];
+    uint32_t typ4 = 0;
+    uint32_t auxv[S2_ITEMS] = {0, 0, 0, 0};
+#pragma unroll 1
+    for (int j = 0; j < S2_ITEMS; j++) {
+        const uint32_t i = i0 + j;
+        if (i >= p.n) break;
+        const uint64_t ps = sel4(pos, j);
         const bool has_next = i + 1 < p.n;
-        const uint64_t next_pos = has_next ? p.idx[i + 1] : pos;
+        const uint64_t next_pos = sel4(nxt, j);
+        const uint32_t ch = sel4(c, j);
         uint32_t t = T_INVALID, aux = 0;
-        switch (c) {
+        switch (ch) {
         case '{': t = T_OBJ_OPEN; break;
         case '[': t = T_ARR_OPEN; break;
         case '}': t = T_OBJ_CLOSE; break;
         case ']': t = T_ARR_CLOSE; break;
         case ':': t = T_COLON; break;
         case ',': t = T_COMMA; break;
-        case 't': t = atom_ok(p.msg, pos, p.len, "true", 4) ? T_TRUE : T_INVALID; break;
-        case 'f': t = atom_ok(p.msg, pos, p.len, "false", 5) ? T_FALSE : T_INVALID; break;
-        case 'n': t = atom_ok(p.msg, pos, p.len, "null", 4) ? T_NULL : T_INVALID; break;
+        case 't': t = atom_ok(p.msg, ps, p.len, "true", 4) ? T_TRUE : T_INVALID; break;
+        case 'f': t = atom_ok(p.msg, ps, p.len, "false", 5) ? T_FALSE : T_INVALID; break;
+        case 'n': t = atom_ok(p.msg, ps, p.len, "null", 4) ? T_NULL : T_INVALID; break;
         case '\n': t = p.ndjson ? T_NEWLINE : T_INVALID; break;
         case '"': {
             uint64_t sl = 0, dl = 0;
@@ -455,14 +488,14 @@ __global__ void __launch_bounds__(S2_THREADS) s2_classify_measure_kernel(const S
                 // last non-blank byte in front of it.  With no backslash in the blocks the body
                 // touches (K1's per-block map) nothing needs scanning: src_len == dst_len.
                 uint64_t e = next_pos - 1;
-                while (e > pos) {
+                while (e > ps) {
                     uint32_t ce = p.msg[e];
                     if (!(ce == 0x20 || ce == 0x0a || ce == 0x09 || ce == 0x0d)) break;
                     e--;
                 }
-                if (e > pos && p.msg[e] == '"') {
+                if (e > ps && p.msg[e] == '"') {
                     // any backslash block among blocks [b0, b1] of K1's map?  (one word in practice)
-                    const uint32_t b0 = (uint32_t)((pos + 1) >> 6), b1 = (uint32_t)(e >> 6);
+                    const uint32_t b0 = (uint32_t)((ps + 1) >> 6), b1 = (uint32_t)(e >> 6);
                     uint32_t hit = 0;
                     for (uint32_t wd = b0 >> 5; wd <= (b1 >> 5) && !hit; wd++) {
                         const uint32_t lo_bit = wd == (b0 >> 5) ? (b0 & 31) : 0, hi_bit = wd == (b1 >> 5) ? (b1 & 31) : 31;
@@ -470,15 +503,15 @@ __global__ void __launch_bounds__(S2_THREADS) s2_classify_measure_kernel(const S
                     }
                     fast = hit == 0;
                     if (fast) {
-                        sl = dl = e - pos - 1;
+                        sl = dl = e - ps - 1;
                         ok = true;
                     }
                 }
             }
             if (!fast) {
-                StrCursor s{p.msg + pos + 1, p.len - pos - 1};
+                StrCursor sc{p.msg + ps + 1, p.len - ps - 1};
                 // peekSize: distance to the next structural, 0 when there is none (stage2...go:63-70)
-                ok = string_measure(s, next_pos - pos, &sl, &dl);
+                ok = string_measure(sc, next_pos - ps, &sl, &dl);
             }
             if (ok) {
                 t = T_STRING;
@@ -488,18 +521,31 @@ __global__ void __launch_bounds__(S2_THREADS) s2_classify_measure_kernel(const S
             break;
         }
         default:
-            if (c == '-' || (c - '0') <= 9u) t = T_NUMBER;
+            if (ch == '-' || (ch - '0') <= 9u) t = T_NUMBER;
             break;
         }
-        p.typ[i] = (uint8_t)t;
-        p.aux[i] = aux;
-        uint32_t next_t = T_START;
-        if (has_next) next_t = p.msg[next_pos] == '\n' ? T_NEWLINE : T_INVALID;  // only "newline or not" matters
-        v = contribution(t, aux, next_t);
+        typ4 |= t << (8 * j);
+        if (j == 0) auxv[0] = aux; else if (j == 1) auxv[1] = aux; else if (j == 2) auxv[2] = aux; else auxv[3] = aux;
+        uint32_t next_t = T_START;  // only "newline or not" matters
+        if (has_next) next_t = (j + 1 < S2_ITEMS ? sel4(c, (j + 1) & 3) : cn) == '\n' ? T_NEWLINE : T_INVALID;
+        v = sv_add(v, contribution(t, aux, next_t));
+    }
+    if (i0 + S2_ITEMS <= p.n) {
+        *reinterpret_cast<uint32_t*>(p.typ + i0) = typ4;
+        *reinterpret_cast<uint4*>(p.aux + i0) = make_uint4(auxv[0], auxv[1], auxv[2], auxv[3]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < S2_ITEMS; j++)
+            if (i0 + j < p.n) {
+                p.typ[i0 + j] = (uint8_t)(typ4 >> (8 * j));
+                p.aux[i0 + j] = auxv[j];
+            }
     }
     ScanVal total;
-    block_exclusive_scan_small<S2_THREADS>(v, total);
+    const ScanVal ex = block_exclusive_scan_small<S2_THREADS, S2_ITEMS>(v, total);
     if (threadIdx.x == 0) p.tile_sum[blockIdx.x] = total;
+    // K2c works on quarter tiles (S2_THREADS structurals): their prefix inside the tile
+    if ((threadIdx.x & (S2_THREADS / S2_ITEMS - 1)) == 0) p.sub_pre[blockIdx.x * S2_ITEMS + threadIdx.x / (S2_THREADS / S2_ITEMS)] = ex;
 }
 
 // ---------------------------------------------------------------------------------
@@ -539,6 +585,8 @@ __global__ void __launch_bounds__(1024) s2_scan_top_kernel(const ScanVal* in, ui
 // ---------------------------------------------------------------------------------
 // K2c
 // ---------------------------------------------------------------------------------
+// One structural per thread (S2_THREADS per block = a quarter of a K2b tile): with four per thread
+// the tape stores of a warp spread over 32 sectors and the kernel got slower (541 -> 640 us).
 __global__ void __launch_bounds__(S2_THREADS) s2_emit_kernel(const Stage2Params p) {
     const uint32_t i = blockIdx.x * S2_THREADS + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31;
@@ -551,9 +599,10 @@ __global__ void __launch_bounds__(S2_THREADS) s2_emit_kernel(const Stage2Params 
         v = contribution(t, aux, next_t);
     }
     ScanVal total;
-    ScanVal e = block_exclusive_scan_small<S2_THREADS>(v, total);
-    const uint32_t tile = blockIdx.x;
-    e = sv_add(e, sv_add(p.tile_pre[tile], p.grp_pre[tile >> 10]));
+    ScanVal e = block_exclusive_scan_small<S2_THREADS, 1>(v, total);
+    // a block = one quarter of a K2b tile: prefix of the tile + prefix of the quarter inside it (from K2a)
+    const uint32_t tile = blockIdx.x / S2_ITEMS;
+    e = sv_add(e, sv_add(p.sub_pre[blockIdx.x], sv_add(p.tile_pre[tile], p.grp_pre[tile >> 10])));
     const uint64_t tp = 1 + (uint64_t)e.w;  // slot 0 is the first root word
     bool live = i < p.n;
     if (live && tp + v.w > p.tape_cap) {
@@ -796,8 +845,8 @@ __global__ void __launch_bounds__(S2_THREADS) s2_scope_kernel(const Stage2Params
 
 // Four consecutive structurals per thread (the per-structural work is a handful of instructions
 // behind two dependent loads, so one structural per thread is latency-bound): a block covers
-// 4 * S2_THREADS structurals = four K2b tiles, 64 threads (two warps) per tile.
-constexpr int S2E_ITEMS = 4;
+// S2_TILE structurals = one K2b tile.
+constexpr int S2E_ITEMS = S2_ITEMS;
 __global__ void __launch_bounds__(S2_THREADS) s2_grammar_kernel(const Stage2Params p) {
     __shared__ uint32_t s_wcnt[S2_THREADS / 32];
     __shared__ uint32_t s_tr[TRANS_WORDS];
@@ -828,8 +877,10 @@ __global__ void __launch_bounds__(S2_THREADS) s2_grammar_kernel(const Stage2Para
     if (lane == 0) s_wcnt[warp] = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
     __syncthreads();
     if (i0 >= p.n) return;
-    if (warp & 1) before += s_wcnt[warp - 1];  // S2_THREADS / S2E_ITEMS = 64 threads per tile
-    const uint32_t tile = i0 / S2_THREADS;
+#pragma unroll
+    for (int w2 = 0; w2 < S2_THREADS / 32; w2++)
+        if (w2 < (int)warp) before += s_wcnt[w2];
+    const uint32_t tile = blockIdx.x;  // a block = one K2b tile of S2_TILE structurals
     before += p.tile_pre[tile].brk + p.grp_pre[tile >> 10].brk;
 #pragma unroll
     for (int j = 0; j < S2E_ITEMS; j++) {
