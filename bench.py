@@ -188,6 +188,17 @@ def run_reference(args, rank, world):
 # --------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------
+def k1_traffic(batch_bytes):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE K1 launch on this batch, from the committed
+    `ncu --set full` capture of this very command (profiles/k1_traffic.json); None for other batch sizes."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "k1_traffic.json")) as f:
+            t = json.load(f)
+        return t["dram_bytes_read"] + t["dram_bytes_write"] if int(t["batch_bytes"]) == int(batch_bytes) else None
+    except (OSError, ValueError, KeyError):
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -382,7 +393,7 @@ def main():
                     "calls_in_flight": len(workers), "timer": "host wall clock around the in-flight calls, device synchronised on both sides"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "stage1_flatten_kernel<ndjson>", "achieved": round(achieved, 2), "peak": peak,
-                         "unit": "GB/s", "frac": round(achieved / peak, 4), "peak_kind": peak_kind, "traffic": None,
+                         "unit": "GB/s", "frac": round(achieved / peak, 4), "peak_kind": peak_kind, "traffic": k1_traffic(n),
                          "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": round(t_s1 * 1e3, 4),
                          "input_read_gbs": round(n / t_s1 / 1e9, 2)},
             "clocks": sampler.summary(),
