@@ -71,8 +71,8 @@ __global__ void test_finalize_kernel(const uint64_t* in, size_t n, uint64_t* out
     out[2 * i + 1] = pp;
 }
 
-// one warp walks the mask sequence 32 masks (= one 2 KiB step) at a time through the same
-// flatten_step the stage-1 kernel uses
+// one warp walks the mask sequence 32 masks (= one 2 KiB step) at a time through flatten_step,
+// the stage-1 kernel's per-step path (the kernel's staged path is covered by sj_find_structural_indices)
 __global__ void test_flatten_kernel(const uint64_t* masks, size_t nmasks, uint32_t* out, size_t cap, uint64_t* n_out) {
     const uint32_t lane = threadIdx.x & 31;
     uint32_t prev_last = 0xffffffffu, overflow = 0;

@@ -54,13 +54,7 @@ constexpr int S1_STEP_BYTES = 32 * 64;
 constexpr int S1_SLAB_BYTES = S1_STEPS * S1_STEP_BYTES;  // 6 KiB per warp
 constexpr int S1_TILE_BYTES = S1_WARPS * S1_SLAB_BYTES;  // one look-back per tile
 constexpr int S1_BUFS = 2;
-#ifdef SJ_CLASSIFY_LUT
-constexpr int S1_LUT_COPIES = 8;                         // table copies (lane & 7) to thin out bank conflicts
-constexpr size_t S1_LUT_BYTES = 2 * 256 * S1_LUT_COPIES * 4;  // two class tables
-#else
-constexpr size_t S1_LUT_BYTES = 0;
-#endif
-constexpr size_t S1_SMEM_BYTES = (size_t)S1_BUFS * S1_TILE_BYTES + 64 + S1_LUT_BYTES;
+constexpr size_t S1_SMEM_BYTES = (size_t)S1_BUFS * S1_TILE_BYTES + 64;  // tiles + mbarriers
 
 struct Stage1Result {
     uint32_t n_idx;           // total structurals found
@@ -224,7 +218,8 @@ __device__ __forceinline__ SlowMasks classify_block_slow(const uint32_t (&w)[16]
 // the planes evaluated for 32 bytes per LOP3: no per-class compares, no flag gathering, and
 // tab / LF / CR / control masks come for free.  About 230 instructions per 64-byte block for
 // all six masks, against 464 (4 masks) to 750 (with the control-character pass) for the
-// word-wise SWAR compares above, which remain available under -DSJ_CLASSIFY_SWAR.
+// word-wise SWAR compares above; those stay as an independent second implementation that the
+// test hook sj_test_block_masks cross-checks against this one on every block.
 // ---------------------------------------------------------------------------------
 struct PlaneMasks {
     uint64_t bs, qt, st, ws, ct, nl;
@@ -429,7 +424,6 @@ __device__ __forceinline__ uint32_t flatten_step(uint64_t S, uint32_t blockpos, 
     }
     uint32_t pos0 = blockpos;
     if (stage && total <= stage_cap) {  // warp-uniform
-#ifndef SJ_FLATTEN_SERIAL
         // the two 32-bit halves are extracted side by side (two independent dependency chains,
         // half the trip count of the divergent loop); bit-reversed so that one FLO finds the
         // next position
@@ -459,24 +453,6 @@ __device__ __forceinline__ uint32_t flatten_step(uint64_t S, uint32_t blockpos, 
             alo += 4 * SJ_FLATTEN_UNROLL;
             ahi += 4 * SJ_FLATTEN_UNROLL;
         }
-#else
-        uint32_t so = inc - c;
-        while (lo) {
-            uint32_t b = __ffs(lo) - 1;
-            lo &= lo - 1;
-            uint32_t p = pos0 + b;
-            stage[so++] = DELTAS ? p - prev : p;
-            prev = p;
-        }
-        pos0 += 32;
-        while (hi) {
-            uint32_t b = __ffs(hi) - 1;
-            hi &= hi - 1;
-            uint32_t p = pos0 + b;
-            stage[so++] = DELTAS ? p - prev : p;
-            prev = p;
-        }
-#endif
         __syncwarp();
         for (uint32_t k = lane; k < total; k += 32) out[base + k] = stage[k];
         __syncwarp();
@@ -791,64 +767,6 @@ __device__ __forceinline__ uint32_t backslash_run_before(const uint8_t* __restri
     }
 }
 
-#ifdef SJ_CLASSIFY_LUT
-// ---------------------------------------------------------------------------------
-// Table-driven classification.  The SWAR compares keep the ALU pipe busy; a 256-entry class
-// table in shared memory moves the work to the load/store unit and the FMA pipe (IMAD):
-//   entry(b) = one flag per BYTE LANE (bit 0, 8, 16, 24) for four classes;
-//   acc = acc * 2 + entry(b)  over 8 consecutive input bytes leaves, in every byte lane, the
-//   8 flags of one class -- ready-made mask bytes that PRMT assembles into 64-bit masks.
-// table 1: {quote, structural, whitespace, rare = backslash or control}    (always)
-// table 2: {backslash, control (< 0x20), newline, -}                        (only if a step has a rare byte)
-// Each table exists in 8 copies indexed by (lane & 7): [byte][copy] -> bank 8*(byte%4)+copy.
-// ---------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t lut1_entry(uint32_t b) {
-    uint32_t e = 0;
-    if (b == '"') e |= 1u;
-    if (b == '{' || b == '}' || b == '[' || b == ']' || b == ':' || b == ',') e |= 1u << 8;
-    if (b == 0x20 || b == 0x09 || b == 0x0a || b == 0x0d) e |= 1u << 16;
-    if (b == '\\' || b < 0x20) e |= 1u << 24;
-    return e;
-}
-__device__ __forceinline__ uint32_t lut2_entry(uint32_t b) {
-    uint32_t e = 0;
-    if (b == '\\') e |= 1u;
-    if (b < 0x20) e |= 1u << 8;
-    if (b == 0x0a) e |= 1u << 16;
-    return e;
-}
-__device__ __forceinline__ void lut_init(uint32_t* lut) {  // all threads of the CTA
-    for (uint32_t i = threadIdx.x; i < 256 * S1_LUT_COPIES; i += blockDim.x) {
-        uint32_t b = i / S1_LUT_COPIES;
-        lut[i] = lut1_entry(b);
-        lut[256 * S1_LUT_COPIES + i] = lut2_entry(b);
-    }
-}
-// flags of the 8 bytes (w0 = bytes 0..3, w1 = bytes 4..7): bit i of every byte lane <-> byte i
-__device__ __forceinline__ uint32_t lut_group(const uint32_t* t, uint32_t w0, uint32_t w1) {
-    uint32_t acc = t[__byte_perm(w1, 0, 0x4443) * S1_LUT_COPIES];
-    acc = acc * 2 + t[__byte_perm(w1, 0, 0x4442) * S1_LUT_COPIES];
-    acc = acc * 2 + t[__byte_perm(w1, 0, 0x4441) * S1_LUT_COPIES];
-    acc = acc * 2 + t[__byte_perm(w1, 0, 0x4440) * S1_LUT_COPIES];
-    acc = acc * 2 + t[__byte_perm(w0, 0, 0x4443) * S1_LUT_COPIES];
-    acc = acc * 2 + t[__byte_perm(w0, 0, 0x4442) * S1_LUT_COPIES];
-    acc = acc * 2 + t[__byte_perm(w0, 0, 0x4441) * S1_LUT_COPIES];
-    acc = acc * 2 + t[__byte_perm(w0, 0, 0x4440) * S1_LUT_COPIES];
-    return acc;
-}
-// byte lane c of A[0..7] -> 64-bit mask (A[g] covers bytes 8g..8g+7 of the block)
-template <int C>
-__device__ __forceinline__ uint64_t lut_mask(const uint32_t (&A)[8]) {
-    constexpr uint32_t sel = C | ((4 + C) << 4);  // byte C of the first, byte C of the second operand
-    uint32_t t01 = __byte_perm(A[0], A[1], sel), t23 = __byte_perm(A[2], A[3], sel);
-    uint32_t t45 = __byte_perm(A[4], A[5], sel), t67 = __byte_perm(A[6], A[7], sel);
-    return mk64(__byte_perm(t01, t23, 0x5410), __byte_perm(t45, t67, 0x5410));
-}
-__device__ __forceinline__ void lut_classify(const uint32_t* t, const uint32_t (&w)[16], uint32_t (&A)[8]) {
-#pragma unroll
-    for (int g = 0; g < 8; g++) A[g] = lut_group(t, w[2 * g], w[2 * g + 1]);
-}
-#endif  // SJ_CLASSIFY_LUT
 
 #ifdef SJ_PROFILE_PHASES
 // development aid: per-phase cycle totals (lane 0 of every warp), summed into prof[0..7]
@@ -940,12 +858,6 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
     uint64_t* const bar_Q = bars + 5;  // scan -> workers: in-string state in front of every slab  (count = 1)
     const uint64_t len16 = (p.len + 15) & ~15ull;
     const int G = (int)gridDim.x;
-#ifdef SJ_CLASSIFY_LUT
-    uint32_t* lut = reinterpret_cast<uint32_t*>(smem + (size_t)S1_BUFS * S1_TILE_BYTES + 64);
-    lut_init(lut);  // visible after the __syncthreads below
-    const uint32_t* lut1 = lut + (lane & (S1_LUT_COPIES - 1));
-    const uint32_t* lut2 = lut1 + 256 * S1_LUT_COPIES;
-#endif
 
     // Tiles are dealt round-robin to the CTAs of a COOPERATIVE launch (all CTAs co-resident), so
     // every predecessor a look-back waits for is owned by a running CTA; thread 0 issues one TMA
