@@ -1050,13 +1050,13 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
         }
 
         // ---------------- phase A: classify, escape analysis, slab quote parity ----------------
-        uint64_t qb[S1_STEPS], st[S1_STEPS], ws[S1_STEPS], ct[S1_STEPS], nl[S1_STEPS], bsm[S1_STEPS];
+        uint64_t qb[S1_STEPS], st[S1_STEPS], ws[S1_STEPS], ct[S1_STEPS], nl[S1_STEPS], bsm[S1_STEPS], qmr[S1_STEPS];
         uint32_t slab_par = 0;
         uint32_t* const stage = reinterpret_cast<uint32_t*>(smem + (size_t)b * S1_TILE_BYTES + (size_t)warp * S1_SLAB_BYTES);
         const uint32_t pslab_pos = (uint32_t)(((uint64_t)prev_tile * S1_WARPS + warp) * S1_SLAB_BYTES);
 #pragma unroll
         for (int s = 0; s < S1_STEPS; s++) {
-            qb[s] = st[s] = ws[s] = ct[s] = nl[s] = bsm[s] = 0;
+            qb[s] = st[s] = ws[s] = ct[s] = nl[s] = bsm[s] = qmr[s] = 0;
             if (active) {
                 uint32_t w[16];
                 load_block_words(buf + s * S1_STEP_BYTES, lane, w);
@@ -1089,8 +1089,12 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
                     odd_ends = odd_backslash_ends(bs, cin, nullptr);
                 }
                 qb[s] &= ~odd_ends;
-                uint32_t P = __ballot_sync(FULL, (__popcll(qb[s]) & 1) != 0);
+                // quote mask relative to the start of the slab (find_quote_mask_and_bits_amd64.s:49-66); the
+                // state in front of the slab is XORed in once chain 1 has delivered it (phase B)
+                const uint32_t P = __ballot_sync(FULL, (__popcll(qb[s]) & 1) != 0);
+                const uint32_t lane_rel = slab_par ^ (__popc(P & lanemask_lt()) & 1);
                 slab_par ^= __popc(P) & 1;
+                qmr[s] = prefix_xor64(qb[s]) ^ (lane_rel ? ~0ull : 0ull);
                 if (p.bsmap && lane == 0) p.bsmap[slab * S1_STEPS + s] = hasbs;
             }
         }
@@ -1158,14 +1162,11 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
 
         // ---------------- phase B: quote mask, finalize, counts ----------------
         uint32_t err = 0;
-        uint32_t par = par_in;
         uint32_t slab_count = 0;
+        const uint64_t flip = par_in ? ~0ull : 0ull;
 #pragma unroll
         for (int s = 0; s < S1_STEPS; s++) {
-            uint32_t P = __ballot_sync(FULL, (__popcll(qb[s]) & 1) != 0);
-            uint32_t lane_in = par ^ (__popc(P & lanemask_lt()) & 1);
-            par ^= __popc(P) & 1;
-            uint64_t qm = prefix_xor64(qb[s]) ^ (lane_in ? ~0ull : 0ull);
+            const uint64_t qm = qmr[s] ^ flip;
             if (ct[s] & qm) err = 1;  // find_quote_mask_and_bits_amd64.s:69-80
             // pseudo_pred bit of the previous block: previous lane, or the carry for lane 0
             uint64_t s0 = (st[s] & ~qm) | qb[s];

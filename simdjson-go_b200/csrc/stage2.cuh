@@ -592,24 +592,27 @@ __global__ void __launch_bounds__(S2_THREADS) s2_emit_kernel(const Stage2Params 
     const uint32_t lane = threadIdx.x & 31;
     uint32_t t = T_INVALID, aux = 0;
     ScanVal v = sv_zero();
+    uint64_t pos = 0;
+    // every global load of the thread is issued up front, in front of the scan's barriers
     if (i < p.n) {
         t = p.typ[i];
         aux = p.aux[i];
+        pos = p.idx[i];
         uint32_t next_t = i + 1 < p.n ? p.typ[i + 1] : (uint32_t)T_START;
         v = contribution(t, aux, next_t);
     }
-    ScanVal total;
-    ScanVal e = block_exclusive_scan_small<S2_THREADS, 1>(v, total);
     // a block = one quarter of a K2b tile: prefix of the tile + prefix of the quarter inside it (from K2a)
     const uint32_t tile = blockIdx.x / S2_ITEMS;
-    e = sv_add(e, sv_add(p.sub_pre[blockIdx.x], sv_add(p.tile_pre[tile], p.grp_pre[tile >> 10])));
+    const ScanVal blk = sv_add(p.sub_pre[blockIdx.x], sv_add(p.tile_pre[tile], p.grp_pre[tile >> 10]));
+    ScanVal total;
+    ScanVal e = block_exclusive_scan_small<S2_THREADS, 1>(v, total);
+    e = sv_add(e, blk);
     const uint64_t tp = 1 + (uint64_t)e.w;  // slot 0 is the first root word
     bool live = i < p.n;
     if (live && tp + v.w > p.tape_cap) {
         if (v.w) atomicOr(&p.result->overflow, 1u);
         live = false;
     }
-    const uint64_t pos = live ? p.idx[i] : 0;
     uint32_t fast_len = 0;  // escape-free string to be copied by the whole warp below
     if (live) {
         switch (t) {
@@ -620,7 +623,8 @@ __global__ void __launch_bounds__(S2_THREADS) s2_emit_kernel(const Stage2Params 
             p.brk_i[e.brk] = i;
             p.brk_tp[e.brk] = (uint32_t)tp;
             p.brk_depth[e.brk] = e.depth;
-            p.tape[tp] = (uint64_t)p.msg[pos] << 56;  // payload cross-linked by K2e
+            // the bracket itself (no need to re-read the message); payload cross-linked by K2e
+            p.tape[tp] = (uint64_t)(t == T_OBJ_OPEN ? '{' : t == T_ARR_OPEN ? '[' : t == T_OBJ_CLOSE ? '}' : ']') << 56;
             break;
         case T_STRING: {
             const uint32_t dl = aux & AUX_LEN;
