@@ -147,7 +147,7 @@ static int run_stage2(sj_ctx* c, const uint8_t* d_msg, size_t len, const uint32_
     const uint32_t ngroups = (ntiles + 1023) / 1024;
     // ---- phase 1 scratch ----
     size_t need1 = Carver::need({(size_t)n + 16, ((size_t)n + 16) * 4, (size_t)ntiles * sizeof(ScanVal),
-                                 (size_t)ntiles * sizeof(ScanVal), (size_t)ntiles * S2_ITEMS * sizeof(ScanVal),
+                                 (size_t)ntiles * sizeof(ScanVal), (size_t)ntiles * (S2_TILE / 32) * sizeof(ScanVal),
                                  (size_t)ngroups * sizeof(ScanVal), (size_t)ngroups * sizeof(ScanVal)});
     int rc = c->s2a.reserve(need1);
     if (rc) return rc;
@@ -165,7 +165,7 @@ static int run_stage2(sj_ctx* c, const uint8_t* d_msg, size_t len, const uint32_
     p.aux = k1.take<uint32_t>(n);
     p.tile_sum = k1.take<ScanVal>(ntiles);
     p.tile_pre = k1.take<ScanVal>(ntiles);
-    p.sub_pre = k1.take<ScanVal>((size_t)ntiles * S2_ITEMS);
+    p.sub_pre = k1.take<ScanVal>((size_t)ntiles * (S2_TILE / 32));
     p.grp_sum = k1.take<ScanVal>(ngroups);
     p.grp_pre = k1.take<ScanVal>(ngroups);
     p.ntiles = ntiles;

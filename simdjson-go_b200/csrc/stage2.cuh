@@ -192,6 +192,33 @@ __device__ __forceinline__ ScanVal block_exclusive_scan_small(const ScanVal& v, 
     return r;
 }
 
+// exclusive scan of one contribution per lane across the WARP only (same packing; no shared memory,
+// no barrier): K2c gets the prefix in front of its 32 structurals from K2a
+__device__ __forceinline__ ScanVal warp_exclusive_scan_small(const ScanVal& v) {
+    const int lane = threadIdx.x & 31;
+    const unsigned long long own = (unsigned long long)v.w | ((unsigned long long)v.brk << 16) | ((unsigned long long)v.rec << 32) |
+                                   ((unsigned long long)(uint32_t)(v.depth + 1) << 48);
+    unsigned long long pk = own;
+    uint32_t st = v.str;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long tp = __shfl_up_sync(FULL, pk, d);
+        const uint32_t ts = __shfl_up_sync(FULL, st, d);
+        if (lane >= d) {
+            pk += tp;
+            st += ts;
+        }
+    }
+    const unsigned long long ex = pk - own;
+    ScanVal r;
+    r.w = (uint32_t)(ex & 0xffff);
+    r.brk = (uint32_t)((ex >> 16) & 0xffff);
+    r.rec = (uint32_t)((ex >> 32) & 0xffff);
+    r.depth = (int32_t)(ex >> 48) - lane;
+    r.str = st - v.str;
+    return r;
+}
+
 struct Stage2Result {
     uint64_t tape_len;     // total tape words (including both root words of the last record)
     uint64_t strings_len;  // bytes of the string buffer
@@ -214,7 +241,7 @@ struct Stage2Params {
     uint32_t* aux;       // [n] strings: dst_len | AUX_COPY
     ScanVal* tile_sum;   // [ntiles]
     ScanVal* tile_pre;   // [ntiles] exclusive within its group of 1024 tiles
-    ScanVal* sub_pre;    // [ntiles * S2_ITEMS] exclusive prefix of each quarter tile inside its tile (K2a)
+    ScanVal* sub_pre;    // [ntiles * S2_TILE / 32] exclusive prefix of every 32 structurals inside their tile (K2a)
     ScanVal* grp_sum;    // [ngroups]
     ScanVal* grp_pre;    // [ngroups] exclusive
     uint32_t ntiles, ngroups;
@@ -544,8 +571,8 @@ __global__ void __launch_bounds__(S2_THREADS) s2_classify_measure_kernel(const S
     ScanVal total;
     const ScanVal ex = block_exclusive_scan_small<S2_THREADS, S2_ITEMS>(v, total);
     if (threadIdx.x == 0) p.tile_sum[blockIdx.x] = total;
-    // K2c works on quarter tiles (S2_THREADS structurals): their prefix inside the tile
-    if ((threadIdx.x & (S2_THREADS / S2_ITEMS - 1)) == 0) p.sub_pre[blockIdx.x * S2_ITEMS + threadIdx.x / (S2_THREADS / S2_ITEMS)] = ex;
+    // K2c works warp by warp (32 structurals = 8 threads here): their prefix inside the tile
+    if ((threadIdx.x & (32 / S2_ITEMS - 1)) == 0) p.sub_pre[i0 >> 5] = ex;
 }
 
 // ---------------------------------------------------------------------------------
@@ -585,8 +612,8 @@ __global__ void __launch_bounds__(1024) s2_scan_top_kernel(const ScanVal* in, ui
 // ---------------------------------------------------------------------------------
 // K2c
 // ---------------------------------------------------------------------------------
-// One structural per thread (S2_THREADS per block = a quarter of a K2b tile): with four per thread
-// the tape stores of a warp spread over 32 sectors and the kernel got slower (541 -> 640 us).
+// One structural per thread, warps independent of each other: with four structurals per thread the
+// tape stores of a warp spread over 32 sectors and the kernel got slower (541 -> 640 us).
 __global__ void __launch_bounds__(S2_THREADS) s2_emit_kernel(const Stage2Params p) {
     const uint32_t i = blockIdx.x * S2_THREADS + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31;
@@ -601,12 +628,11 @@ __global__ void __launch_bounds__(S2_THREADS) s2_emit_kernel(const Stage2Params 
         uint32_t next_t = i + 1 < p.n ? p.typ[i + 1] : (uint32_t)T_START;
         v = contribution(t, aux, next_t);
     }
-    // a block = one quarter of a K2b tile: prefix of the tile + prefix of the quarter inside it (from K2a)
-    const uint32_t tile = blockIdx.x / S2_ITEMS;
-    const ScanVal blk = sv_add(p.sub_pre[blockIdx.x], sv_add(p.tile_pre[tile], p.grp_pre[tile >> 10]));
-    ScanVal total;
-    ScanVal e = block_exclusive_scan_small<S2_THREADS, 1>(v, total);
-    e = sv_add(e, blk);
+    // prefix in front of the warp's 32 structurals: K2b's tile prefix + K2a's prefix inside the tile;
+    // the rest is a warp scan -- no shared memory, no barrier in this kernel
+    const uint32_t tile = i / S2_TILE;
+    const ScanVal blk = sv_add(p.sub_pre[i >> 5], sv_add(p.tile_pre[tile], p.grp_pre[tile >> 10]));
+    ScanVal e = sv_add(warp_exclusive_scan_small(v), blk);
     const uint64_t tp = 1 + (uint64_t)e.w;  // slot 0 is the first root word
     bool live = i < p.n;
     if (live && tp + v.w > p.tape_cap) {
