@@ -89,6 +89,25 @@ int sj_parse_device(sj_ctx* ctx, const uint8_t* d_msg, size_t len, uint32_t flag
                     size_t* tape_len, uint8_t* d_strings, size_t strings_cap, size_t* strings_len);
 
 /*
+ * Device-side tape consumers: the reference's NDJSON workloads walk
+ * the tape right after the parse -- countWhere(key, value, pj) ndjson_test.go:421-459 built
+ * on Object.FindKey parsed_object.go:97-140, countObjects ndjson_test.go:461-474, benchmarked
+ * as parse + count in BenchmarkNdjsonColdCountStarWithWhere parse_json_amd64_test.go:134-157.
+ * Here the walk runs on the tape in HBM, so only two integers travel back over PCIe.
+ *   *roots    number of root elements (= countObjects)
+ *   *matches  roots whose element is an object whose FIRST member named `key` is a string
+ *             equal to `value` (= countWhere)
+ * sj_count_where_device: tape / strings / message already in device memory (as left by
+ * sj_parse_device; d_msg is only read for no-copy strings).  sj_parse_count_where: HOST
+ * message in, parse on the device, count on the device; nothing but the counts is copied back.
+ */
+int sj_count_where_device(sj_ctx* ctx, const uint8_t* d_msg, const uint64_t* d_tape, size_t tape_len,
+                          const uint8_t* d_strings, const uint8_t* key, size_t key_len, const uint8_t* value,
+                          size_t value_len, uint64_t* roots, uint64_t* matches);
+int sj_parse_count_where(sj_ctx* ctx, const uint8_t* msg, size_t len, uint32_t flags, const uint8_t* key,
+                         size_t key_len, const uint8_t* value, size_t value_len, uint64_t* roots, uint64_t* matches);
+
+/*
  * Stage 1 + flatten only (findStructuralIndices, stage1_find_marks_amd64.go:41):
  * writes the concatenated uint32 index deltas the reference would hand to stage 2
  * (flatten_bits_amd64.s:26-60: delta to the previous structural, first = position+1).

@@ -73,6 +73,9 @@ class Oracle:
         L.sjo_parse.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t),
                                 C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t),
                                 C.POINTER(C.c_size_t)]
+        L.sjo_count_where.restype = C.c_uint64
+        L.sjo_count_where.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_char_p, C.c_size_t, C.c_char_p,
+                                      C.c_size_t, u64p]
         L.sjo_stage1_count.restype = C.c_size_t
         L.sjo_stage1_count.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_int)]
 
@@ -173,6 +176,16 @@ class Oracle:
         if rc != 0:
             return rc, None, None, (mo.value, ml.value)
         return rc, tape[:tl.value].copy(), strings[:sl.value].tobytes(), (mo.value, ml.value)
+
+    def count_where(self, tape, strings, message, key, value):
+        """countWhere(key, value) + countObjects over a finished tape: (roots, matches)."""
+        import numpy as np
+        t = np.ascontiguousarray(tape, dtype=np.uint64)
+        sb, mb = _buf(strings), _buf(message)
+        roots = C.c_uint64(0)
+        n = self.lib.sjo_count_where(t.ctypes.data, t.size, C.addressof(sb), C.addressof(mb), bytes(key), len(key),
+                                     bytes(value), len(value), C.byref(roots))
+        return roots.value, n
 
     def stage1_count(self, msg, ndjson=False):
         ok = C.c_int(0)

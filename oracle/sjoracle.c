@@ -1136,3 +1136,61 @@ int sjo_parse(const uint8_t *msg, size_t len, uint32_t flags, uint64_t *tape, si
     if (m.overflow) return SJO_ERR_CAPACITY;
     return SJO_OK;
 }
+
+/* ======================================================================= */
+/* tape consumers of the reference's NDJSON tests / benchmarks              */
+/* ======================================================================= */
+#define SJO_VALUE_MASK 0x00ffffffffffffffull /* JSONVALUEMASK parsed_json.go:26 */
+#define SJO_STRINGBUFBIT 0x80000000000000ull /* parsed_json.go:29 */
+
+/* parsed_json.go:107-120 stringByteAt */
+static const uint8_t *tape_string(uint64_t w, const uint8_t *strings, const uint8_t *msg) {
+    uint64_t v = w & SJO_VALUE_MASK;
+    return (v & SJO_STRINGBUFBIT) ? strings + (v - SJO_STRINGBUFBIT) : msg + v;
+}
+
+/* countWhere(key, value, pj) ndjson_test.go:421-459: the roots are chained through their
+ * payload (count_raw_tape, ndjson_test.go:410-419); for every root whose element is an
+ * object, Object.FindKey (parsed_object.go:97-140) returns the FIRST member named key, and
+ * the record counts when that member is a string equal to value.  *roots = countObjects
+ * (ndjson_test.go:461-474). */
+uint64_t sjo_count_where(const uint64_t *tape, size_t tape_len, const uint8_t *strings, const uint8_t *msg,
+                         const uint8_t *key, size_t klen, const uint8_t *value, size_t vlen, uint64_t *roots) {
+    uint64_t count = 0, nroots = 0;
+    size_t open = 0;
+    while (open < tape_len) {
+        uint64_t rw = tape[open];
+        size_t next_root = (size_t)(rw & SJO_VALUE_MASK);
+        if ((rw >> 56) != 'r' || next_root <= open) break;
+        nroots++;
+        if (open + 2 < tape_len && (tape[open + 1] >> 56) == '{') {
+            size_t close = (size_t)(tape[open + 1] & SJO_VALUE_MASK) - 1;
+            size_t i = open + 2;
+            while (i < close && i + 2 < tape_len) {
+                uint64_t kw = tape[i];
+                if ((kw >> 56) != '"') break;
+                uint64_t kl = tape[i + 1];
+                size_t vi = i + 2;
+                uint64_t vw = tape[vi];
+                uint8_t vt = (uint8_t)(vw >> 56);
+                if (kl == klen && memcmp(tape_string(kw, strings, msg), key, klen) == 0) {
+                    if (vt == '"' && tape[vi + 1] == vlen && memcmp(tape_string(vw, strings, msg), value, vlen) == 0)
+                        count++;
+                    break;
+                }
+                size_t nx;
+                if (vt == '"' || vt == 'l' || vt == 'u' || vt == 'd')
+                    nx = vi + 2;
+                else if (vt == '{' || vt == '[')
+                    nx = (size_t)(vw & SJO_VALUE_MASK);
+                else
+                    nx = vi + 1;
+                if (nx <= i) break;
+                i = nx;
+            }
+        }
+        open = next_root;
+    }
+    if (roots) *roots = nroots;
+    return count;
+}

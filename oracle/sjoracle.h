@@ -83,6 +83,11 @@ int sjo_parse(const uint8_t *msg, size_t len, uint32_t flags, uint64_t *tape, si
  * chunk loop without keeping the indexes; returns the number of indexes. */
 size_t sjo_stage1_count(const uint8_t *msg, size_t len, int ndjson, int *ok);
 
+/* countWhere / countObjects over a finished tape (ndjson_test.go:421-474, Object.FindKey
+ * parsed_object.go:97-140): returns the matches, *roots = number of root elements */
+uint64_t sjo_count_where(const uint64_t *tape, size_t tape_len, const uint8_t *strings, const uint8_t *msg,
+                         const uint8_t *key, size_t klen, const uint8_t *value, size_t vlen, uint64_t *roots);
+
 #ifdef __cplusplus
 }
 #endif

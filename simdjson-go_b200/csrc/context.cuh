@@ -52,5 +52,14 @@ struct sj_ctx {
     // stage 2
     DevBuf s2a, s2b, s2c, s2d, s2e, s2f, s2g;  // s2a/s2b: stage-2 scratch (before / after the totals are known), s2c: backslash block map
     DevBuf tape, strings;  // device outputs for the host-buffer API
+    // tape consumers (consume.cuh): needles + counters, root list of a foreign tape
+    DevBuf tc_small, tc_roots;
+    // what the last successful stage 2 of this context left in device memory (valid until the next call)
+    const uint32_t* last_rootpos = nullptr;  // stage 2's root list (slot of every record's root-open word, [0] implicit)
+    uint64_t last_records = 0;               // record boundaries = roots - 1
+    const uint64_t* last_tape = nullptr;
+    uint64_t last_tape_len = 0;
+    const uint8_t* last_strings = nullptr;
+    const uint8_t* last_msg = nullptr;
     DevBuf test_in, test_out, test_aux;
 };

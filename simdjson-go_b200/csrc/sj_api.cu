@@ -12,6 +12,7 @@
 #include "context.cuh"
 #include "stage1.cuh"
 #include "stage2.cuh"
+#include "consume.cuh"
 
 using namespace sj;
 
@@ -167,7 +168,8 @@ extern "C" void sj_ctx_destroy(sj_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->msg,  &c->idx, &c->desc, &c->result, &c->s2a,     &c->s2b,     &c->s2c,      &c->s2d,
-                      &c->s2e,  &c->s2f, &c->s2g,  &c->tape,   &c->strings, &c->test_in, &c->test_out, &c->test_aux};
+                      &c->s2e,  &c->s2f, &c->s2g,  &c->tape,   &c->strings, &c->test_in, &c->test_out, &c->test_aux,
+                      &c->tc_small, &c->tc_roots};
     for (DevBuf* b : bufs) b->release();
     if (c->host_result) cudaFreeHost(c->host_result);
     cudaEventDestroy(c->ev[0]);
@@ -405,6 +407,7 @@ extern "C" int sj_test_flatten_bits(sj_ctx* c, const uint64_t* masks, size_t nma
 }
 
 #include "sj_parse.inl"
+#include "sj_consume.inl"
 
 #ifdef SJ_PROFILE_PHASES
 // development aid (not part of the C ABI): read / clear the per-phase cycle counters

@@ -140,11 +140,14 @@ struct Carver {  // sub-allocates one DevBuf
 // stage 2 driver.  d_tape / d_strings may be null: then the context's own output buffers
 // are sized from the totals (host-buffer API).
 // ---------------------------------------------------------------------------------
+static int stage2_verdict(const Stage2Result& r);
+
 static int run_stage2(sj_ctx* c, const uint8_t* d_msg, size_t len, const uint32_t* d_idx, uint32_t n, uint32_t flags,
                       uint64_t* d_tape, size_t tape_cap, uint8_t* d_strings, size_t strings_cap, Stage2Result* out,
                       const uint32_t* d_bsmap) {
     const uint32_t ntiles = (n + S2_TILE - 1) / S2_TILE;
     const uint32_t ngroups = (ntiles + 1023) / 1024;
+    c->last_tape = nullptr;  // the device-side results of the previous parse are about to be overwritten
     // ---- phase 1 scratch ----
     size_t need1 = Carver::need({(size_t)n + 16, ((size_t)n + 16) * 4, (size_t)ntiles * sizeof(ScanVal),
                                  (size_t)ntiles * sizeof(ScanVal), (size_t)ntiles * (S2_TILE / 32) * sizeof(ScanVal),
@@ -263,6 +266,14 @@ static int run_stage2(sj_ctx* c, const uint8_t* d_msg, size_t len, const uint32_
     SJ_CUDA_CHECK(cudaMemcpyAsync(h_res, d_res, sizeof(Stage2Result), cudaMemcpyDeviceToHost, c->stream));
     SJ_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     *out = *h_res;
+    if (stage2_verdict(*out) == SJ_OK) {  // what the tape consumers (sj_consume.inl) may read until the next call
+        c->last_rootpos = p.rootpos;
+        c->last_records = tot.n_records;
+        c->last_tape = d_tape;
+        c->last_tape_len = tot.tape_len;
+        c->last_strings = d_strings;
+        c->last_msg = d_msg;
+    }
     return SJ_OK;
 }
 
@@ -305,12 +316,8 @@ extern "C" int sj_parse_device(sj_ctx* c, const uint8_t* d_msg, size_t len, uint
     Stage1Result r1;
     int rc = stage1_positions(c, d_msg, len, (flags & SJ_FLAG_NDJSON) != 0, &r1);
     if (rc) return rc;
-    uint8_t last_char = 0;
-    if (r1.n_idx && r1.last_pos < len) {
-        SJ_CUDA_CHECK(cudaMemcpyAsync(c->host_result, d_msg + r1.last_pos, 1, cudaMemcpyDeviceToHost, c->stream));
-        SJ_CUDA_CHECK(cudaStreamSynchronize(c->stream));
-        last_char = *reinterpret_cast<uint8_t*>(c->host_result);
-    }
+    // the byte under the last structural comes back with the stage-1 result (stage1_finish_kernel)
+    const uint8_t last_char = r1.n_idx && r1.last_pos < len ? (uint8_t)r1.last_char : 0;
     if (!stage1_ok(r1, last_char)) return SJ_ERR_STAGE1;
     Stage2Result r2;
     rc = run_stage2(c, d_msg, len, c->idx.as<uint32_t>(), r1.n_idx, flags, d_tape, tape_cap, d_strings, strings_cap, &r2,

@@ -62,7 +62,8 @@ struct Stage1Result {
     uint32_t ends_in_string;  // message ends inside an unterminated string
     uint32_t last_pos;        // position of the last structural (valid if n_idx > 0)
     uint32_t overflow;        // index buffer too small (n_idx is still exact)
-    uint32_t pad[3];
+    uint32_t last_char;       // message byte at last_pos (stage1_find_marks_amd64.go:140-146 tests it for '}' / ']')
+    uint32_t pad[2];
 };
 
 // ---------------------------------------------------------------------------------
@@ -1227,6 +1228,7 @@ __global__ void stage1_finish_kernel(const Stage1Params p) {
         uint32_t l = own;
         while (l == 0 && t > 0) l = p.lastp1[--t];
         p.result->last_pos = l - 1;
+        p.result->last_char = l != 0 && (uint64_t)(l - 1) < p.len ? p.msg[l - 1] : 0;
     }
     if (!DELTAS || own == 0 || s == 0) return;
     int t = s - 1;

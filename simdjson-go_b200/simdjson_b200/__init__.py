@@ -86,6 +86,22 @@ class Context:
             raise SjError(rc)
         return rc, tape[:tl.value].copy(), strings[:sl.value].tobytes(), (mo.value, ml.value)
 
+    # ---- device-side tape consumers ------------------------------------------
+    def parse_count_where(self, msg, key, value, ndjson=True, copy_strings=True):
+        """parseMessage + countWhere(key, value) (parse_json_amd64_test.go:134-157) with the tape left in
+        HBM: (rc, roots, matches).  roots = countObjects (ndjson_test.go:461)."""
+        m = _as_u8(msg)
+        key, value = bytes(key), bytes(value)
+        roots, matches = C.c_uint64(0), C.c_uint64(0)
+        flags = (FLAG_NDJSON if ndjson else 0) | (FLAG_COPY_STRINGS if copy_strings else 0)
+        rc = self.L.sj_parse_count_where(self.h, _addr(m) if m.size else None, m.size, flags, key, len(key), value,
+                                         len(value), C.byref(roots), C.byref(matches))
+        if rc in (ERR_STAGE1, ERR_STAGE2):
+            return rc, 0, 0
+        if rc != OK:
+            raise SjError(rc)
+        return rc, roots.value, matches.value
+
     # ---- unit-test hooks (same method names as oracle.pyoracle.Oracle) -----------
     def block_masks(self, blocks, carries):
         """blocks: (n,64) uint8; carries: (n,4) uint64 -> (n,12) uint64 (see simdjson_b200.h)."""

@@ -20,7 +20,7 @@ EXPORTS = [
     "sj_host_free", "sj_trim_space", "sj_bounds", "sj_parse", "sj_parse_device", "sj_find_structural_indices", "sj_stage1_device",
     "sj_stage1_launch", "sj_ctx_sync", "sj_event_record", "sj_event_elapsed_ms", "sj_kernel_launches",
     "sj_test_block_masks", "sj_test_finalize", "sj_test_flatten_bits", "sj_test_parse_strings",
-    "sj_test_parse_numbers",
+    "sj_test_parse_numbers", "sj_count_where_device", "sj_parse_count_where",
 ]
 
 
@@ -86,6 +86,10 @@ def load():
     L.sj_test_parse_strings.argtypes = [vp, vp, vp, sz, vp, vp, vp, vp, vp]
     L.sj_test_parse_numbers.restype = i32
     L.sj_test_parse_numbers.argtypes = [vp, vp, vp, sz, vp, vp]
+    L.sj_count_where_device.restype = i32
+    L.sj_count_where_device.argtypes = [vp, vp, vp, sz, vp, C.c_char_p, sz, C.c_char_p, sz, C.POINTER(u64), C.POINTER(u64)]
+    L.sj_parse_count_where.restype = i32
+    L.sj_parse_count_where.argtypes = [vp, vp, sz, u32, C.c_char_p, sz, C.c_char_p, sz, C.POINTER(u64), C.POINTER(u64)]
     _lib = L
     return L
 

@@ -9,7 +9,7 @@ import struct
 import numpy as np
 import pytest
 
-from tests.util import SMALL_FILES, TAPE_FILES, golden, load_fixture, unhex
+from tests.util import SMALL_FILES, TAPE_FILES, golden, load_fixture, tricky_ndjson, unhex
 
 M64 = (1 << 64) - 1
 
@@ -337,3 +337,27 @@ def test_trim_space(o):
     for src, want in cases:
         a, b = o.trim_space(src)
         assert src[a:b] == want, src
+
+
+def test_count_where_oracle(o):
+    """countWhere / countObjects (ndjson_test.go:421-474) restated in the oracle: the reference's golden
+    (1000 roots, Make == HOND 116 times, ndjson_test.go:250-266) and agreement with a plain json.loads walk"""
+    g = golden("G18_G19_fixtures")["parking_citations"]
+    msg = load_fixture("parking-citations")
+    for copy in (True, False):
+        rc, tape, strs, (off, ln) = o.parse(msg, ndjson=True, copy_strings=copy)
+        assert rc == 0
+        assert o.count_where(tape, strs, msg[off:off + ln], b"Make", b"HOND") == (g["roots"], g["make_hond"])
+    nd, recs = tricky_ndjson()
+    for copy in (True, False):
+        rc, tape, strs, (off, ln) = o.parse(nd, ndjson=True, copy_strings=copy)
+        assert rc == 0
+        for key, value in ((b"Make", b"HOND"), (b"Make", b""), (b"", b""), (b"Make", b"TOYT"), (b"x", b"1")):
+            want = 0
+            for r in recs:
+                first = {}
+                for k, v in json.loads(r, object_pairs_hook=list) if r.startswith(b"{") else []:
+                    first.setdefault(k, v)
+                v = first.get(key.decode())
+                want += isinstance(v, str) and v == value.decode()
+            assert o.count_where(tape, strs, nd[off:off + ln], key, value) == (len(recs), want), (key, value, copy)

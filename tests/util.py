@@ -103,3 +103,22 @@ def _go_string(lit):
         else:
             raise ValueError(e)
     return bytes(out)
+
+
+def tricky_ndjson():
+    """records that exercise FindKey's corner cases (parsed_object.go:97-140)"""
+    recs = [
+        b'{"Make":"HOND","x":1}',
+        b'{"a":{"Make":"HOND"},"Make":"TOYT"}',              # nested member of the same name does not count
+        b'{"a":[{"Make":"HOND"},2,[3]],"Make":"HOND"}',      # containers are skipped as a whole
+        b'{"Make":"TOYT","Make":"HOND"}',                    # the FIRST member of that name decides
+        b'{"Make":"HOND","Make":"TOYT"}',
+        b'{"Make":1}', b'{"Make":null}', b'{"Make":["HOND"]}', b'{"Make":{"Make":"HOND"}}',
+        b'{"make":"HOND"}', b'{"Make ":"HOND"}', b'{"Make":"HOND "}', b'{"Make":"HON"}', b'{"Mak":"HOND"}',
+        b'["Make","HOND"]', b'[]', b'{}', b'[{"Make":"HOND"}]',
+        b'{"t":true,"f":false,"n":null,"d":1.5,"l":-3,"u":18446744073709551615,"Make":"HOND"}',
+        b'{"M\\u0061ke":"HOND"}',                             # escaped name: compared after unescaping
+        b'{"Make":"HO\\u004eD"}',
+        b'{"":"","Make":""}',
+    ]
+    return b"\n".join(recs), recs
