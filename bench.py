@@ -113,10 +113,11 @@ _cpu_pool = None
 _cpu_local = threading.local()
 
 
-def cpu_parse_stream(buf, threads, chunk=10 << 20):
+def cpu_parse_stream(buf, threads, chunk=10 << 20, count_where=None):
     """Parse `buf` as NDJSON in newline-aligned ~10 MiB chunks on `threads` host threads
     (persistent workers with reused output buffers, like the reference's `reuse` channel,
-    simdjson_amd64.go:116).  Returns (seconds, bytes parsed)."""
+    simdjson_amd64.go:116).  With count_where=(key, value) every chunk's tape is then walked by
+    countWhere (ndjson_test.go:421).  Returns (seconds, bytes parsed)."""
     global _cpu_pool
     from concurrent.futures import ThreadPoolExecutor
     from oracle.pyoracle import FLAG_COPY_STRINGS, FLAG_NDJSON, Oracle
@@ -146,6 +147,10 @@ def cpu_parse_stream(buf, threads, chunk=10 << 20):
                              local.tape.size, C.byref(tl), local.strs.ctypes.data, local.strs.size, C.byref(sl),
                              C.byref(mo), C.byref(ml))
         assert rc == 0, rc
+        if count_where:
+            roots = C.c_uint64(0)
+            o.lib.sjo_count_where(local.tape.ctypes.data, tl.value, local.strs.ctypes.data, arr[a + mo.value:].ctypes.data,
+                                  count_where[0], len(count_where[0]), count_where[1], len(count_where[1]), C.byref(roots))
         return n
 
     t0 = time.perf_counter()
@@ -208,6 +213,7 @@ def main():
     ap.add_argument("--batch-mib", type=int, default=512, help="NDJSON bytes per step per GPU")
     ap.add_argument("--cpu-sample-mib", type=int, default=1024)
     ap.add_argument("--inflight", type=int, default=3, help="host-API calls kept in flight for the e2e number")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs under ncu)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -350,14 +356,42 @@ def main():
     torch.cuda.synchronize()
     t_e2e = reduce_max(time.perf_counter() - t0)
     barrier()
-    sampler.stop_flag = True
-    sampler.join(timeout=3)
     for w in workers[: min(len(workers), args.steps)]:
         assert np.array_equal(w["tape"][:tape_words].numpy().view(np.uint64), tape_h)
 
+    # ---- tape consumer on the device: parseMessage + countWhere("Make", "HOND"), the reference's
+    # BenchmarkNdjsonColdCountStarWithWhere (parse_json_amd64_test.go:134): host input, only two counts come back ----
+    n_records = batch.count(b"\n") + 1
+    cw_seen = []
+
+    def step_count(w):
+        roots, matches = C.c_uint64(0), C.c_uint64(0)
+        r = L.sj_parse_count_where(w["ctx"].h, h_in.data_ptr(), n, flags, b"Make", 4, b"HOND", 4, C.byref(roots), C.byref(matches))
+        assert r == 0 and roots.value == n_records, (r, roots.value)
+        cw_seen.append(matches.value)
+
+    def run_count_steps(count):
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=len(workers)) as ex:
+            futs = [ex.submit(lambda k=k: [step_count(workers[k]) for _ in range(k, count, len(workers))])
+                    for k in range(len(workers))]
+            for f in futs:
+                f.result()
+
+    run_count_steps(max(args.warmup, len(workers)))
+    barrier()
+    t0 = time.perf_counter()
+    run_count_steps(args.steps)
+    torch.cuda.synchronize()
+    t_cw = reduce_max(time.perf_counter() - t0)
+    barrier()
+    assert len(set(cw_seen)) == 1 and cw_seen[0] == 116 * (n_records // 1000), cw_seen[:3]  # ndjson_test.go:263 per 1000 records
+    sampler.stop_flag = True
+    sampler.join(timeout=3)
+
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same stream ----
     cpu = None
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and not args.no_cpu:
         threads, quota = host_threads()
         sample = batch
         while len(sample) < (args.cpu_sample_mib << 20):
@@ -374,8 +408,10 @@ def main():
             secs += t2
             nb += n2
             reps += 1
+        t_c, n_c = cpu_parse_stream(sample, threads, count_where=(b"Make", b"HOND"))
         cpu = {"value": round(nb / secs / 1e9, 4), "unit": "GB/s", "cores": threads, "kind": "port",
-               "sample": "%d x %d MiB of the same NDJSON stream, 10 MiB chunks on all host threads (oracle port; the Go reference cannot be built here) %s" % (reps, len(sample) >> 20, quota)}
+               "sample": "%d x %d MiB of the same NDJSON stream, 10 MiB chunks on all host threads (oracle port; the Go reference cannot be built here) %s" % (reps, len(sample) >> 20, quota),
+               "parse_count_where": round(n_c / t_c / 1e9, 4)}
 
     if rank == 0:
         total_bytes = n * world * args.steps
@@ -396,6 +432,14 @@ def main():
                          "unit": "GB/s", "frac": round(achieved / peak, 4), "peak_kind": peak_kind, "traffic": k1_traffic(n),
                          "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": round(t_s1 * 1e3, 4),
                          "input_read_gbs": round(n / t_s1 / 1e9, 2)},
+            "roofline_parse": {"bound": "hbm", "what": "whole device-resident step (K1 + K2a-f), algorithmic bytes 2*N_in + 8*N_idx + 8*N_tape + N_strings (SURVEY.md 8d)",
+                               "achieved": round((2 * n + 8 * int(info.n_idx) + 8 * tape_words + string_bytes) * world * args.steps / t_dev / 1e9, 2),
+                               "peak": peak, "unit": "GB/s",
+                               "frac": round((2 * n + 8 * int(info.n_idx) + 8 * tape_words + string_bytes) * args.steps / t_dev / 1e9 / peak, 4)},
+            "parse_count_where": {"value": round(total_bytes / t_cw / 1e9, 3), "unit": "GB/s", "ms_per_step": round(t_cw / args.steps * 1e3, 3),
+                                  "h2d_bytes_per_step": n, "d2h_bytes_per_step": 16, "records": n_records, "matches": int(cw_seen[0]),
+                                  "what": "sj_parse_count_where: host NDJSON in, parse + countWhere(Make == HOND) on the device "
+                                          "(parse_json_amd64_test.go:134), tape stays in HBM; same in-flight scheme and timer as e2e"},
             "clocks": sampler.summary(),
         }
         if cpu:

@@ -368,18 +368,33 @@ extern "C" int sj_parse(sj_ctx* c, const uint8_t* msg, size_t len, uint32_t flag
 // ---------------------------------------------------------------------------------
 // unit-test hooks for the stage-2 leaf routines
 // ---------------------------------------------------------------------------------
+// one WARP per string: the thread-serial routines (string_measure / string_copy) and the
+// warp-cooperative ones (warp_string_measure / warp_string_copy) both run and must agree; a
+// disagreement is reported as src_len = ~0
 __global__ void test_strings_kernel(const uint8_t* buf, const uint64_t* offs, size_t n, const uint64_t* max_size,
-                                    uint8_t* ok, uint64_t* src_len, uint64_t* dst_len, uint8_t* dst) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+                                    uint8_t* ok, uint64_t* src_len, uint64_t* dst_len, uint8_t* dst, uint8_t* dst2) {
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (i >= n) return;  // warp-uniform
     const uint64_t o = offs[i], e = offs[i + 1];
     StrCursor s{buf + o + 1, e > o ? e - o - 1 : 0};
-    uint64_t sl = 0, dl = 0;
-    bool good = e > o && string_measure(s, max_size[i], &sl, &dl);
-    ok[i] = good;
-    src_len[i] = sl;
-    dst_len[i] = dl;
-    if (good) string_copy(s, dst + o);
+    uint64_t sl = 0, dl = 0, sl_w = 0, dl_w = 0;
+    const bool good = e > o && string_measure(s, max_size[i], &sl, &dl);
+    const bool good_w = e > o && warp_string_measure(s, max_size[i], &sl_w, &dl_w);
+    bool same = good == good_w && (!good || (sl == sl_w && dl == dl_w));
+    if (good && same) {
+        if (lane == 0) string_copy(s, dst2 + o);
+        warp_string_copy(s, dst + o);
+        __syncwarp();
+        bool eq = true;
+        for (uint64_t k = lane; k < dl; k += 32) eq = eq && dst[o + k] == dst2[o + k];
+        same = __all_sync(FULL, eq);
+    }
+    if (lane == 0) {
+        ok[i] = good;
+        src_len[i] = same ? sl : ~0ull;
+        dst_len[i] = dl;
+    }
 }
 
 __global__ void test_numbers_kernel(const uint8_t* buf, const uint64_t* offs, size_t n, uint64_t* tag, uint64_t* val) {
@@ -396,7 +411,7 @@ extern "C" int sj_test_parse_strings(sj_ctx* c, const uint8_t* buf, const uint64
     if (!c || n == 0) return SJ_ERR_ARGUMENT;
     SJ_CUDA_CHECK(cudaSetDevice(c->device));
     const size_t total = offs[n];
-    size_t need = Carver::need({total + 64, (n + 1) * 8, n * 8, n, n * 8, n * 8, total + 64});
+    size_t need = Carver::need({total + 64, (n + 1) * 8, n * 8, n, n * 8, n * 8, total + 64, total + 64});
     int rc = c->test_in.reserve(need);
     if (rc) return rc;
     Carver k(c->test_in.p);
@@ -407,12 +422,14 @@ extern "C" int sj_test_parse_strings(sj_ctx* c, const uint8_t* buf, const uint64
     uint64_t* d_sl = k.take<uint64_t>(n);
     uint64_t* d_dl = k.take<uint64_t>(n);
     uint8_t* d_dst = k.take<uint8_t>(total + 64);
+    uint8_t* d_dst2 = k.take<uint8_t>(total + 64);
     SJ_CUDA_CHECK(cudaMemsetAsync(d_buf, 0, total + 64, c->stream));
     SJ_CUDA_CHECK(cudaMemcpyAsync(d_buf, buf, total, cudaMemcpyHostToDevice, c->stream));
     SJ_CUDA_CHECK(cudaMemcpyAsync(d_offs, offs, (n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
     SJ_CUDA_CHECK(cudaMemcpyAsync(d_max, max_size, n * 8, cudaMemcpyHostToDevice, c->stream));
     SJ_CUDA_CHECK(cudaMemsetAsync(d_dst, 0, total + 64, c->stream));
-    test_strings_kernel<<<(unsigned)((n + 63) / 64), 64, 0, c->stream>>>(d_buf, d_offs, n, d_max, d_ok, d_sl, d_dl, d_dst);
+    SJ_CUDA_CHECK(cudaMemsetAsync(d_dst2, 0, total + 64, c->stream));
+    test_strings_kernel<<<(unsigned)((n + 1) / 2), 64, 0, c->stream>>>(d_buf, d_offs, n, d_max, d_ok, d_sl, d_dl, d_dst, d_dst2);
     c->launches++;
     SJ_CUDA_CHECK(cudaGetLastError());
     SJ_CUDA_CHECK(cudaMemcpyAsync(ok, d_ok, n, cudaMemcpyDeviceToHost, c->stream));

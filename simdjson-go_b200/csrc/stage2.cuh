@@ -44,10 +44,13 @@ constexpr uint32_t AUX_LEN = 0x3fffffffu;
 constexpr int S2_THREADS = 256;
 constexpr int S2_ITEMS = 4;                       // consecutive structurals per thread in K2a / K2c / K2e
 constexpr int S2_TILE = S2_THREADS * S2_ITEMS;     // structurals per block = granularity of the K2b scan
-#ifndef SJ_S2_SHORT_STRING
-#define SJ_S2_SHORT_STRING 24
+// Strings that need the byte-exact slow paths (escapes, or no escape-free proof from K1's backslash
+// map) are handled by their own thread up to this extent and by the whole warp beyond it: one long
+// string per warp would otherwise keep 31 lanes idle for hundreds of serial iterations.
+#ifndef SJ_S2_COOP_MIN
+#define SJ_S2_COOP_MIN 64
 #endif
-constexpr uint32_t S2_SHORT_STRING = SJ_S2_SHORT_STRING;  // strings up to this length are copied by their own thread
+constexpr uint32_t S2_COOP_MIN = SJ_S2_COOP_MIN;  // 0xffffffff: never (thread-serial paths only)
 
 struct ScanVal {
     uint32_t w;     // tape words
@@ -418,6 +421,78 @@ __device__ __forceinline__ void string_copy(const StrCursor& s, uint8_t* dst) {
     }
 }
 
+// ---- the same two routines executed by a whole warp for ONE string (all 32 lanes call them with
+// identical arguments; control flow is warp-uniform).  The reference's assembly works on 32-byte
+// windows too (parse_string_amd64.s:84-100, 272-290): a window is loaded, the first '"' or '\\' in
+// it decides what happens next.  Here lane j holds byte j of the window and two ballots replace
+// VPCMPEQB / VPMOVMSKB; the escape itself is decoded redundantly by every lane (same addresses:
+// the loads broadcast). ----
+__device__ __forceinline__ bool warp_string_measure(const StrCursor& s, uint64_t max_string_size, uint64_t* src_len,
+                                                    uint64_t* dst_len) {
+    if (max_string_size == 0) return false;
+    const uint32_t lane = threadIdx.x & 31;
+    uint64_t p = 0, dl = 0;
+    for (;;) {
+        const uint32_t c = s.at(p + lane);
+        const uint32_t qm = __ballot_sync(FULL, c == '"'), ev = qm | __ballot_sync(FULL, c == '\\');
+        if (ev == 0) {
+            p += 32;
+            dl += 32;
+        } else {
+            const uint32_t j = __ffs(ev) - 1;
+            if ((qm >> j) & 1) {
+                *src_len = p + j;
+                *dst_len = dl + j;
+                return true;
+            }
+            uint32_t adv, cp, n;
+            if (!escape_step(s, p + j, &adv, &cp, &n)) return false;
+            dl += j + n;
+            p += j + adv;
+        }
+        if (!(p < max_string_size)) return false;
+    }
+}
+
+__device__ __forceinline__ void warp_string_copy(const StrCursor& s, uint8_t* dst) {
+    const uint32_t lane = threadIdx.x & 31;
+    uint64_t p = 0, dl = 0;
+    for (;;) {
+        const uint32_t c = s.at(p + lane);
+        const uint32_t qm = __ballot_sync(FULL, c == '"'), ev = qm | __ballot_sync(FULL, c == '\\');
+        const uint32_t j = ev ? __ffs(ev) - 1 : 32;
+        if (lane < j) dst[dl + lane] = (uint8_t)c;  // the plain bytes in front of the first event
+        if (ev == 0) {
+            p += 32;
+            dl += 32;
+            continue;
+        }
+        if ((qm >> j) & 1) return;
+        uint32_t adv, cp, n;
+        if (!escape_step(s, p + j, &adv, &cp, &n)) return;  // cannot happen after validation
+        if (lane == 0) {
+            uint8_t* o = dst + dl + j;
+            if (n == 1) {
+                o[0] = (uint8_t)cp;
+            } else if (n == 2) {
+                o[0] = (uint8_t)(0xC0 + (cp >> 6));
+                o[1] = (uint8_t)(0x80 | (cp & 63));
+            } else if (n == 3) {
+                o[0] = (uint8_t)(0xE0 + (cp >> 12));
+                o[1] = (uint8_t)(0x80 | ((cp >> 6) & 63));
+                o[2] = (uint8_t)(0x80 | (cp & 63));
+            } else {
+                o[0] = (uint8_t)(0xF0 + (cp >> 18));
+                o[1] = (uint8_t)(0x80 | ((cp >> 12) & 63));
+                o[2] = (uint8_t)(0x80 | ((cp >> 6) & 63));
+                o[3] = (uint8_t)(0x80 | (cp & 63));
+            }
+        }
+        dl += j + n;
+        p += j + adv;
+    }
+}
+
 // element j (runtime index) of four registers
 template <typename T>
 __device__ __forceinline__ T sel4(const T (&a)[4], int j) {
@@ -483,9 +558,9 @@ __global__ void __launch_bounds__(S2_THREADS) s2_classify_measure_kernel(const S
 #pragma unroll
     for (int j = 0; j < S2_ITEMS; j++) c[j] = i0 + j < p.n ? p.msg[pos[j]] : 0;
     if (i0 + S2_ITEMS < p.n) cn = p.msg[nxt[S2_ITEMS - 1]];
-    ScanVal v = sv_zero();
     uint32_t typ4 = 0;
     uint32_t auxv[S2_ITEMS] = {0, 0, 0, 0};
+    uint32_t coop = 0;  // bit j: string j is long and needs the byte-exact scan -> measured by the whole warp below
 #pragma unroll 1
     for (int j = 0; j < S2_ITEMS; j++) {
         const uint32_t i = i0 + j;
@@ -536,9 +611,13 @@ __global__ void __launch_bounds__(S2_THREADS) s2_classify_measure_kernel(const S
                 }
             }
             if (!fast) {
-                StrCursor sc{p.msg + ps + 1, p.len - ps - 1};
                 // peekSize: distance to the next structural, 0 when there is none (stage2...go:63-70)
-                ok = string_measure(sc, next_pos - ps, &sl, &dl);
+                if (next_pos - ps >= S2_COOP_MIN) {
+                    coop |= 1u << j;
+                } else {
+                    StrCursor sc{p.msg + ps + 1, p.len - ps - 1};
+                    ok = string_measure(sc, next_pos - ps, &sl, &dl);
+                }
             }
             if (ok) {
                 t = T_STRING;
@@ -553,9 +632,34 @@ __global__ void __launch_bounds__(S2_THREADS) s2_classify_measure_kernel(const S
         }
         typ4 |= t << (8 * j);
         if (j == 0) auxv[0] = aux; else if (j == 1) auxv[1] = aux; else if (j == 2) auxv[2] = aux; else auxv[3] = aux;
-        uint32_t next_t = T_START;  // only "newline or not" matters
-        if (has_next) next_t = (j + 1 < S2_ITEMS ? sel4(c, (j + 1) & 3) : cn) == '\n' ? T_NEWLINE : T_INVALID;
-        v = sv_add(v, contribution(t, aux, next_t));
+    }
+    // long strings left over: one at a time, 32 bytes per step, by the whole warp (every thread of the
+    // block gets here, so the full-mask ballots are safe)
+#pragma unroll
+    for (int j = 0; j < S2_ITEMS; j++) {
+        uint32_t m = __ballot_sync(FULL, (coop >> j) & 1);
+        while (m) {
+            const int owner = __ffs(m) - 1;
+            m &= m - 1;
+            const uint64_t ps = __shfl_sync(FULL, pos[j], owner), next_pos = __shfl_sync(FULL, nxt[j], owner);
+            const StrCursor sc{p.msg + ps + 1, p.len - ps - 1};
+            uint64_t sl = 0, dl = 0;
+            const bool ok = warp_string_measure(sc, next_pos - ps, &sl, &dl);
+            if (ok && (int)(threadIdx.x & 31) == owner) {
+                typ4 |= (uint32_t)T_STRING << (8 * j);  // was T_INVALID
+                auxv[j] = (uint32_t)dl | ((p.copy_strings || sl != dl) ? AUX_COPY : 0) | (sl != dl ? AUX_ESC : 0);
+            }
+        }
+    }
+    ScanVal v = sv_zero();
+#pragma unroll
+    for (int j = 0; j < S2_ITEMS; j++) {
+        const uint32_t i = i0 + j;
+        if (i < p.n) {
+            uint32_t next_t = T_START;  // only "newline or not" matters
+            if (i + 1 < p.n) next_t = (j + 1 < S2_ITEMS ? c[(j + 1) & 3] : cn) == '\n' ? T_NEWLINE : T_INVALID;
+            v = sv_add(v, contribution((typ4 >> (8 * j)) & 0xff, auxv[j], next_t));
+        }
     }
     if (i0 + S2_ITEMS <= p.n) {
         *reinterpret_cast<uint32_t*>(p.typ + i0) = typ4;
@@ -640,6 +744,7 @@ __global__ void __launch_bounds__(S2_THREADS) s2_emit_kernel(const Stage2Params 
         live = false;
     }
     uint32_t fast_len = 0;  // escape-free string to be copied by the whole warp below
+    bool coop_esc = false;  // long string with escapes: parse_string by the whole warp below
     if (live) {
         switch (t) {
         case T_OBJ_OPEN:
@@ -658,8 +763,12 @@ __global__ void __launch_bounds__(S2_THREADS) s2_emit_kernel(const Stage2Params 
                 p.tape[tp] = ((uint64_t)'"' << 56) | (STRINGBUFBIT + e.str);
                 if ((uint64_t)e.str + dl <= p.strings_cap) {
                     if (aux & AUX_ESC) {
-                        StrCursor s{p.msg + pos + 1, p.len - pos - 1};
-                        string_copy(s, p.strings + e.str);
+                        if (dl >= S2_COOP_MIN) {
+                            coop_esc = true;  // unescaped by the whole warp below
+                        } else {
+                            StrCursor s{p.msg + pos + 1, p.len - pos - 1};
+                            string_copy(s, p.strings + e.str);
+                        }
                     } else {
                         fast_len = dl;  // copied by the warp below
                     }
@@ -720,6 +829,16 @@ __global__ void __launch_bounds__(S2_THREADS) s2_emit_kernel(const Stage2Params 
             uint8_t* dst = p.strings + dp;
             for (uint32_t o = lane; o < ln; o += 32) dst[o] = src[o];
         }
+    }
+    // ---- long strings with escapes: one at a time, 32 source bytes per step (parse_string_amd64.s:260-479) ----
+    uint32_t em = __ballot_sync(FULL, coop_esc);
+    while (em) {
+        const int owner = __ffs(em) - 1;
+        em &= em - 1;
+        const uint64_t sp = __shfl_sync(FULL, (uint32_t)pos, owner);
+        const uint32_t dp = __shfl_sync(FULL, e.str, owner);
+        const StrCursor s{p.msg + sp + 1, p.len - sp - 1};
+        warp_string_copy(s, p.strings + dp);
     }
 }
 

@@ -86,6 +86,29 @@ def test_strings_random_vs_oracle(ctx, oracle):
             assert out == oracle.parse_string(it)[1], it
 
 
+def test_strings_long_random_vs_oracle(ctx, oracle):
+    """multi-window strings: the warp-cooperative measure / unescape (32 source bytes per step) and the
+    thread-serial routines both run in the hook and must agree with each other and with the oracle"""
+    rng = np.random.default_rng(424242)
+    alphabet = [b"a", b"\\", b'"', b"u", b"8", b"F", b"\\u", b"\\ud83d", b"\\ude00", b"\\uD800", b"n", b"/", b"\x00", b" ",
+                b"\xc3\xa9", b"\\\\", b'\\"', b"\\n", b"\\/", b"\\u00e9", b"\\u20AC", b"xyz" * 5, b"t" * 31, b"q" * 33, b"w" * 64,
+                b"0123456789abcdef" * 9]
+    items, maxs = [], []
+    for _ in range(4000):
+        body = b"".join(alphabet[j] for j in rng.integers(0, len(alphabet), rng.integers(0, 48)))
+        tail = b'"' if rng.integers(0, 10) else b""
+        it = b'"' + body + tail + b" " * int(rng.integers(0, 3)) + b","
+        items.append(it)
+        maxs.append(max(0, int(rng.integers(len(it) - 8, len(it) + 40))) if rng.integers(0, 4) else int(rng.integers(0, len(it) + 1)))
+    res = ctx.parse_strings(items, maxs)
+    for it, mx, (ok, sl, dl, out) in zip(items, maxs, res):
+        ok_o, sl_o, dl_o = oracle.parse_string_validate_only(it, mx)
+        assert ok == ok_o, (it, mx)
+        if ok:
+            assert (sl, dl) == (sl_o, dl_o), it
+            assert out == oracle.parse_string(it)[1], it
+
+
 def _tagname(tag):
     return chr(tag >> 56) if tag else ""
 
@@ -207,6 +230,33 @@ def test_structure_edge_cases(ctx, oracle):
         for copy in (True, False):
             _same_parse(ctx, oracle, d, ndjson=True, copy=copy)
         _same_parse(ctx, oracle, d, ndjson=False)
+
+
+def test_long_and_escaped_strings_in_documents(ctx, oracle):
+    """strings of 0..400 bytes with and without escapes, mixed inside the same warps: the short ones take the
+    thread-serial measure / unescape, the long ones (>= S2_COOP_MIN bytes) the warp-cooperative one; invalid
+    escapes and unterminated \\u sequences must fail exactly where the oracle fails"""
+    rng = np.random.default_rng(20240923)
+    pieces = [b"a", b"bc", b"\\n", b"\\/", b'\\"', b"\\\\", b"\\u00e9", b"\\ud83d\\ude00", b"\xe2\x82\xac", b" ", b"x" * 17, b"y" * 40,
+              b"http:\\/\\/t.co\\/", b"0123456789" * 7]
+
+    def rand_string(maxtok):
+        return b'"' + b"".join(pieces[j] for j in rng.integers(0, len(pieces), rng.integers(0, maxtok))) + b'"'
+
+    for trial in range(12):
+        maxtok = (3, 12, 40)[trial % 3]
+        vals = [rand_string(maxtok) for _ in range(700)]
+        doc = b"[" + b",".join(vals) + b"]"
+        obj = b"{" + b",".join(rand_string(maxtok) + b" : " + rand_string(maxtok) for _ in range(300)) + b"}"
+        for d in (doc, obj, doc[:-1] + b"," + obj + b"]"):
+            for copy in (True, False):
+                assert _same_parse(ctx, oracle, d, copy=copy) == 0
+    bad = [b'["' + b"x" * 100 + b'\\q' + b"y" * 100 + b'"]', b'["' + b"x" * 100 + b'\\u12"]', b'["' + b"x" * 90 + b'\\ud800\\n' + b"z" * 70 + b'"]',
+           b'["' + b"x" * 70 + b'\\ud800' + b"z" * 70 + b'"]', b'["' + b"x" * 64 + b'\\uZZZZ' + b"z" * 64 + b'"]',
+           b'["' + b"k" * 200 + b'\\u00e9' * 30 + b'", "' + b"k" * 31 + b'\\', b'["' + b"s" * 300 + b'\\ud83d\\ude00' * 20 + b'"]']
+    for d in bad:
+        for copy in (True, False):
+            _same_parse(ctx, oracle, d, copy=copy)
 
 
 def test_large_documents(ctx, oracle_native):

@@ -1,7 +1,7 @@
 """Device-resident timings of the BASELINE.json configs that are not the bench.py line:
 single documents built by replicating a fixture inside one array (`[doc,doc,...]`), parsed with
 sj_parse_device (stage 1 + stage 2) and with the stage-1 kernel alone.  Prints a markdown table.
-usage: config_bench.py [MiB per document] (default 256)"""
+usage: config_bench.py [MiB per document (default 256)] [comma-separated input names (default all)]"""
 import ctypes as C
 import os
 import sys
@@ -17,6 +17,7 @@ from simdjson_b200 import _lib
 from tests.util import load_fixture
 
 target = int(float(sys.argv[1]) * (1 << 20)) if len(sys.argv) > 1 else 256 << 20
+only = set(sys.argv[2].split(",")) if len(sys.argv) > 2 else None
 dev = torch.device("cuda:0")
 ctx = sj.Context(0)
 L = ctx.L
@@ -24,6 +25,8 @@ print("| input (replicated to ~%d MiB) | bytes | structurals | tape words | stri
 print("|---|---|---|---|---|---|---|---|---|---|")
 for name, nd in (("twitter", False), ("twitterescaped", False), ("canada", False), ("gsoc-2018", False), ("citm_catalog", False),
                  ("parking-citations", True)):
+    if only and name not in only:
+        continue
     doc = load_fixture(name).strip()
     k = max(1, target // (len(doc) + 1))
     msg = (b"\n".join([doc] * k)) if nd else (b"[" + b",".join([doc] * k) + b"]")

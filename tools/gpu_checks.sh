@@ -1,0 +1,38 @@
+#!/bin/bash
+# One gpurun call: GPU parity tests, per-config timings of the string-path variants, bench line,
+# ncu launch lists.  Everything lands in gpurun_out/ (scratch; summaries are copied to profiles/ by hand).
+#   usage: gpurun --timeout 900 -- 'bash tools/gpu_checks.sh [full|final]'
+set -u
+MODE=${1:-full}
+O=gpurun_out
+mkdir -p $O
+nvidia-smi --query-gpu=name,clocks.max.sm,clocks.max.mem --format=csv,noheader > $O/gpu.txt 2>&1
+nproc >> $O/gpu.txt
+( time timeout 700 python -m pytest tests -m gpu -q --timeout 300 ) > $O/pytest_gpu.log 2>&1
+echo "pytest rc=$?" >> $O/pytest_gpu.log
+tail -4 $O/pytest_gpu.log
+V=$PWD/build_variants
+if [ "$MODE" = full ]; then
+  if grep -Eq "failed|error" $O/pytest_gpu.log; then
+    ( SJ_B200_LIB=$V/serial.so timeout 700 python -m pytest tests -m gpu -q --timeout 300 ) > $O/pytest_gpu_serial.log 2>&1
+    tail -4 $O/pytest_gpu_serial.log
+  fi
+  timeout 300 python tools/config_bench.py 256 > $O/config_coop64.md 2>&1
+  SJ_B200_LIB=$V/serial.so timeout 300 python tools/config_bench.py 256 twitter,twitterescaped,gsoc-2018 > $O/config_serial.md 2>&1
+  SJ_B200_LIB=$V/coop32.so timeout 200 python tools/config_bench.py 256 twitter,twitterescaped,gsoc-2018 > $O/config_coop32.md 2>&1
+  SJ_B200_LIB=$V/coop128.so timeout 200 python tools/config_bench.py 256 twitter,twitterescaped,gsoc-2018 > $O/config_coop128.md 2>&1
+  tail -n +3 $O/config_coop64.md $O/config_serial.md $O/config_coop32.md $O/config_coop128.md | cut -d'|' -f2,7,10,11
+fi
+timeout 500 python bench.py > $O/bench_n1.json 2> $O/bench_n1.err
+echo "bench rc=$?"; cut -c1-400 $O/bench_n1.json
+if [ "$MODE" = final ]; then
+  timeout 300 python bench.py --impl reference > $O/bench_reference.json 2> $O/bench_reference.err
+  cut -c1-200 $O/bench_reference.json
+fi
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file $O/launches_bench_ndjson128MiB.csv \
+    python bench.py --steps 2 --warmup 1 --batch-mib 128 --inflight 1 --no-cpu > $O/bench_under_ncu.log 2>&1
+if [ "$MODE" = full ]; then
+  timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $O/launches_configs_64MiB.csv \
+      python tools/config_bench.py 64 twitterescaped,canada,gsoc-2018 > $O/configs_under_ncu.log 2>&1
+fi
+ls -la $O | tail -20
