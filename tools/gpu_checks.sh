@@ -19,9 +19,7 @@ if [ "$MODE" = full ]; then
   fi
   timeout 300 python tools/config_bench.py 256 > $O/config_coop64.md 2>&1
   SJ_B200_LIB=$V/serial.so timeout 300 python tools/config_bench.py 256 twitter,twitterescaped,gsoc-2018 > $O/config_serial.md 2>&1
-  SJ_B200_LIB=$V/coop32.so timeout 200 python tools/config_bench.py 256 twitter,twitterescaped,gsoc-2018 > $O/config_coop32.md 2>&1
-  SJ_B200_LIB=$V/coop128.so timeout 200 python tools/config_bench.py 256 twitter,twitterescaped,gsoc-2018 > $O/config_coop128.md 2>&1
-  tail -n +3 $O/config_coop64.md $O/config_serial.md $O/config_coop32.md $O/config_coop128.md | cut -d'|' -f2,7,10,11
+  tail -n +3 $O/config_coop64.md $O/config_serial.md | cut -d'|' -f2,7,10,11
 fi
 timeout 500 python bench.py > $O/bench_n1.json 2> $O/bench_n1.err
 echo "bench rc=$?"; cut -c1-400 $O/bench_n1.json
