@@ -70,3 +70,14 @@ def rebase_shard_tape(tape, tape_base, strings_base, msg_base):
     in_msg = strs & ~in_buf
     out[in_msg] = t[in_msg] + np.uint64(msg_base)
     return out
+
+
+def reduce_counts(local, group=None, device=None):
+    """countWhere / countObjects over a sharded stream (consume.cuh): records are independent, so the
+    answer for the whole stream is the sum of the per-shard (roots, matches) -- one all_reduce of
+    two integers.  Works on gloo (CPU tensors) and nccl (device tensors)."""
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([int(x) for x in local], dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return tuple(int(x) for x in t.tolist())

@@ -37,6 +37,10 @@ def _worker(rank, world, port, copy, outdir):
     base, totals = exchange_totals((b - a, len(tape), len(strings)))
     assert base[0] == a and len(totals) == world
     reb = rebase_shard_tape(tape, base[1], base[2], a + off)
+    # tape consumers over a sharded stream: per-shard countWhere, one all_reduce of two integers
+    from simdjson_b200.parallel import reduce_counts
+    roots, matches = o.count_where(tape, strings, stream[a + off:a + off + ln], b"Make", b"HOND")
+    assert reduce_counts((roots, matches)) == (1000, 116)  # ndjson_test.go:263
     np.save(os.path.join(outdir, "tape%d.npy" % rank), reb)
     with open(os.path.join(outdir, "str%d.bin" % rank), "wb") as f:
         f.write(strings)
@@ -83,3 +87,20 @@ def test_split_at_newlines_covers_and_aligns():
         assert parts[0][0] == 0 and parts[-1][1] == len(buf)
         for (a, b), (c, d) in zip(parts, parts[1:]):
             assert b == c and (b == len(buf) or buf[b - 1:b] == b"\n")
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference (the CPU arm of the driver's ratio) runs without a GPU and prints one
+    JSON line with the contract's keys"""
+    import json
+    import subprocess
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["value"] > 0 and line["unit"] == "GB/s"
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
