@@ -39,6 +39,9 @@ extern "C" {
 #define SJ_ERR_CAPACITY 4   /* caller buffer too small; *_len hold the required sizes */
 #define SJ_ERR_TOO_LARGE 5  /* message longer than SJ_MAX_MESSAGE bytes per call */
 #define SJ_ERR_ARGUMENT 6
+#define SJ_STREAM_END 7   /* sj_stream_next: input closed and every result delivered (io.EOF, simdjson_amd64.go:189) */
+#define SJ_STREAM_EMPTY 8 /* sj_stream_next: nothing handed to a worker yet -- write more (or close the input) */
+#define SJ_STREAM_BUSY 9  /* sj_stream_close_input: every slot is in use -- take a result first, then call again */
 /* negative values: -(1000 + cudaError_t) */
 
 #define SJ_MAX_MESSAGE 0x7fffff00ull /* positions are uint32, string lengths keep one flag bit */
@@ -106,6 +109,39 @@ int sj_count_where_device(sj_ctx* ctx, const uint8_t* d_msg, const uint64_t* d_t
                           size_t value_len, uint64_t* roots, uint64_t* matches);
 int sj_parse_count_where(sj_ctx* ctx, const uint8_t* msg, size_t len, uint32_t flags, const uint8_t* key,
                          size_t key_len, const uint8_t* value, size_t value_len, uint64_t* roots, uint64_t* matches);
+
+/*
+ * ParseNDStream (simdjson_amd64.go:116-215) inside the library: the caller pushes the bytes of an
+ * NDJSON stream (any host memory, pageable included: they are staged once into pinned buffers),
+ * the library cuts them at record boundaries into chunks of about `chunk_bytes` (:157-174; sized
+ * to fill a GPU instead of the reference's 10 MiB), parses up to `inflight` chunks concurrently
+ * (:132; each on its own context = CUDA stream, so H2D, kernels and D2H overlap) and hands the
+ * results out in input order (:134-152), each an independent {Message, Tape, Strings} triple.
+ * The first failing chunk ends the stream with its error (:196).  No call blocks on a full
+ * pipeline, so one thread can drive it:
+ *     while (input left)  { sj_stream_write(s, p, n, &taken); p += taken; n -= taken;
+ *                           if (taken == 0) { sj_stream_next(s, &r); ...use r...; sj_stream_release(s, &r); } }
+ *     while (sj_stream_close_input(s) == SJ_STREAM_BUSY) { next / release }
+ *     while (sj_stream_next(s, &r) == SJ_OK) { ...; sj_stream_release(s, &r); }      // ends with SJ_STREAM_END
+ * One writer thread and one reader thread may also run concurrently.
+ */
+typedef struct sj_stream sj_stream;
+typedef struct {
+    const uint8_t* message;  /* trimmed chunk = ParsedJson.Message (no-copy string offsets index into it) */
+    size_t message_len;
+    const uint64_t* tape;    /* ParsedJson.Tape */
+    size_t tape_len;
+    const uint8_t* strings;  /* ParsedJson.Strings.B */
+    size_t strings_len;
+    uint64_t seq;            /* chunk number in input order */
+    void* slot;              /* owner of the (pinned) buffers above; valid until sj_stream_release */
+} sj_stream_result;
+int sj_stream_create(int device, int inflight, size_t chunk_bytes, uint32_t flags, sj_stream** out);
+void sj_stream_destroy(sj_stream* s);
+int sj_stream_write(sj_stream* s, const uint8_t* data, size_t len, size_t* taken);
+int sj_stream_close_input(sj_stream* s);
+int sj_stream_next(sj_stream* s, sj_stream_result* res);
+int sj_stream_release(sj_stream* s, const sj_stream_result* res);
 
 /*
  * Stage 1 + flatten only (findStructuralIndices, stage1_find_marks_amd64.go:41):

@@ -118,6 +118,9 @@ extern "C" const char* sj_error_string(int rc) {
     case SJ_ERR_CAPACITY: return "output buffer too small";
     case SJ_ERR_TOO_LARGE: return "message too large for one call";
     case SJ_ERR_ARGUMENT: return "bad argument";
+    case SJ_STREAM_END: return "end of stream";
+    case SJ_STREAM_EMPTY: return "no chunk in flight";
+    case SJ_STREAM_BUSY: return "every stream slot is in use";
     default: return rc < 0 ? cudaGetErrorString((cudaError_t)(-rc - 1000)) : "unknown error";
     }
 }
@@ -408,6 +411,7 @@ extern "C" int sj_test_flatten_bits(sj_ctx* c, const uint64_t* masks, size_t nma
 
 #include "sj_parse.inl"
 #include "sj_consume.inl"
+#include "sj_stream.inl"
 
 #ifdef SJ_PROFILE_PHASES
 // development aid (not part of the C ABI): read / clear the per-phase cycle counters

@@ -87,24 +87,8 @@ extern "C" int sj_parse_count_where(sj_ctx* c, const uint8_t* msg, size_t len, u
     if (!c || !roots || !matches) return SJ_ERR_ARGUMENT;
     *roots = 0;
     *matches = 0;
-    size_t a = 0, b = 0;
-    if (len) trim_space(msg, len, &a, &b);
-    const size_t n = b - a;
-    if (n == 0) return SJ_ERR_STAGE1;
-    if (n > SJ_MAX_MESSAGE) return SJ_ERR_TOO_LARGE;
-    SJ_CUDA_CHECK(cudaSetDevice(c->device));
-    int rc = upload_message(c, msg + a, n);
-    if (rc) return rc;
-    Stage1Result r1;
-    rc = stage1_positions(c, c->msg.as<uint8_t>(), n, (flags & SJ_FLAG_NDJSON) != 0, &r1);
-    if (rc) return rc;
-    const uint8_t last_char = r1.n_idx && r1.last_pos < n ? msg[a + r1.last_pos] : 0;
-    if (!stage1_ok(r1, last_char)) return SJ_ERR_STAGE1;
     Stage2Result r2;
-    rc = run_stage2(c, c->msg.as<uint8_t>(), n, c->idx.as<uint32_t>(), r1.n_idx, flags, nullptr, 0, nullptr, 0, &r2,
-                    c->s2c.as<uint32_t>());
-    if (rc) return rc;
-    rc = stage2_verdict(r2);
+    int rc = parse_into_ctx(c, msg, len, flags, nullptr, nullptr, &r2);
     if (rc) return rc;
     // tape, strings and message stay in HBM; only the two counts travel back
     return sj_count_where_device(c, c->last_msg, c->last_tape, (size_t)c->last_tape_len, c->last_strings, key, klen, value,

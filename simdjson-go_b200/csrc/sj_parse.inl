@@ -365,6 +365,32 @@ extern "C" int sj_parse(sj_ctx* c, const uint8_t* msg, size_t len, uint32_t flag
     return SJ_OK;
 }
 
+// parseMessage up to the point where tape and strings sit in the context's device buffers
+// (c->last_*): trim, upload, stage 1, stage 2, verdict.  Shared by the entry points that do not
+// copy into caller-provided host buffers (tape consumers, the NDJSON stream).
+static int parse_into_ctx(sj_ctx* c, const uint8_t* msg, size_t len, uint32_t flags, size_t* msg_off, size_t* msg_len,
+                          Stage2Result* r2) {
+    size_t a = 0, b = 0;
+    if (len) trim_space(msg, len, &a, &b);
+    if (msg_off) *msg_off = a;
+    if (msg_len) *msg_len = b - a;
+    const size_t n = b - a;
+    if (n == 0) return SJ_ERR_STAGE1;
+    if (n > SJ_MAX_MESSAGE) return SJ_ERR_TOO_LARGE;
+    SJ_CUDA_CHECK(cudaSetDevice(c->device));
+    int rc = upload_message(c, msg + a, n);
+    if (rc) return rc;
+    Stage1Result r1;
+    rc = stage1_positions(c, c->msg.as<uint8_t>(), n, (flags & SJ_FLAG_NDJSON) != 0, &r1);
+    if (rc) return rc;
+    const uint8_t last_char = r1.n_idx && r1.last_pos < n ? msg[a + r1.last_pos] : 0;
+    if (!stage1_ok(r1, last_char)) return SJ_ERR_STAGE1;
+    rc = run_stage2(c, c->msg.as<uint8_t>(), n, c->idx.as<uint32_t>(), r1.n_idx, flags, nullptr, 0, nullptr, 0, r2,
+                    c->s2c.as<uint32_t>());
+    if (rc) return rc;
+    return stage2_verdict(*r2);
+}
+
 // ---------------------------------------------------------------------------------
 // unit-test hooks for the stage-2 leaf routines
 // ---------------------------------------------------------------------------------

@@ -20,8 +20,15 @@ EXPORTS = [
     "sj_host_free", "sj_trim_space", "sj_bounds", "sj_parse", "sj_parse_device", "sj_find_structural_indices", "sj_stage1_device",
     "sj_stage1_launch", "sj_ctx_sync", "sj_event_record", "sj_event_elapsed_ms", "sj_kernel_launches",
     "sj_test_block_masks", "sj_test_finalize", "sj_test_flatten_bits", "sj_test_parse_strings",
-    "sj_test_parse_numbers", "sj_count_where_device", "sj_parse_count_where",
+    "sj_test_parse_numbers", "sj_count_where_device", "sj_parse_count_where", "sj_stream_create", "sj_stream_destroy",
+    "sj_stream_write", "sj_stream_close_input", "sj_stream_next", "sj_stream_release",
 ]
+STREAM_END, STREAM_EMPTY, STREAM_BUSY = 7, 8, 9
+
+
+class StreamResult(C.Structure):
+    _fields_ = [("message", C.c_void_p), ("message_len", C.c_size_t), ("tape", C.c_void_p), ("tape_len", C.c_size_t),
+                ("strings", C.c_void_p), ("strings_len", C.c_size_t), ("seq", C.c_uint64), ("slot", C.c_void_p)]
 
 
 class Stage1Info(C.Structure):
@@ -90,6 +97,18 @@ def load():
     L.sj_count_where_device.argtypes = [vp, vp, vp, sz, vp, C.c_char_p, sz, C.c_char_p, sz, C.POINTER(u64), C.POINTER(u64)]
     L.sj_parse_count_where.restype = i32
     L.sj_parse_count_where.argtypes = [vp, vp, sz, u32, C.c_char_p, sz, C.c_char_p, sz, C.POINTER(u64), C.POINTER(u64)]
+    L.sj_stream_create.restype = i32
+    L.sj_stream_create.argtypes = [i32, i32, sz, u32, C.POINTER(vp)]
+    L.sj_stream_destroy.restype = None
+    L.sj_stream_destroy.argtypes = [vp]
+    L.sj_stream_write.restype = i32
+    L.sj_stream_write.argtypes = [vp, vp, sz, szp]
+    L.sj_stream_close_input.restype = i32
+    L.sj_stream_close_input.argtypes = [vp]
+    L.sj_stream_next.restype = i32
+    L.sj_stream_next.argtypes = [vp, C.POINTER(StreamResult)]
+    L.sj_stream_release.restype = i32
+    L.sj_stream_release.argtypes = [vp, C.POINTER(StreamResult)]
     _lib = L
     return L
 

@@ -67,3 +67,73 @@ def ParseNDStream(reader, chunk_bytes=256 << 20, inflight=3, copy_strings=True, 
     finally:
         for c in ctxs:
             c.close()
+
+
+def ParseNDStreamNative(reader, chunk_bytes=256 << 20, inflight=3, copy_strings=True, device=0, read_bytes=16 << 20):
+    """The same stream driven through the library's own pipeline (sj_stream_*, sj_stream.inl): the
+    chunking at record boundaries, the pinned staging of (pageable) input, the worker threads and the
+    ordered delivery all live behind the C ABI, which is what a cgo caller binds.  One Python thread
+    drives it: write until the pipeline takes nothing more, then take the oldest result."""
+    import ctypes as C
+
+    import numpy as np
+
+    from . import _lib
+    L = _lib.load()
+    h = C.c_void_p()
+    rc = L.sj_stream_create(device, inflight, chunk_bytes, _lib.FLAG_COPY_STRINGS if copy_strings else 0, C.byref(h))
+    if rc != _lib.OK:
+        raise _lib.SjError(rc)
+
+    def take():
+        """next result as a ParsedJson (copied out of the pinned slot), None when nothing is in flight / at the end"""
+        res = _lib.StreamResult()
+        rc = L.sj_stream_next(h, C.byref(res))
+        if rc in (_lib.STREAM_EMPTY, _lib.STREAM_END):
+            return rc, None
+        if rc in (ERR_STAGE1, ERR_STAGE2):
+            raise ParseError("parsing input: " + ("Failed to find all structural indices for stage 1"
+                                                  if rc == ERR_STAGE1 else "Bad parsing while executing stage 2"))
+        if rc != _lib.OK:
+            raise _lib.SjError(rc)
+        msg = C.string_at(res.message, res.message_len)
+        tape = np.frombuffer(C.string_at(res.tape, res.tape_len * 8), dtype=np.uint64)
+        strings = C.string_at(res.strings, res.strings_len) if res.strings_len else b""
+        L.sj_stream_release(h, C.byref(res))
+        return rc, ParsedJson(msg, tape, strings)
+
+    try:
+        taken = C.c_size_t(0)
+        while True:
+            blk = reader.read(read_bytes)
+            if not blk:
+                break
+            view = np.frombuffer(blk, dtype=np.uint8)
+            off = 0
+            while off < view.size:
+                rc = L.sj_stream_write(h, view[off:].ctypes.data, view.size - off, C.byref(taken))
+                if rc in (ERR_STAGE1, ERR_STAGE2):
+                    take()  # raises the stream's error
+                if rc != _lib.OK:
+                    raise _lib.SjError(rc)
+                off += taken.value
+                if taken.value == 0:  # every slot is busy: deliver the oldest chunk
+                    rc, pj = take()
+                    if pj is not None:
+                        yield pj
+        while True:
+            rc = L.sj_stream_close_input(h)
+            if rc != _lib.STREAM_BUSY:
+                break
+            rc, pj = take()
+            if pj is not None:
+                yield pj
+        if rc != _lib.OK:
+            raise _lib.SjError(rc)
+        while True:
+            rc, pj = take()
+            if pj is None:
+                break
+            yield pj
+    finally:
+        L.sj_stream_destroy(h)

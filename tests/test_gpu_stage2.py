@@ -337,3 +337,51 @@ def test_parse_nd_stream(oracle_native):
     assert roots == 1000 * copies and hond == 116 * copies
     with pytest.raises(Exception):
         list(ParseNDStream(io.BytesIO(b'{"a":1}\n{"b":\n'), chunk_bytes=1 << 20))
+
+
+@pytest.mark.parametrize("chunk,inflight", [(300_000, 3), (50_000, 1), (1_500_000, 4)])
+def test_parse_nd_stream_native(oracle_native, chunk, inflight):
+    """the same ParseNDStream contract through the library's own pipeline (sj_stream_*): chunks cut at record
+    boundaries, several in flight, ordered delivery, every chunk bit-equal to the oracle's parse of the same bytes,
+    the whole stream covered exactly once"""
+    import io
+    from simdjson_b200.stream import ParseNDStreamNative
+    pk = load_fixture("parking-citations").strip()
+    copies = 7
+    stream = b"\n".join([pk] * copies) + b"\n\n  \n"
+    hond = roots = 0
+    pos = 0
+    nchunks = 0
+    for pj in ParseNDStreamNative(io.BytesIO(stream), chunk_bytes=chunk, inflight=inflight, read_bytes=777_777):
+        start = stream.index(pj.Message[:64], pos)
+        assert stream[start:start + len(pj.Message)] == pj.Message       # consecutive windows of the input
+        assert stream[pos:start].strip() == b""                           # nothing but blanks skipped in between
+        rc, tape, strs, _ = oracle_native.parse(pj.Message, ndjson=True)
+        assert rc == 0 and np.array_equal(pj.Tape, tape) and pj.Strings == strs
+        pos = start + len(pj.Message)
+        it = pj.Iter()
+        hond += it.count_where("Make", "HOND")
+        roots += sum(1 for _ in it.roots())
+        nchunks += 1
+    assert stream[pos:].strip() == b""
+    assert roots == 1000 * copies and hond == 116 * copies
+    assert nchunks >= len(stream) // (chunk + 400) and nchunks <= len(stream) // chunk + 2
+
+
+def test_parse_nd_stream_native_errors_and_big_records():
+    import io
+    from simdjson_b200.stream import ParseNDStreamNative
+    from simdjson_b200 import ParseError
+    with pytest.raises(ParseError):
+        list(ParseNDStreamNative(io.BytesIO(b'{"a":1}\n{"b":\n'), chunk_bytes=1 << 20))
+    with pytest.raises(ParseError):   # the second chunk fails: the first one is still delivered, then the error ends the stream
+        got = []
+        for pj in ParseNDStreamNative(io.BytesIO(b'{"a":1}\n' * 100 + b'{"b" 2}\n' * 100), chunk_bytes=800, inflight=2):
+            got.append(pj)
+    assert len(got) >= 1
+    assert list(ParseNDStreamNative(io.BytesIO(b""), chunk_bytes=1 << 20)) == []
+    assert list(ParseNDStreamNative(io.BytesIO(b" \n\n "), chunk_bytes=1 << 20)) == []
+    # one record much larger than the chunk size: the chunk grows until a record boundary shows up
+    big = b'{"k":"' + b"x" * 100_000 + b'"}'
+    out = list(ParseNDStreamNative(io.BytesIO(big + b"\n" + big + b"\n" + b'{"s":1}'), chunk_bytes=10_000, inflight=2, read_bytes=4096))
+    assert sum(sum(1 for _ in pj.Iter().roots()) for pj in out) == 3
