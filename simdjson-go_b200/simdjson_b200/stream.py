@@ -119,8 +119,9 @@ def ParseNDStreamNative(reader, chunk_bytes=256 << 20, inflight=3, copy_strings=
                 off += taken.value
                 if taken.value == 0:  # every slot is busy: deliver the oldest chunk
                     rc, pj = take()
-                    if pj is not None:
-                        yield pj
+                    if pj is None:
+                        raise RuntimeError("sj_stream: nothing taken and nothing in flight")
+                    yield pj
         while True:
             rc = L.sj_stream_close_input(h)
             if rc != _lib.STREAM_BUSY:
