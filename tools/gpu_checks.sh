@@ -23,6 +23,10 @@ if [ "$MODE" = full ]; then
 fi
 timeout 500 python bench.py > $O/bench_n1.json 2> $O/bench_n1.err
 echo "bench rc=$?"; cut -c1-400 $O/bench_n1.json
+if [ "$MODE" = full ]; then   # does a deeper pipeline close the gaps on the D2H engine?
+  timeout 300 python bench.py --inflight 5 --no-cpu > $O/bench_n1_inflight5.json 2> $O/bench_n1_inflight5.err
+  python -c "import json,sys; d=json.load(open('$O/bench_n1_inflight5.json')); print('inflight5 e2e', d['e2e'], 'pcw', d['parse_count_where']['value'])"
+fi
 if [ "$MODE" = final ]; then
   timeout 300 python bench.py --impl reference > $O/bench_reference.json 2> $O/bench_reference.err
   cut -c1-200 $O/bench_reference.json
