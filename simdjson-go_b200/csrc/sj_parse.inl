@@ -216,7 +216,11 @@ static int run_stage2(sj_ctx* c, const uint8_t* d_msg, size_t len, const uint32_
             lvl_total += sz;
         }
     }
-    size_t need2 = Carver::need({nb * 4, nb * 4, nb * 4, nb * 4, nb * 4, nb, (lvl_total + 8) * 4, ((size_t)tot.n_records + 2) * 4});
+    // numbers get their own dense kernels when at least one structural in 16 is a number
+    const uint32_t n_num = tot.n_numbers;
+    const bool dense_numbers = S2_DENSE_NUMBERS && n_num != 0 && (uint64_t)n_num * 16 >= n;
+    size_t need2 = Carver::need({nb * 4, nb * 4, nb * 4, nb * 4, nb * 4, nb, (lvl_total + 8) * 4, ((size_t)tot.n_records + 2) * 4,
+                                 dense_numbers ? (size_t)n_num * 4 : 0});
     rc = c->s2b.reserve(need2);
     if (rc) return rc;
     Carver k2(c->s2b.p);
@@ -228,9 +232,15 @@ static int run_stage2(sj_ctx* c, const uint8_t* d_msg, size_t len, const uint32_
     p.ctx_after = k2.take<uint8_t>(nb);
     int32_t* lvl_mem = k2.take<int32_t>(lvl_total + 8);
     p.rootpos = k2.take<uint32_t>((size_t)tot.n_records + 2);
+    p.numlist = dense_numbers ? k2.take<uint32_t>(n_num) : nullptr;
 
     s2_emit_kernel<<<(n + S2_THREADS - 1) / S2_THREADS, S2_THREADS, 0, c->stream>>>(p);
     c->launches++;
+    if (dense_numbers) {
+        s2_numlist_kernel<<<(n + 1023) / 1024, 1024, 0, c->stream>>>(p, n_num);
+        s2_numbers_kernel<<<(n_num + S2_THREADS - 1) / S2_THREADS, S2_THREADS, 0, c->stream>>>(p, n_num);
+        c->launches += 2;
+    }
     if (nb > 0) {
         AnsvLevels L;
         memset(&L, 0, sizeof L);

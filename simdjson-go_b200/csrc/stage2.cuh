@@ -51,6 +51,10 @@ constexpr int S2_TILE = S2_THREADS * S2_ITEMS;     // structurals per block = gr
 #define SJ_S2_COOP_MIN 64
 #endif
 constexpr uint32_t S2_COOP_MIN = SJ_S2_COOP_MIN;  // 0xffffffff: never (thread-serial paths only)
+#ifndef SJ_S2_DENSE_NUMBERS
+#define SJ_S2_DENSE_NUMBERS 1
+#endif
+constexpr bool S2_DENSE_NUMBERS = SJ_S2_DENSE_NUMBERS != 0;  // number-heavy documents: numbers parsed by their own dense kernel
 
 struct ScanVal {
     uint32_t w;     // tape words
@@ -230,6 +234,8 @@ struct Stage2Result {
     int64_t final_depth;
     uint32_t error;        // any stage-2 failure
     uint32_t overflow;     // tape / string capacity exceeded
+    uint32_t n_numbers;    // structurals that start a number (K2a)
+    uint32_t num_fill;     // fill pointer of the number list (K2g)
 };
 
 struct Stage2Params {
@@ -256,6 +262,7 @@ struct Stage2Params {
     int32_t* enc_after;  // [nb] innermost scope that is open right AFTER bracket k (bracket index, -1 = top level)
     uint8_t* ctx_after;  // [nb] its kind (CTX_ROOT / CTX_OBJ / CTX_ARR)
     uint32_t* rootpos;   // [records + 1] tape slot of each record's root-open word
+    uint32_t* numlist;   // [n_numbers] structural index of every number, or null: numbers are parsed inline by K2c
     // outputs
     uint64_t* tape;
     uint64_t tape_cap;
@@ -312,7 +319,10 @@ struct StrCursor {
 
 // One \-escape starting at body[b].  The window logic of the assembly reduces to: D = distance
 // from the backslash to the next raw '"' byte (looked for within 12 bytes);  \uXXXX needs
-// D >= 6, a surrogate pair D >= 12 (parse_string_amd64.s:101-148,178-180).
+// D >= 6, a surrogate pair D >= 12 (parse_string_amd64.s:101-148,178-180).  With body[b+1] == 'u'
+// that is: no raw quote among the four hex positions (digit_to_val would read it as 0), and for a
+// pair none among the second four either (positions 6 and 7 must be "\u" anyway) -- so the bytes
+// the decoder loads anyway are enough and no separate 12-byte search is needed.
 __device__ __forceinline__ bool escape_step(const StrCursor& s, uint64_t b, uint32_t* adv, uint32_t* cp_out,
                                             uint32_t* nbytes) {
     uint32_t e = s.at(b + 1);
@@ -324,21 +334,17 @@ __device__ __forceinline__ bool escape_step(const StrCursor& s, uint64_t b, uint
         *nbytes = 1;
         return true;
     }
-    uint32_t D = 12;
-    for (uint32_t d = 1; d < 12; d++)
-        if (s.at(b + d) == '"') {
-            D = d;
-            break;
-        }
-    if (D < 6) return false;
-    uint32_t cp = ((uint32_t)digit_to_val(s.at(b + 2)) << 12) | ((uint32_t)digit_to_val(s.at(b + 3)) << 8) |
-                  ((uint32_t)digit_to_val(s.at(b + 4)) << 4) | (uint32_t)digit_to_val(s.at(b + 5));
+    const uint32_t c2 = s.at(b + 2), c3 = s.at(b + 3), c4 = s.at(b + 4), c5 = s.at(b + 5);
+    if (c2 == '"' || c3 == '"' || c4 == '"' || c5 == '"') return false;  // D < 6
+    uint32_t cp = ((uint32_t)digit_to_val(c2) << 12) | ((uint32_t)digit_to_val(c3) << 8) | ((uint32_t)digit_to_val(c4) << 4) |
+                  (uint32_t)digit_to_val(c5);
     uint32_t a = 6;
     if ((cp & 0xFFFFFC00u) == 0xD800u) {
-        if (D < 12) return false;
         if (s.at(b + 6) != '\\' || s.at(b + 7) != 'u') return false;
-        uint32_t cp2 = ((uint32_t)digit_to_val(s.at(b + 8)) << 12) | ((uint32_t)digit_to_val(s.at(b + 9)) << 8) |
-                       ((uint32_t)digit_to_val(s.at(b + 10)) << 4) | (uint32_t)digit_to_val(s.at(b + 11));
+        const uint32_t c8 = s.at(b + 8), c9 = s.at(b + 9), c10 = s.at(b + 10), c11 = s.at(b + 11);
+        if (c8 == '"' || c9 == '"' || c10 == '"' || c11 == '"') return false;  // D < 12
+        uint32_t cp2 = ((uint32_t)digit_to_val(c8) << 12) | ((uint32_t)digit_to_val(c9) << 8) |
+                       ((uint32_t)digit_to_val(c10) << 4) | (uint32_t)digit_to_val(c11);
         if ((cp | cp2) > 0xFFFFu) return false;
         cp = (((cp << 10) + 0xFCA00000u) | (cp2 + 0xFFFF2400u)) + 0x10000u;  // low surrogate range NOT checked
         a = 12;
@@ -672,8 +678,23 @@ __global__ void __launch_bounds__(S2_THREADS) s2_classify_measure_kernel(const S
                 p.aux[i0 + j] = auxv[j];
             }
     }
+    // numbers of the block (decides whether they get their own dense kernel, K2g / K2h)
+    __shared__ uint32_t s_nnum[S2_THREADS / 32];
+    {
+        uint32_t nnum = 0;
+#pragma unroll
+        for (int j = 0; j < S2_ITEMS; j++) nnum += ((typ4 >> (8 * j)) & 0xff) == T_NUMBER ? 1u : 0u;
+        nnum = __reduce_add_sync(FULL, nnum);
+        if ((threadIdx.x & 31) == 0) s_nnum[threadIdx.x >> 5] = nnum;
+    }
     ScanVal total;
-    const ScanVal ex = block_exclusive_scan_small<S2_THREADS, S2_ITEMS>(v, total);
+    const ScanVal ex = block_exclusive_scan_small<S2_THREADS, S2_ITEMS>(v, total);  // (its barriers publish s_nnum)
+    if (threadIdx.x == 0) {
+        uint32_t nn = 0;
+#pragma unroll
+        for (int w = 0; w < S2_THREADS / 32; w++) nn += s_nnum[w];
+        if (nn) atomicAdd(&p.result->n_numbers, nn);
+    }
     if (threadIdx.x == 0) p.tile_sum[blockIdx.x] = total;
     // K2c works warp by warp (32 structurals = 8 threads here): their prefix inside the tile
     if ((threadIdx.x & (32 / S2_ITEMS - 1)) == 0) p.sub_pre[i0 >> 5] = ex;
@@ -782,6 +803,10 @@ __global__ void __launch_bounds__(S2_THREADS) s2_emit_kernel(const Stage2Params 
             break;
         }
         case T_NUMBER: {
+            if (p.numlist) {  // number-heavy document: parsed by K2h in dense warps; leave the tape slot behind
+                p.aux[i] = (uint32_t)tp;
+                break;
+            }
             uint64_t val = 0;
             uint64_t tag = parse_number(p.msg + pos, p.len - pos, &val);
             if (tag == 0) atomicOr(&p.result->error, 1u);
@@ -797,6 +822,9 @@ __global__ void __launch_bounds__(S2_THREADS) s2_emit_kernel(const Stage2Params 
             break;
         default: break;
         }
+    }
+    else if (i < p.n && t == T_NUMBER && p.numlist) {
+        p.aux[i] = 0xffffffffu;  // no room on the tape: K2h skips it
     }
     // ---- warp-cooperative copy of the warp's escape-free strings.  A string's own thread would copy
     // it byte by byte (one LSU transaction per byte and lane, trip count = the longest string of the
@@ -840,6 +868,53 @@ __global__ void __launch_bounds__(S2_THREADS) s2_emit_kernel(const Stage2Params 
         const StrCursor s{p.msg + sp + 1, p.len - sp - 1};
         warp_string_copy(s, p.strings + dp);
     }
+}
+
+// ---------------------------------------------------------------------------------
+// K2g / K2h: numbers in dense warps.  In a number-heavy document (canada.json: every third
+// structural) K2c's warps run parse_number with a third of their lanes.  K2g compacts the structural
+// indexes of the numbers (one atomic per block; the order of the list is irrelevant, every entry
+// carries its own tape slot in aux[]), K2h parses one number per thread with all lanes busy.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) s2_numlist_kernel(const Stage2Params p, uint32_t cap) {
+    __shared__ uint32_t s_cnt[32];
+    __shared__ uint32_t s_base;
+    const uint32_t i = blockIdx.x * 1024 + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool is_num = i < p.n && p.typ[i] == T_NUMBER;
+    const uint32_t m = __ballot_sync(FULL, is_num);
+    if (lane == 0) s_cnt[warp] = __popc(m);
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t own = s_cnt[lane];
+        uint32_t inc = own;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(FULL, inc, d);
+            if (lane >= (uint32_t)d) inc += t;
+        }
+        s_cnt[lane] = inc - own;  // exclusive prefix of the warp counts
+        if (lane == 31) s_base = inc ? atomicAdd(&p.result->num_fill, inc) : 0u;
+    }
+    __syncthreads();
+    if (is_num) {
+        const uint32_t slot = s_base + s_cnt[warp] + __popc(m & lanemask_lt());
+        if (slot < cap) p.numlist[slot] = i;
+    }
+}
+
+__global__ void __launch_bounds__(S2_THREADS) s2_numbers_kernel(const Stage2Params p, uint32_t count) {
+    const uint32_t k = blockIdx.x * S2_THREADS + threadIdx.x;
+    if (k >= count) return;
+    const uint32_t i = p.numlist[k];
+    const uint32_t tp = p.aux[i];
+    if (tp == 0xffffffffu) return;
+    const uint64_t pos = p.idx[i];
+    uint64_t val = 0;
+    const uint64_t tag = parse_number(p.msg + pos, p.len - pos, &val);  // parse_number.go:65
+    if (tag == 0) atomicOr(&p.result->error, 1u);
+    p.tape[tp] = tag;
+    p.tape[tp + 1] = val;
 }
 
 // ---------------------------------------------------------------------------------

@@ -259,6 +259,45 @@ def test_long_and_escaped_strings_in_documents(ctx, oracle):
             _same_parse(ctx, oracle, d, copy=copy)
 
 
+def test_number_heavy_documents_dense_kernel(ctx, oracle):
+    """documents where at least one structural in 16 is a number take the dense number kernels (K2g / K2h);
+    sparse ones keep the inline parse in K2c -- both must give the oracle's tape, and a bad number anywhere must
+    fail the document"""
+    rng = np.random.default_rng(5150)
+
+    def rand_number():
+        k = int(rng.integers(0, 8))
+        if k == 0:
+            return str(int(rng.integers(-2**63, 2**63 - 1, dtype=np.int64))).encode()
+        if k == 1:
+            return str(int(rng.integers(0, 2**64 - 1, dtype=np.uint64))).encode()
+        if k == 2:
+            return repr(float(rng.standard_normal() * 10.0 ** int(rng.integers(-300, 300)))).encode()
+        if k == 3:
+            return b"%d.%de%d" % (rng.integers(0, 10**9), rng.integers(0, 10**9), rng.integers(-330, 290))
+        if k == 4:
+            return b"-%d.%018d" % (rng.integers(0, 200), rng.integers(0, 10**18))
+        if k == 5:
+            return b"%d" % rng.integers(-1000, 1000)
+        if k == 6:
+            return b"0.%s" % (b"".join(b"%d" % d for d in rng.integers(0, 10, rng.integers(1, 40))))
+        return b"%dE+%d" % (rng.integers(1, 10**6), rng.integers(0, 30))
+
+    nums = [rand_number() for _ in range(20000)]
+    dense = b"[" + b",".join(nums) + b"]"
+    pairs = b"[" + b",".join(b"[%s,%s]" % (nums[i], nums[i + 1]) for i in range(0, 6000, 2)) + b"]"
+    sparse = b"[" + b",".join(b'{"k%d":"v","n":%s,"t":true,"s":"%s"}' % (i, nums[i], b"x" * (i % 50)) for i in range(1500)) + b"]"
+    nd = b"\n".join(b'{"a":%s,"b":[%s,%s]}' % (nums[i], nums[i + 1], nums[i + 2]) for i in range(0, 9000, 3))
+    for d, isnd in ((dense, False), (pairs, False), (sparse, False), (nd, True)):
+        for copy in (True, False):
+            assert _same_parse(ctx, oracle, d, ndjson=isnd, copy=copy) == 0
+    for badnum in (b"1e", b"-", b"01", b"1.", b"--1", b"1e400", b"0x10", b"1_000", b"+1", b".5"):
+        for where in (0, 7777, 19999):
+            bad = list(nums)
+            bad[where] = badnum
+            _same_parse(ctx, oracle, b"[" + b",".join(bad) + b"]")
+
+
 def test_large_documents(ctx, oracle_native):
     tw = load_fixture("twitter")
     big = b"[" + b",".join([tw] * 24) + b"]"           # ~15 MB single document, 60 k brackets per copy

@@ -13,13 +13,12 @@ echo "pytest rc=$?" >> $O/pytest_gpu.log
 tail -4 $O/pytest_gpu.log
 V=$PWD/build_variants
 if [ "$MODE" = full ]; then
-  if grep -Eq "failed|error" $O/pytest_gpu.log; then
-    ( SJ_B200_LIB=$V/serial.so timeout 700 python -m pytest tests -m gpu -q --timeout 300 ) > $O/pytest_gpu_serial.log 2>&1
-    tail -4 $O/pytest_gpu_serial.log
-  fi
-  timeout 300 python tools/config_bench.py 256 > $O/config_coop64.md 2>&1
-  SJ_B200_LIB=$V/serial.so timeout 300 python tools/config_bench.py 256 twitter,twitterescaped,gsoc-2018 > $O/config_serial.md 2>&1
-  tail -n +3 $O/config_coop64.md $O/config_serial.md | cut -d'|' -f2,7,10,11
+  timeout 300 python tools/config_bench.py 256 > $O/config_default.md 2>&1
+  for v in $V/*.so; do   # whatever variants were built for this run (compile-time switches)
+    n=$(basename $v .so)
+    SJ_B200_LIB=$v timeout 200 python tools/config_bench.py 256 twitterescaped,canada,citm_catalog > $O/config_$n.md 2>&1
+  done
+  tail -n +3 $O/config_*.md | cut -d'|' -f2,7,10,11
 fi
 timeout 500 python bench.py > $O/bench_n1.json 2> $O/bench_n1.err
 echo "bench rc=$?"; cut -c1-400 $O/bench_n1.json
@@ -35,6 +34,6 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --c
     python bench.py --steps 2 --warmup 1 --batch-mib 128 --inflight 1 --no-cpu > $O/bench_under_ncu.log 2>&1
 if [ "$MODE" = full ]; then
   timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $O/launches_configs_64MiB.csv \
-      python tools/config_bench.py 64 twitterescaped,canada,gsoc-2018 > $O/configs_under_ncu.log 2>&1
+      python tools/config_bench.py 64 twitterescaped,canada,twitter > $O/configs_under_ncu.log 2>&1
 fi
 ls -la $O | tail -20
