@@ -26,10 +26,8 @@ if [ "$MODE" = full ]; then   # does a deeper pipeline close the gaps on the D2H
   timeout 300 python bench.py --inflight 5 --no-cpu > $O/bench_n1_inflight5.json 2> $O/bench_n1_inflight5.err
   python -c "import json,sys; d=json.load(open('$O/bench_n1_inflight5.json')); print('inflight5 e2e', d['e2e'], 'pcw', d['parse_count_where']['value'])"
 fi
-if [ "$MODE" = final ]; then
-  timeout 300 python bench.py --impl reference > $O/bench_reference.json 2> $O/bench_reference.err
-  cut -c1-200 $O/bench_reference.json
-fi
+timeout 300 python bench.py --impl reference > $O/bench_reference.json 2> $O/bench_reference.err
+cut -c1-200 $O/bench_reference.json
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file $O/launches_bench_ndjson128MiB.csv \
     python bench.py --steps 2 --warmup 1 --batch-mib 128 --inflight 1 --no-cpu > $O/bench_under_ncu.log 2>&1
 if [ "$MODE" = full ]; then
