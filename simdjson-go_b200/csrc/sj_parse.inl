@@ -404,26 +404,36 @@ static int parse_into_ctx(sj_ctx* c, const uint8_t* msg, size_t len, uint32_t fl
 // ---------------------------------------------------------------------------------
 // unit-test hooks for the stage-2 leaf routines
 // ---------------------------------------------------------------------------------
-// one WARP per string: the thread-serial routines (string_measure / string_copy) and the
-// warp-cooperative ones (warp_string_measure / warp_string_copy) both run and must agree; a
-// disagreement is reported as src_len = ~0
+// one WARP per string: the thread-serial routines (string_measure / string_copy), the warp-cooperative ones
+// (warp_string_measure / warp_string_copy) and the all-escapes-at-once one (warp_string_fast, resolved against the
+// bound exactly as K2a does) all run and must agree; a disagreement is reported as src_len = ~0
 __global__ void test_strings_kernel(const uint8_t* buf, const uint64_t* offs, size_t n, const uint64_t* max_size,
-                                    uint8_t* ok, uint64_t* src_len, uint64_t* dst_len, uint8_t* dst, uint8_t* dst2) {
+                                    uint8_t* ok, uint64_t* src_len, uint64_t* dst_len, uint8_t* dst, uint8_t* dst2,
+                                    uint8_t* dst3) {
     const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
     if (i >= n) return;  // warp-uniform
     const uint64_t o = offs[i], e = offs[i + 1];
     StrCursor s{buf + o + 1, e > o ? e - o - 1 : 0};
-    uint64_t sl = 0, dl = 0, sl_w = 0, dl_w = 0;
-    const bool good = e > o && string_measure(s, max_size[i], &sl, &dl);
-    const bool good_w = e > o && warp_string_measure(s, max_size[i], &sl_w, &dl_w);
-    bool same = good == good_w && (!good || (sl == sl_w && dl == dl_w));
+    uint64_t sl = 0, dl = 0, sl_w = 0, dl_w = 0, sl_f = 0, dl_f = 0;
+    const uint64_t mx = max_size[i];
+    const bool good = e > o && string_measure(s, mx, &sl, &dl);
+    const bool good_w = e > o && warp_string_measure(s, mx, &sl_w, &dl_w);
+    bool good_f = false;
+    if (e > o && mx != 0) {
+        const int r = warp_string_fast<false>(s, mx, nullptr, &sl_f, &dl_f);
+        good_f = r == 1;
+        if (r == 2 || (r == 1 && sl_f >= mx)) good_f = warp_string_measure(s, mx, &sl_f, &dl_f);
+    }
+    bool same = good == good_w && good == good_f && (!good || (sl == sl_w && dl == dl_w && sl == sl_f && dl == dl_f));
     if (good && same) {
         if (lane == 0) string_copy(s, dst2 + o);
-        warp_string_copy(s, dst + o);
+        warp_string_copy(s, dst3 + o);
+        uint64_t sl_c = 0, dl_c = 0;
+        const int r = warp_string_fast<true>(s, ~0ull, dst + o, &sl_c, &dl_c);
         __syncwarp();
-        bool eq = true;
-        for (uint64_t k = lane; k < dl; k += 32) eq = eq && dst[o + k] == dst2[o + k];
+        bool eq = r == 1 && sl_c == sl && dl_c == dl;
+        for (uint64_t k = lane; k < dl; k += 32) eq = eq && dst[o + k] == dst2[o + k] && dst3[o + k] == dst2[o + k];
         same = __all_sync(FULL, eq);
     }
     if (lane == 0) {
@@ -447,7 +457,7 @@ extern "C" int sj_test_parse_strings(sj_ctx* c, const uint8_t* buf, const uint64
     if (!c || n == 0) return SJ_ERR_ARGUMENT;
     SJ_CUDA_CHECK(cudaSetDevice(c->device));
     const size_t total = offs[n];
-    size_t need = Carver::need({total + 64, (n + 1) * 8, n * 8, n, n * 8, n * 8, total + 64, total + 64});
+    size_t need = Carver::need({total + 64, (n + 1) * 8, n * 8, n, n * 8, n * 8, total + 64, total + 64, total + 64});
     int rc = c->test_in.reserve(need);
     if (rc) return rc;
     Carver k(c->test_in.p);
@@ -459,13 +469,15 @@ extern "C" int sj_test_parse_strings(sj_ctx* c, const uint8_t* buf, const uint64
     uint64_t* d_dl = k.take<uint64_t>(n);
     uint8_t* d_dst = k.take<uint8_t>(total + 64);
     uint8_t* d_dst2 = k.take<uint8_t>(total + 64);
+    uint8_t* d_dst3 = k.take<uint8_t>(total + 64);
     SJ_CUDA_CHECK(cudaMemsetAsync(d_buf, 0, total + 64, c->stream));
     SJ_CUDA_CHECK(cudaMemcpyAsync(d_buf, buf, total, cudaMemcpyHostToDevice, c->stream));
     SJ_CUDA_CHECK(cudaMemcpyAsync(d_offs, offs, (n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
     SJ_CUDA_CHECK(cudaMemcpyAsync(d_max, max_size, n * 8, cudaMemcpyHostToDevice, c->stream));
     SJ_CUDA_CHECK(cudaMemsetAsync(d_dst, 0, total + 64, c->stream));
     SJ_CUDA_CHECK(cudaMemsetAsync(d_dst2, 0, total + 64, c->stream));
-    test_strings_kernel<<<(unsigned)((n + 1) / 2), 64, 0, c->stream>>>(d_buf, d_offs, n, d_max, d_ok, d_sl, d_dl, d_dst, d_dst2);
+    SJ_CUDA_CHECK(cudaMemsetAsync(d_dst3, 0, total + 64, c->stream));
+    test_strings_kernel<<<(unsigned)((n + 1) / 2), 64, 0, c->stream>>>(d_buf, d_offs, n, d_max, d_ok, d_sl, d_dl, d_dst, d_dst2, d_dst3);
     c->launches++;
     SJ_CUDA_CHECK(cudaGetLastError());
     SJ_CUDA_CHECK(cudaMemcpyAsync(ok, d_ok, n, cudaMemcpyDeviceToHost, c->stream));

@@ -55,6 +55,10 @@ constexpr uint32_t S2_COOP_MIN = SJ_S2_COOP_MIN;  // 0xffffffff: never (thread-s
 #define SJ_S2_DENSE_NUMBERS 1
 #endif
 constexpr bool S2_DENSE_NUMBERS = SJ_S2_DENSE_NUMBERS != 0;  // number-heavy documents: numbers parsed by their own dense kernel
+#ifndef SJ_S2_FAST_ESCAPES
+#define SJ_S2_FAST_ESCAPES 1
+#endif
+constexpr bool S2_FAST_ESCAPES = SJ_S2_FAST_ESCAPES != 0;  // warp routines decode all escapes of a window at once (warp_string_fast)
 
 struct ScanVal {
     uint32_t w;     // tape words
@@ -499,6 +503,161 @@ __device__ __forceinline__ void warp_string_copy(const StrCursor& s, uint8_t* ds
     }
 }
 
+// ---- all escapes of a 32-byte window at once.  The two routines above pay one window (load, two
+// ballots, a redundant decode) per ESCAPE; text that is escaped character by character (twitterescaped:
+// "\u30c6\u30b9\u30c8...") makes that one window per six bytes.  Here every lane decodes "the escape
+// that would start at my byte" from its neighbours (shuffles), the lanes that really start one are
+// found from the parity of their backslash run, and prefix counts place every output byte -- about
+// the same work per window whatever the number of escapes in it.
+//   * a backslash starts an escape iff it sits at an even offset in its run of backslashes (the
+//     window begins at an unconsumed byte), unless it is the "\u" of the second half of a surrogate
+//     pair whose first half starts six bytes earlier;
+//   * only starts at lanes <= 20 are decoded (a pair needs 12 bytes); the window is consumed up to
+//     the closing quote or up to the first undecoded start (>= lane 21), whichever comes first;
+//   * two high surrogates six bytes apart make "which one is the second half" a chain: such a
+//     window takes one exact step instead (warp_string_copy's step), as does nothing else.
+// Returns 0 = invalid, 1 = done (src_len / dst_len set), 2 = `bound` source bytes passed without a
+// closing quote (the caller lets the exact routine decide).  The exact routines above stay the
+// reference: the test hook runs all versions on every input. ----
+template <bool COPY>
+__device__ __forceinline__ int warp_string_fast(const StrCursor& s, uint64_t bound, uint8_t* dst, uint64_t* src_len,
+                                                uint64_t* dst_len) {
+    const uint32_t lane = threadIdx.x & 31, lt = lanemask_lt();
+    uint64_t p = 0, dl = 0;
+    for (;;) {
+        if (p >= bound) return 2;
+        const uint32_t c = s.at(p + lane);
+        const uint32_t bs = __ballot_sync(FULL, c == '\\'), qm = __ballot_sync(FULL, c == '"');
+        if (bs == 0) {  // plain window
+            const uint32_t j = qm ? __ffs(qm) - 1 : 32;
+            if (COPY && lane < j) dst[dl + lane] = (uint8_t)c;
+            if (qm) {
+                *src_len = p + j;
+                *dst_len = dl + j;
+                return 1;
+            }
+            p += 32;
+            dl += 32;
+            continue;
+        }
+        // escape starts by run parity
+        bool sp = false;
+        if ((bs >> lane) & 1) {
+            const uint32_t below = ~bs & lt;
+            const uint32_t run_start = below ? 32 - __clz(below) : 0;
+            sp = ((lane - run_start) & 1) == 0;
+        }
+        const uint32_t SP = __ballot_sync(FULL, sp);
+        const uint32_t um = __ballot_sync(FULL, c == 'u');
+        // "\uXXXX starting at my byte": digits from lanes +2..+5 (meaningful for lanes <= 26)
+        const int32_t dv = digit_to_val(c);
+        const uint32_t d2 = (uint32_t)__shfl_down_sync(FULL, dv, 2), d3 = (uint32_t)__shfl_down_sync(FULL, dv, 3),
+                       d4 = (uint32_t)__shfl_down_sync(FULL, dv, 4), d5 = (uint32_t)__shfl_down_sync(FULL, dv, 5);
+        const uint32_t cpu = (d2 << 12) | (d3 << 8) | (d4 << 4) | d5;
+        const bool in5 = lane + 5 < 32;
+        const bool uok = in5 && ((qm >> ((lane + 2) & 31)) & 0xFu) == 0 && cpu <= 0xFFFFu;  // no raw quote among the digits
+        const bool isu = lane < 31 && ((um >> ((lane + 1) & 31)) & 1);
+        const uint32_t H = __ballot_sync(FULL, sp && isu && uok && (cpu & 0xFC00u) == 0xD800u);
+        const uint32_t e = __shfl_down_sync(FULL, c, 1);
+        const uint32_t cp2 = __shfl_down_sync(FULL, cpu, 6);
+        const bool uok2 = __shfl_down_sync(FULL, (int)uok, 6) != 0;
+        if (H & (H << 6)) {
+            // chain of high surrogates: one exact step (first event of the window), then look again
+            const uint32_t ev = bs | qm, j = __ffs(ev) - 1;
+            if (COPY && lane < j) dst[dl + lane] = (uint8_t)c;
+            if ((qm >> j) & 1) {
+                *src_len = p + j;
+                *dst_len = dl + j;
+                return 1;
+            }
+            uint32_t adv1, cp1, n1;
+            if (!escape_step(s, p + j, &adv1, &cp1, &n1)) return 0;
+            if (COPY && lane == 0) {
+                uint8_t* o = dst + dl + j;
+                if (n1 == 1) {
+                    o[0] = (uint8_t)cp1;
+                } else if (n1 == 2) {
+                    o[0] = (uint8_t)(0xC0 + (cp1 >> 6)), o[1] = (uint8_t)(0x80 | (cp1 & 63));
+                } else if (n1 == 3) {
+                    o[0] = (uint8_t)(0xE0 + (cp1 >> 12)), o[1] = (uint8_t)(0x80 | ((cp1 >> 6) & 63)), o[2] = (uint8_t)(0x80 | (cp1 & 63));
+                } else {
+                    o[0] = (uint8_t)(0xF0 + (cp1 >> 18)), o[1] = (uint8_t)(0x80 | ((cp1 >> 12) & 63));
+                    o[2] = (uint8_t)(0x80 | ((cp1 >> 6) & 63)), o[3] = (uint8_t)(0x80 | (cp1 & 63));
+                }
+            }
+            dl += j + n1;
+            p += j + adv1;
+            continue;
+        }
+        const uint32_t real = SP & ~(H << 6);  // second halves of pairs are not starts
+        const bool mine = ((real >> lane) & 1) && lane <= 20;
+        uint32_t adv = 0, n = 0, outcp = 0;
+        bool ok = true;
+        if (mine) {
+            if (!isu) {
+                outcp = escape_map(e);
+                ok = outcp != 0;
+                adv = 2;
+                n = 1;
+            } else if (!uok) {
+                ok = false;
+                adv = 6;
+                n = 1;
+            } else if ((cpu & 0xFC00u) == 0xD800u) {
+                adv = 12;
+                n = 4;
+                if (!(((bs >> (lane + 6)) & 1) && ((um >> (lane + 7)) & 1) && uok2)) {
+                    ok = false;
+                } else {
+                    const uint32_t x = (((cpu << 10) + 0xFCA00000u) | (cp2 + 0xFFFF2400u)) + 0x10000u;  // low surrogate range NOT checked
+                    if (x > 0x10FFFFu) {
+                        ok = false;
+                    } else {
+                        outcp = x;
+                        n = x < 0x80u ? 1 : x < 0x800u ? 2 : x < 0x10000u ? 3 : 4;
+                    }
+                }
+            } else {
+                adv = 6;
+                outcp = cpu;
+                n = cpu < 0x80u ? 1 : cpu < 0x800u ? 2 : 3;
+            }
+        }
+        const uint32_t consumed = __reduce_or_sync(FULL, mine ? (((1u << adv) - 1u) << lane) : 0u);
+        const uint32_t late = SP & ~consumed & 0xFFE00000u;  // undecoded starts (lanes >= 21)
+        const uint32_t Z = late ? __ffs(late) - 1 : 32;
+        const uint32_t qreal = qm & ~consumed;
+        const uint32_t Q = qreal ? __ffs(qreal) - 1 : 32;
+        const uint32_t E = Q < Z ? Q : Z;
+        if (__ballot_sync(FULL, mine && lane < E && !ok)) return 0;
+        uint32_t cnt = 0;
+        if (lane < E) cnt = mine ? n : (((consumed >> lane) & 1) ? 0u : 1u);
+        const uint32_t b0 = __ballot_sync(FULL, cnt & 1), b1 = __ballot_sync(FULL, cnt & 2), b2 = __ballot_sync(FULL, cnt & 4);
+        if (COPY && cnt) {
+            uint8_t* o = dst + dl + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
+            if (!mine) {
+                o[0] = (uint8_t)c;
+            } else if (n == 1) {
+                o[0] = (uint8_t)outcp;
+            } else if (n == 2) {
+                o[0] = (uint8_t)(0xC0 + (outcp >> 6)), o[1] = (uint8_t)(0x80 | (outcp & 63));
+            } else if (n == 3) {
+                o[0] = (uint8_t)(0xE0 + (outcp >> 12)), o[1] = (uint8_t)(0x80 | ((outcp >> 6) & 63)), o[2] = (uint8_t)(0x80 | (outcp & 63));
+            } else {
+                o[0] = (uint8_t)(0xF0 + (outcp >> 18)), o[1] = (uint8_t)(0x80 | ((outcp >> 12) & 63));
+                o[2] = (uint8_t)(0x80 | ((outcp >> 6) & 63)), o[3] = (uint8_t)(0x80 | (outcp & 63));
+            }
+        }
+        dl += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+        if (Q < Z) {
+            *src_len = p + Q;
+            *dst_len = dl;
+            return 1;
+        }
+        p += E;
+    }
+}
+
 // element j (runtime index) of four registers
 template <typename T>
 __device__ __forceinline__ T sel4(const T (&a)[4], int j) {
@@ -650,7 +809,16 @@ __global__ void __launch_bounds__(S2_THREADS) s2_classify_measure_kernel(const S
             const uint64_t ps = __shfl_sync(FULL, pos[j], owner), next_pos = __shfl_sync(FULL, nxt[j], owner);
             const StrCursor sc{p.msg + ps + 1, p.len - ps - 1};
             uint64_t sl = 0, dl = 0;
-            const bool ok = warp_string_measure(sc, next_pos - ps, &sl, &dl);
+            bool ok;
+            if (S2_FAST_ESCAPES) {
+                // the fast routine has no per-step bound test: its answer stands when the string closes inside the
+                // bound (every step of the exact routine then starts below it); anything else the exact one decides
+                const int r = warp_string_fast<false>(sc, next_pos - ps, nullptr, &sl, &dl);
+                ok = r == 1;
+                if (r == 2 || (r == 1 && sl >= next_pos - ps)) ok = warp_string_measure(sc, next_pos - ps, &sl, &dl);
+            } else {
+                ok = warp_string_measure(sc, next_pos - ps, &sl, &dl);
+            }
             if (ok && (int)(threadIdx.x & 31) == owner) {
                 typ4 |= (uint32_t)T_STRING << (8 * j);  // was T_INVALID
                 auxv[j] = (uint32_t)dl | ((p.copy_strings || sl != dl) ? AUX_COPY : 0) | (sl != dl ? AUX_ESC : 0);
@@ -739,7 +907,7 @@ __global__ void __launch_bounds__(1024) s2_scan_top_kernel(const ScanVal* in, ui
 // ---------------------------------------------------------------------------------
 // One structural per thread, warps independent of each other: with four structurals per thread the
 // tape stores of a warp spread over 32 sectors and the kernel got slower (541 -> 640 us).
-__global__ void __launch_bounds__(S2_THREADS) s2_emit_kernel(const Stage2Params p) {
+__global__ void __launch_bounds__(S2_THREADS, 8) s2_emit_kernel(const Stage2Params p) {  // 8 blocks per SM = 32 registers: the kernel hides its load latency with occupancy
     const uint32_t i = blockIdx.x * S2_THREADS + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31;
     uint32_t t = T_INVALID, aux = 0;
@@ -866,7 +1034,12 @@ __global__ void __launch_bounds__(S2_THREADS) s2_emit_kernel(const Stage2Params 
         const uint64_t sp = __shfl_sync(FULL, (uint32_t)pos, owner);
         const uint32_t dp = __shfl_sync(FULL, e.str, owner);
         const StrCursor s{p.msg + sp + 1, p.len - sp - 1};
-        warp_string_copy(s, p.strings + dp);
+        if (S2_FAST_ESCAPES) {
+            uint64_t sl_unused, dl_unused;
+            warp_string_fast<true>(s, ~0ull, p.strings + dp, &sl_unused, &dl_unused);  // validated by K2a: always ends at its quote
+        } else {
+            warp_string_copy(s, p.strings + dp);
+        }
     }
 }
 

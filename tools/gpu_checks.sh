@@ -16,7 +16,7 @@ if [ "$MODE" = full ]; then
   timeout 300 python tools/config_bench.py 256 > $O/config_default.md 2>&1
   for v in $V/*.so; do   # whatever variants were built for this run (compile-time switches)
     n=$(basename $v .so)
-    SJ_B200_LIB=$v timeout 200 python tools/config_bench.py 256 twitterescaped,canada,citm_catalog > $O/config_$n.md 2>&1
+    SJ_B200_LIB=$v timeout 200 python tools/config_bench.py 256 twitter,twitterescaped,gsoc-2018 > $O/config_$n.md 2>&1
   done
   tail -n +3 $O/config_*.md | cut -d'|' -f2,7,10,11
 fi
