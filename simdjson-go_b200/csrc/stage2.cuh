@@ -59,6 +59,10 @@ constexpr bool S2_DENSE_NUMBERS = SJ_S2_DENSE_NUMBERS != 0;  // number-heavy doc
 #define SJ_S2_FAST_ESCAPES 1
 #endif
 constexpr bool S2_FAST_ESCAPES = SJ_S2_FAST_ESCAPES != 0;  // warp routines decode all escapes of a window at once (warp_string_fast)
+#ifndef SJ_S2_FAST_MIN_BACKSLASHES
+#define SJ_S2_FAST_MIN_BACKSLASHES 3
+#endif
+constexpr uint32_t S2_FAST_MIN_BACKSLASHES = SJ_S2_FAST_MIN_BACKSLASHES;  // fewer in a window: one exact step per escape instead
 
 struct ScanVal {
     uint32_t w;     // tape words
@@ -540,29 +544,36 @@ __device__ __forceinline__ int warp_string_fast(const StrCursor& s, uint64_t bou
             dl += 32;
             continue;
         }
-        // escape starts by run parity
-        bool sp = false;
-        if ((bs >> lane) & 1) {
-            const uint32_t below = ~bs & lt;
-            const uint32_t run_start = below ? 32 - __clz(below) : 0;
-            sp = ((lane - run_start) & 1) == 0;
+        // one or two backslashes: the exact step (first event of the window) is cheaper than decoding all lanes
+        bool single = __popc(bs) <= (int)S2_FAST_MIN_BACKSLASHES - 1;
+        uint32_t SP = 0, um = 0, cpu = 0, H = 0, e = 0, cp2 = 0;
+        bool uok = false, isu = false, uok2 = false;
+        if (!single) {  // (warp-uniform: bs is a ballot)
+            // escape starts by run parity
+            bool sp = false;
+            if ((bs >> lane) & 1) {
+                const uint32_t below = ~bs & lt;
+                const uint32_t run_start = below ? 32 - __clz(below) : 0;
+                sp = ((lane - run_start) & 1) == 0;
+            }
+            SP = __ballot_sync(FULL, sp);
+            um = __ballot_sync(FULL, c == 'u');
+            // "\uXXXX starting at my byte": digits from lanes +2..+5 (meaningful for lanes <= 26)
+            const int32_t dv = digit_to_val(c);
+            const uint32_t d2 = (uint32_t)__shfl_down_sync(FULL, dv, 2), d3 = (uint32_t)__shfl_down_sync(FULL, dv, 3),
+                           d4 = (uint32_t)__shfl_down_sync(FULL, dv, 4), d5 = (uint32_t)__shfl_down_sync(FULL, dv, 5);
+            cpu = (d2 << 12) | (d3 << 8) | (d4 << 4) | d5;
+            const bool in5 = lane + 5 < 32;
+            uok = in5 && ((qm >> ((lane + 2) & 31)) & 0xFu) == 0 && cpu <= 0xFFFFu;  // no raw quote among the digits
+            isu = lane < 31 && ((um >> ((lane + 1) & 31)) & 1);
+            H = __ballot_sync(FULL, sp && isu && uok && (cpu & 0xFC00u) == 0xD800u);
+            e = __shfl_down_sync(FULL, c, 1);
+            cp2 = __shfl_down_sync(FULL, cpu, 6);
+            uok2 = __shfl_down_sync(FULL, (int)uok, 6) != 0;
         }
-        const uint32_t SP = __ballot_sync(FULL, sp);
-        const uint32_t um = __ballot_sync(FULL, c == 'u');
-        // "\uXXXX starting at my byte": digits from lanes +2..+5 (meaningful for lanes <= 26)
-        const int32_t dv = digit_to_val(c);
-        const uint32_t d2 = (uint32_t)__shfl_down_sync(FULL, dv, 2), d3 = (uint32_t)__shfl_down_sync(FULL, dv, 3),
-                       d4 = (uint32_t)__shfl_down_sync(FULL, dv, 4), d5 = (uint32_t)__shfl_down_sync(FULL, dv, 5);
-        const uint32_t cpu = (d2 << 12) | (d3 << 8) | (d4 << 4) | d5;
-        const bool in5 = lane + 5 < 32;
-        const bool uok = in5 && ((qm >> ((lane + 2) & 31)) & 0xFu) == 0 && cpu <= 0xFFFFu;  // no raw quote among the digits
-        const bool isu = lane < 31 && ((um >> ((lane + 1) & 31)) & 1);
-        const uint32_t H = __ballot_sync(FULL, sp && isu && uok && (cpu & 0xFC00u) == 0xD800u);
-        const uint32_t e = __shfl_down_sync(FULL, c, 1);
-        const uint32_t cp2 = __shfl_down_sync(FULL, cpu, 6);
-        const bool uok2 = __shfl_down_sync(FULL, (int)uok, 6) != 0;
-        if (H & (H << 6)) {
-            // chain of high surrogates: one exact step (first event of the window), then look again
+        if (H & (H << 6)) single = true;  // chain of high surrogates: which one is a second half is sequential
+        if (single) {
+            // one exact step (first event of the window), then look again
             const uint32_t ev = bs | qm, j = __ffs(ev) - 1;
             if (COPY && lane < j) dst[dl + lane] = (uint8_t)c;
             if ((qm >> j) & 1) {
