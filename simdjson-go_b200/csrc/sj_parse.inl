@@ -421,7 +421,7 @@ __global__ void test_strings_kernel(const uint8_t* buf, const uint64_t* offs, si
     const bool good_w = e > o && warp_string_measure(s, mx, &sl_w, &dl_w);
     bool good_f = false;
     if (e > o && mx != 0) {
-        const int r = warp_string_fast<false>(s, mx, nullptr, &sl_f, &dl_f);
+        const int r = warp_string_fast<false, 1>(s, mx, nullptr, &sl_f, &dl_f);
         good_f = r == 1;
         if (r == 2 || (r == 1 && sl_f >= mx)) good_f = warp_string_measure(s, mx, &sl_f, &dl_f);
     }
@@ -430,7 +430,7 @@ __global__ void test_strings_kernel(const uint8_t* buf, const uint64_t* offs, si
         if (lane == 0) string_copy(s, dst2 + o);
         warp_string_copy(s, dst3 + o);
         uint64_t sl_c = 0, dl_c = 0;
-        const int r = warp_string_fast<true>(s, ~0ull, dst + o, &sl_c, &dl_c);
+        const int r = warp_string_fast<true, (int)SJ_S2_FAST_MIN_BACKSLASHES>(s, ~0ull, dst + o, &sl_c, &dl_c);
         __syncwarp();
         bool eq = r == 1 && sl_c == sl && dl_c == dl;
         for (uint64_t k = lane; k < dl; k += 32) eq = eq && dst[o + k] == dst2[o + k] && dst3[o + k] == dst2[o + k];

@@ -59,10 +59,15 @@ constexpr bool S2_DENSE_NUMBERS = SJ_S2_DENSE_NUMBERS != 0;  // number-heavy doc
 #define SJ_S2_FAST_ESCAPES 1
 #endif
 constexpr bool S2_FAST_ESCAPES = SJ_S2_FAST_ESCAPES != 0;  // warp routines decode all escapes of a window at once (warp_string_fast)
+// K2c (unescape): windows with one or two backslashes take the exact step -- measured: twitter 224 -> 215 us,
+// twitterescaped 532 -> 556 us per 64 MiB against decoding every window.  K2a (measure): see SJ_S2_FAST_MEASURE.
 #ifndef SJ_S2_FAST_MIN_BACKSLASHES
 #define SJ_S2_FAST_MIN_BACKSLASHES 3
 #endif
-constexpr uint32_t S2_FAST_MIN_BACKSLASHES = SJ_S2_FAST_MIN_BACKSLASHES;  // fewer in a window: one exact step per escape instead
+// K2a's long-string measure: 0 = exact warp routine, 1 = warp_string_fast inlined, 2 = warp_string_fast behind a call
+#ifndef SJ_S2_FAST_MEASURE
+#define SJ_S2_FAST_MEASURE 0
+#endif
 
 struct ScanVal {
     uint32_t w;     // tape words
@@ -523,7 +528,7 @@ __device__ __forceinline__ void warp_string_copy(const StrCursor& s, uint8_t* ds
 // Returns 0 = invalid, 1 = done (src_len / dst_len set), 2 = `bound` source bytes passed without a
 // closing quote (the caller lets the exact routine decide).  The exact routines above stay the
 // reference: the test hook runs all versions on every input. ----
-template <bool COPY>
+template <bool COPY, int MIN_BACKSLASHES>
 __device__ __forceinline__ int warp_string_fast(const StrCursor& s, uint64_t bound, uint8_t* dst, uint64_t* src_len,
                                                 uint64_t* dst_len) {
     const uint32_t lane = threadIdx.x & 31, lt = lanemask_lt();
@@ -544,8 +549,8 @@ __device__ __forceinline__ int warp_string_fast(const StrCursor& s, uint64_t bou
             dl += 32;
             continue;
         }
-        // one or two backslashes: the exact step (first event of the window) is cheaper than decoding all lanes
-        bool single = __popc(bs) <= (int)S2_FAST_MIN_BACKSLASHES - 1;
+        // fewer backslashes than MIN_BACKSLASHES: the exact step (first event of the window) instead of decoding all lanes
+        bool single = __popc(bs) < MIN_BACKSLASHES;
         uint32_t SP = 0, um = 0, cpu = 0, H = 0, e = 0, cp2 = 0;
         bool uok = false, isu = false, uok2 = false;
         if (!single) {  // (warp-uniform: bs is a ballot)
@@ -667,6 +672,12 @@ __device__ __forceinline__ int warp_string_fast(const StrCursor& s, uint64_t bou
         }
         p += E;
     }
+}
+
+__device__ __noinline__ int warp_string_fast_measure_call(const uint8_t* body, uint64_t avail, uint64_t bound, uint64_t* src_len,
+                                                          uint64_t* dst_len) {
+    const StrCursor s{body, avail};
+    return warp_string_fast<false, 1>(s, bound, nullptr, src_len, dst_len);
 }
 
 // element j (runtime index) of four registers
@@ -821,10 +832,11 @@ __global__ void __launch_bounds__(S2_THREADS) s2_classify_measure_kernel(const S
             const StrCursor sc{p.msg + ps + 1, p.len - ps - 1};
             uint64_t sl = 0, dl = 0;
             bool ok;
-            if (S2_FAST_ESCAPES) {
+            if (S2_FAST_ESCAPES && SJ_S2_FAST_MEASURE != 0) {
                 // the fast routine has no per-step bound test: its answer stands when the string closes inside the
                 // bound (every step of the exact routine then starts below it); anything else the exact one decides
-                const int r = warp_string_fast<false>(sc, next_pos - ps, nullptr, &sl, &dl);
+                const int r = SJ_S2_FAST_MEASURE == 2 ? warp_string_fast_measure_call(sc.body, sc.avail, next_pos - ps, &sl, &dl)
+                                                      : warp_string_fast<false, 1>(sc, next_pos - ps, nullptr, &sl, &dl);
                 ok = r == 1;
                 if (r == 2 || (r == 1 && sl >= next_pos - ps)) ok = warp_string_measure(sc, next_pos - ps, &sl, &dl);
             } else {
@@ -1047,7 +1059,7 @@ __global__ void __launch_bounds__(S2_THREADS, 8) s2_emit_kernel(const Stage2Para
         const StrCursor s{p.msg + sp + 1, p.len - sp - 1};
         if (S2_FAST_ESCAPES) {
             uint64_t sl_unused, dl_unused;
-            warp_string_fast<true>(s, ~0ull, p.strings + dp, &sl_unused, &dl_unused);  // validated by K2a: always ends at its quote
+            warp_string_fast<true, (int)SJ_S2_FAST_MIN_BACKSLASHES>(s, ~0ull, p.strings + dp, &sl_unused, &dl_unused);  // validated by K2a
         } else {
             warp_string_copy(s, p.strings + dp);
         }

@@ -16,16 +16,14 @@ if [ "$MODE" = full ]; then
   timeout 300 python tools/config_bench.py 256 > $O/config_default.md 2>&1
   for v in $V/*.so; do   # whatever variants were built for this run (compile-time switches)
     n=$(basename $v .so)
+    ( SJ_B200_LIB=$v timeout 300 python -m pytest tests -m gpu -q --timeout 300 ) > $O/pytest_gpu_$n.log 2>&1
+    echo "$n: $(tail -1 $O/pytest_gpu_$n.log)"
     SJ_B200_LIB=$v timeout 200 python tools/config_bench.py 256 twitter,twitterescaped,gsoc-2018 > $O/config_$n.md 2>&1
   done
   tail -n +3 $O/config_*.md | cut -d'|' -f2,7,10,11
 fi
 timeout 500 python bench.py > $O/bench_n1.json 2> $O/bench_n1.err
 echo "bench rc=$?"; cut -c1-400 $O/bench_n1.json
-if [ "$MODE" = full ]; then   # does a deeper pipeline close the gaps on the D2H engine?
-  timeout 300 python bench.py --inflight 5 --no-cpu > $O/bench_n1_inflight5.json 2> $O/bench_n1_inflight5.err
-  python -c "import json,sys; d=json.load(open('$O/bench_n1_inflight5.json')); print('inflight5 e2e', d['e2e'], 'pcw', d['parse_count_where']['value'])"
-fi
 timeout 300 python bench.py --impl reference > $O/bench_reference.json 2> $O/bench_reference.err
 cut -c1-200 $O/bench_reference.json
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file $O/launches_bench_ndjson128MiB.csv \
