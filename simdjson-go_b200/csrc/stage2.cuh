@@ -65,8 +65,14 @@ constexpr bool S2_FAST_ESCAPES = SJ_S2_FAST_ESCAPES != 0;  // warp routines deco
 #define SJ_S2_FAST_MIN_BACKSLASHES 3
 #endif
 // K2a's long-string measure: 0 = exact warp routine, 1 = warp_string_fast inlined, 2 = warp_string_fast behind a call
+// measured (twitter / twitterescaped / gsoc-2018, GB/s per 256 MiB document): 0: 157.5 / 37.3 / 178.3,
+// 1: 131.7 / 48.5 / 168.0 (the inlined routine changes the code of the whole kernel), 2: 152.6 / 60.5 / 173.1
 #ifndef SJ_S2_FAST_MEASURE
-#define SJ_S2_FAST_MEASURE 0
+#define SJ_S2_FAST_MEASURE 2
+#endif
+// short-string copy of K2c: 0 = four predicated 8-byte steps per string, 1 = a loop that stops at the string's length
+#ifndef SJ_S2_SHORT_COPY_LOOP
+#define SJ_S2_SHORT_COPY_LOOP 0
 #endif
 
 struct ScanVal {
@@ -1034,9 +1040,13 @@ __global__ void __launch_bounds__(S2_THREADS, 8) s2_emit_kernel(const Stage2Para
             const uint4 d = q[r];
             const uint8_t* src = p.msg + d.x;
             uint8_t* dst = p.strings + d.y;
+#if SJ_S2_SHORT_COPY_LOOP
+            for (uint32_t o = b; o < d.z; o += 8) dst[o] = src[o];
+#else
 #pragma unroll
             for (uint32_t o = 0; o < 32; o += 8)
                 if (o + b < d.z) dst[o + b] = src[o + b];
+#endif
         }
         uint32_t m = longm;
         while (m) {
