@@ -70,10 +70,7 @@ constexpr bool S2_FAST_ESCAPES = SJ_S2_FAST_ESCAPES != 0;  // warp routines deco
 #ifndef SJ_S2_FAST_MEASURE
 #define SJ_S2_FAST_MEASURE 2
 #endif
-// short-string copy of K2c: 0 = four predicated 8-byte steps per string, 1 = a loop that stops at the string's length
-#ifndef SJ_S2_SHORT_COPY_LOOP
-#define SJ_S2_SHORT_COPY_LOOP 0
-#endif
+
 
 struct ScanVal {
     uint32_t w;     // tape words
@@ -1040,13 +1037,9 @@ __global__ void __launch_bounds__(S2_THREADS, 8) s2_emit_kernel(const Stage2Para
             const uint4 d = q[r];
             const uint8_t* src = p.msg + d.x;
             uint8_t* dst = p.strings + d.y;
-#if SJ_S2_SHORT_COPY_LOOP
-            for (uint32_t o = b; o < d.z; o += 8) dst[o] = src[o];
-#else
 #pragma unroll
-            for (uint32_t o = 0; o < 32; o += 8)
+            for (uint32_t o = 0; o < 32; o += 8)  // (a loop bounded by the length was measured: no difference)
                 if (o + b < d.z) dst[o + b] = src[o + b];
-#endif
         }
         uint32_t m = longm;
         while (m) {
