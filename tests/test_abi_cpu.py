@@ -51,3 +51,19 @@ def test_trim_space_matches_oracle(lib, oracle):
         buf = (C.c_uint8 * max(1, len(src))).from_buffer_copy(src or b"\0")
         lib.sj_trim_space(buf, len(src), C.byref(a), C.byref(b))
         assert (a.value, b.value) == oracle.trim_space(src), src
+
+
+def test_header_is_plain_c_and_links_from_c(lib, tmp_path):
+    """include/simdjson_b200.h compiled by a C11 compiler with -Werror, linked against the library from plain C
+    (what cgo sees); without a device the example stops at SJ_ERR_NO_DEVICE -- no CPU fallback"""
+    import subprocess
+    import torch
+    exe = str(tmp_path / "abi_example")
+    libdir = os.path.join(ROOT, "simdjson-go_b200")
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tools", "abi_example.c"), "-L" + libdir, "-lsimdjson_b200",
+                           "-Wl,-rpath," + libdir, "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert "trimmed window: [1, 49)" in out.stdout, out.stdout + out.stderr
+    if not torch.cuda.is_available():
+        assert out.returncode == 3 and "no sm_100 device" in out.stdout, out.stdout + out.stderr
