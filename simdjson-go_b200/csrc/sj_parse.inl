@@ -218,7 +218,7 @@ static int run_stage2(sj_ctx* c, const uint8_t* d_msg, size_t len, const uint32_
     }
     // numbers get their own dense kernels when at least one structural in 16 is a number
     const uint32_t n_num = tot.n_numbers;
-    const bool dense_numbers = S2_DENSE_NUMBERS && n_num != 0 && (uint64_t)n_num * 16 >= n;
+    const bool dense_numbers = S2_DENSE_NUMBERS && n_num != 0 && ((uint64_t)n_num << SJ_S2_DENSE_NUMBERS_SHIFT) >= n;
     size_t need2 = Carver::need({nb * 4, nb * 4, nb * 4, nb * 4, nb * 4, nb, (lvl_total + 8) * 4, ((size_t)tot.n_records + 2) * 4,
                                  dense_numbers ? (size_t)n_num * 4 : 0});
     rc = c->s2b.reserve(need2);

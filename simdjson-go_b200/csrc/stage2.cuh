@@ -55,6 +55,16 @@ constexpr uint32_t S2_COOP_MIN = SJ_S2_COOP_MIN;  // 0xffffffff: never (thread-s
 #define SJ_S2_DENSE_NUMBERS 1
 #endif
 constexpr bool S2_DENSE_NUMBERS = SJ_S2_DENSE_NUMBERS != 0;  // number-heavy documents: numbers parsed by their own dense kernel
+// tuning knobs for `tools/gpu_checks.sh` variants (build_variants/*.so); the defaults are the measured configuration
+#ifndef SJ_S2_DENSE_NUMBERS_SHIFT
+#define SJ_S2_DENSE_NUMBERS_SHIFT 4  // dense kernels when numbers << SHIFT >= structurals (one structural in 16)
+#endif
+#ifndef SJ_S2_EMIT_MIN_BLOCKS
+#define SJ_S2_EMIT_MIN_BLOCKS 8  // K2c: resident blocks per SM the register allocation must allow (8 = 32 registers)
+#endif
+#ifndef SJ_S2_NUMBERS_MIN_BLOCKS
+#define SJ_S2_NUMBERS_MIN_BLOCKS 0  // K2h: 0 = only the block size is given (ptxas settles at 32 registers + small spills today)
+#endif
 #ifndef SJ_S2_FAST_ESCAPES
 #define SJ_S2_FAST_ESCAPES 1
 #endif
@@ -933,7 +943,7 @@ __global__ void __launch_bounds__(1024) s2_scan_top_kernel(const ScanVal* in, ui
 // ---------------------------------------------------------------------------------
 // One structural per thread, warps independent of each other: with four structurals per thread the
 // tape stores of a warp spread over 32 sectors and the kernel got slower (541 -> 640 us).
-__global__ void __launch_bounds__(S2_THREADS, 8) s2_emit_kernel(const Stage2Params p) {  // 8 blocks per SM = 32 registers: the kernel hides its load latency with occupancy
+__global__ void __launch_bounds__(S2_THREADS, SJ_S2_EMIT_MIN_BLOCKS) s2_emit_kernel(const Stage2Params p) {  // 8 blocks per SM = 32 registers: the kernel hides its load latency with occupancy
     const uint32_t i = blockIdx.x * S2_THREADS + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31;
     uint32_t t = T_INVALID, aux = 0;
@@ -1102,7 +1112,11 @@ __global__ void __launch_bounds__(1024) s2_numlist_kernel(const Stage2Params p, 
     }
 }
 
+#if SJ_S2_NUMBERS_MIN_BLOCKS
+__global__ void __launch_bounds__(S2_THREADS, SJ_S2_NUMBERS_MIN_BLOCKS) s2_numbers_kernel(const Stage2Params p, uint32_t count) {
+#else
 __global__ void __launch_bounds__(S2_THREADS) s2_numbers_kernel(const Stage2Params p, uint32_t count) {
+#endif
     const uint32_t k = blockIdx.x * S2_THREADS + threadIdx.x;
     if (k >= count) return;
     const uint32_t i = p.numlist[k];
