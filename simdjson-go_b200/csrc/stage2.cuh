@@ -82,6 +82,15 @@ constexpr bool S2_FAST_ESCAPES = SJ_S2_FAST_ESCAPES != 0;  // warp routines deco
 #endif
 
 
+// K2c short-string copy (the source line with 30 % of K2c's instructions): by default ptxas forms both 64-bit lane
+// addresses again under each of the four predicated steps (LDC.64 + IADD3 + IADD3.X twice: 9 instructions per step);
+// with 1 an empty asm pins the two bases in registers and the steps become ISETP + LDG + STG with immediate offsets.
+// Built and its SASS inspected, NOT yet run on a GPU (the round's GPU budget was spent): the default stays 0 until it
+// has passed the GPU suite -- first candidate of the next round (tools/build_variants.sh pinned="-DSJ_S2_COPY_PINNED_BASE=1").
+#ifndef SJ_S2_COPY_PINNED_BASE
+#define SJ_S2_COPY_PINNED_BASE 0
+#endif
+
 struct ScanVal {
     uint32_t w;     // tape words
     uint32_t brk;   // brackets
@@ -1047,9 +1056,18 @@ __global__ void __launch_bounds__(S2_THREADS, SJ_S2_EMIT_MIN_BLOCKS) s2_emit_ker
             const uint4 d = q[r];
             const uint8_t* src = p.msg + d.x;
             uint8_t* dst = p.strings + d.y;
+#if SJ_S2_COPY_PINNED_BASE
+            const uint8_t* sb = src + b;
+            uint8_t* db = dst + b;
+            asm volatile("" : "+l"(sb), "+l"(db));  // the lane bases stay in registers: [base + 8 k] in the four steps
+#pragma unroll
+            for (uint32_t o = 0; o < 32; o += 8)
+                if (o + b < d.z) db[o] = sb[o];
+#else
 #pragma unroll
             for (uint32_t o = 0; o < 32; o += 8)  // (a loop bounded by the length was measured: no difference)
                 if (o + b < d.z) dst[o + b] = src[o + b];
+#endif
         }
         uint32_t m = longm;
         while (m) {
