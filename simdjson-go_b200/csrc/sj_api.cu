@@ -125,6 +125,8 @@ extern "C" const char* sj_error_string(int rc) {
     }
 }
 
+extern "C" void sj_ctx_destroy(sj_ctx* c);
+
 extern "C" int sj_ctx_create(int device, sj_ctx** out) {
     if (!out) return SJ_ERR_ARGUMENT;
     *out = nullptr;
@@ -142,26 +144,34 @@ extern "C" int sj_ctx_create(int device, sj_ctx** out) {
     if (!c) return SJ_ERR_ARGUMENT;
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
-    SJ_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    SJ_CUDA_CHECK(cudaEventCreate(&c->ev[0]));
-    SJ_CUDA_CHECK(cudaEventCreate(&c->ev[1]));
-    SJ_CUDA_CHECK(cudaHostAlloc(&c->host_result, 256, cudaHostAllocDefault));
-    int rc = c->result.reserve(256);
-    if (rc) return rc;
-    SJ_CUDA_CHECK(cudaFuncSetAttribute(stage1_flatten_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)S1_SMEM_BYTES));
-    SJ_CUDA_CHECK(cudaFuncSetAttribute(stage1_flatten_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)S1_SMEM_BYTES));
-    SJ_CUDA_CHECK(cudaFuncSetAttribute(stage1_flatten_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)S1_SMEM_BYTES));
-    SJ_CUDA_CHECK(cudaFuncSetAttribute(stage1_flatten_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)S1_SMEM_BYTES));
-    int per_sm = 0;
-    SJ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stage1_flatten_kernel<true, true>, S1_THREADS,
-                                                                S1_SMEM_BYTES));
-    if (per_sm < 1) return SJ_ERR_NO_DEVICE;
-    if (per_sm > S1_CTAS_PER_SM) per_sm = S1_CTAS_PER_SM;
-    c->s1_max_ctas = per_sm * c->sm_count;
+    // every failure below leaves through sj_ctx_destroy (stream, events, pinned result block, device scratch)
+    const int rc = [&]() -> int {
+        SJ_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        SJ_CUDA_CHECK(cudaEventCreate(&c->ev[0]));
+        SJ_CUDA_CHECK(cudaEventCreate(&c->ev[1]));
+        SJ_CUDA_CHECK(cudaHostAlloc(&c->host_result, 256, cudaHostAllocDefault));
+        int r = c->result.reserve(256);
+        if (r) return r;
+        SJ_CUDA_CHECK(cudaFuncSetAttribute(stage1_flatten_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)S1_SMEM_BYTES));
+        SJ_CUDA_CHECK(cudaFuncSetAttribute(stage1_flatten_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)S1_SMEM_BYTES));
+        SJ_CUDA_CHECK(cudaFuncSetAttribute(stage1_flatten_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)S1_SMEM_BYTES));
+        SJ_CUDA_CHECK(cudaFuncSetAttribute(stage1_flatten_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)S1_SMEM_BYTES));
+        int per_sm = 0;
+        SJ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stage1_flatten_kernel<true, true>, S1_THREADS,
+                                                                    S1_SMEM_BYTES));
+        if (per_sm < 1) return SJ_ERR_NO_DEVICE;
+        if (per_sm > S1_CTAS_PER_SM) per_sm = S1_CTAS_PER_SM;
+        c->s1_max_ctas = per_sm * c->sm_count;
+        return SJ_OK;
+    }();
+    if (rc) {
+        sj_ctx_destroy(c);
+        return rc;
+    }
     *out = c;
     return SJ_OK;
 }
@@ -169,15 +179,15 @@ extern "C" int sj_ctx_create(int device, sj_ctx** out) {
 extern "C" void sj_ctx_destroy(sj_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->msg,  &c->idx, &c->desc, &c->result, &c->s2a,     &c->s2b,     &c->s2c,      &c->s2d,
                       &c->s2e,  &c->s2f, &c->s2g,  &c->tape,   &c->strings, &c->test_in, &c->test_out, &c->test_aux,
                       &c->tc_small, &c->tc_roots};
     for (DevBuf* b : bufs) b->release();
     if (c->host_result) cudaFreeHost(c->host_result);
-    cudaEventDestroy(c->ev[0]);
-    cudaEventDestroy(c->ev[1]);
-    cudaStreamDestroy(c->stream);
+    if (c->ev[0]) cudaEventDestroy(c->ev[0]);
+    if (c->ev[1]) cudaEventDestroy(c->ev[1]);
+    if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
 

@@ -329,11 +329,13 @@ extern "C" int sj_parse_device(sj_ctx* c, const uint8_t* d_msg, size_t len, uint
     // the byte under the last structural comes back with the stage-1 result (stage1_finish_kernel)
     const uint8_t last_char = r1.n_idx && r1.last_pos < len ? (uint8_t)r1.last_char : 0;
     if (!stage1_ok(r1, last_char)) return SJ_ERR_STAGE1;
-    Stage2Result r2;
+    Stage2Result r2{};
     rc = run_stage2(c, d_msg, len, c->idx.as<uint32_t>(), r1.n_idx, flags, d_tape, tape_cap, d_strings, strings_cap, &r2,
                     c->s2c.as<uint32_t>());
-    *tape_len = r2.tape_len;
-    *strings_len = r2.strings_len;
+    if (rc == SJ_OK || rc == SJ_ERR_CAPACITY) {  // the required sizes (simdjson_b200.h): only when stage 2 got as far as its totals
+        *tape_len = r2.tape_len;
+        *strings_len = r2.strings_len;
+    }
     if (rc) return rc;
     return stage2_verdict(r2);
 }
@@ -359,11 +361,13 @@ extern "C" int sj_parse(sj_ctx* c, const uint8_t* msg, size_t len, uint32_t flag
     if (rc) return rc;
     uint8_t last_char = r1.n_idx && r1.last_pos < n ? msg[a + r1.last_pos] : 0;
     if (!stage1_ok(r1, last_char)) return SJ_ERR_STAGE1;
-    Stage2Result r2;
+    Stage2Result r2{};
     rc = run_stage2(c, c->msg.as<uint8_t>(), n, c->idx.as<uint32_t>(), r1.n_idx, flags, nullptr, 0, nullptr, 0, &r2,
                     c->s2c.as<uint32_t>());
-    *tape_len = r2.tape_len;
-    *strings_len = r2.strings_len;
+    if (rc == SJ_OK || rc == SJ_ERR_CAPACITY) {
+        *tape_len = r2.tape_len;
+        *strings_len = r2.strings_len;
+    }
     if (rc) return rc;
     rc = stage2_verdict(r2);
     if (rc) return rc;

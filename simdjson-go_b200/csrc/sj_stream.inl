@@ -228,9 +228,16 @@ extern "C" int sj_stream_write(sj_stream* s, const uint8_t* data, size_t len, si
                 const void* nl = memrchr(buf, '\n', sl.in_len);  // simdjson_amd64.go:165-174: cut at a record boundary
                 if (nl) {
                     const size_t cut = (size_t)(reinterpret_cast<const uint8_t*>(nl) - buf) + 1;
-                    s->carry.assign(buf + cut, buf + sl.in_len);
-                    sl.in_len = cut;
-                    submit = true;
+                    if (all_space(buf, cut)) {
+                        // only blank lines in front of the cut (e.g. "\n{...a record larger than the chunk...}"): a
+                        // whitespace-only chunk would fail stage 1, the reference skips blank lines -- drop them and keep filling
+                        memmove(buf, buf + cut, sl.in_len - cut);
+                        sl.in_len -= cut;
+                    } else {
+                        s->carry.assign(buf + cut, buf + sl.in_len);
+                        sl.in_len = cut;
+                        submit = true;
+                    }
                 }
             }
         }

@@ -15,7 +15,8 @@ M64 = (1 << 64) - 1
 @pytest.fixture(scope="module")
 def ctx():
     import simdjson_b200 as sj
-    assert sj.SupportedCPU(), "no sm_100 device (the CUDA path has no fallback)"
+    if not sj.SupportedCPU():
+        pytest.skip("no sm_100 device (the CUDA path has no CPU fallback)")
     c = sj.Context(0)
     yield c
     c.close()
