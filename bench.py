@@ -217,6 +217,7 @@ def main():
     ap.add_argument("--batch-mib", type=int, default=512, help="NDJSON bytes per step per GPU")
     ap.add_argument("--cpu-sample-mib", type=int, default=1024)
     ap.add_argument("--inflight", type=int, default=3, help="host-API calls kept in flight for the e2e number")
+    ap.add_argument("--twitter-mib", type=int, default=1024, help="size of the twitter.json-shaped document of roofline_twitter (0: skip)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs under ncu)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -329,6 +330,42 @@ def main():
     peak, peak_kind = read_peaks()
     achieved = alg_bytes / t_s1 / 1e9
 
+    # ---- roofline_twitter: the input the north-star target is stated on: "[" + twitter.json x K + "]",
+    # >= 1 GiB (> L2), one valid document, K1 alone.  Rank 0 at N = 1 only (the other N re-use the N = 1 figure).
+    roof_tw = None
+    if world == 1 and args.twitter_mib > 0:
+        from tests.util import load_fixture
+        tw = load_fixture("twitter").strip()
+        k = max(1, (args.twitter_mib << 20) // (len(tw) + 1))
+        doc = b"[" + b",".join([tw] * k) + b"]"
+        n_tw = len(doc)
+        d_tw = torch.empty(n_tw + (1 << 16), dtype=torch.uint8, device=dev)
+        d_tw[:n_tw].copy_(torch.frombuffer(bytearray(doc), dtype=torch.uint8))
+        d_tw[n_tw:] = 0x20
+        del doc
+        cap_tw = n_tw // 6 + 1024
+        d_idx_tw = torch.empty(cap_tw, dtype=torch.int32, device=dev)
+        info_tw = sj.Stage1Info()
+        r = L.sj_stage1_device(ctx.h, d_tw.data_ptr(), n_tw, 0, 0, d_idx_tw.data_ptr(), cap_tw, C.byref(info_tw))
+        assert r == 0 and not info_tw.overflow and not info_tw.error and int(info_tw.n_idx) == 55263 * k + (k - 1) + 2, (r, info_tw.n_idx)
+        for _ in range(3):
+            L.sj_stage1_launch(ctx.h, d_tw.data_ptr(), n_tw, 0, 0, d_idx_tw.data_ptr(), cap_tw)
+        L.sj_ctx_sync(ctx.h)
+        L.sj_event_record(ctx.h, 0)
+        for _ in range(args.steps):
+            L.sj_stage1_launch(ctx.h, d_tw.data_ptr(), n_tw, 0, 0, d_idx_tw.data_ptr(), cap_tw)
+        L.sj_event_record(ctx.h, 1)
+        L.sj_event_elapsed_ms(ctx.h, C.byref(ms))
+        t_tw = ms.value / 1e3 / args.steps
+        alg_tw = n_tw + 4 * int(info_tw.n_idx)
+        roof_tw = {"bound": "hbm", "kernel": "stage1_flatten_kernel<single document>", "workload": "twitter.json-shaped: '[' + twitter.json x %d + ']' (SURVEY.md 8d S1), %d bytes, %d structurals (= 55 263 per copy, G8)" % (k, n_tw, int(info_tw.n_idx)),
+                   "achieved": round(alg_tw / t_tw / 1e9, 2), "peak": peak, "unit": "GB/s", "frac": round(alg_tw / t_tw / 1e9 / peak, 4),
+                   "peak_kind": peak_kind, "algorithmic_bytes_per_launch": alg_tw, "ms_per_launch": round(t_tw * 1e3, 4),
+                   "input_read_gbs": round(n_tw / t_tw / 1e9, 2), "input_read_frac": round(n_tw / t_tw / 1e9 / peak, 4),
+                   "timer": "CUDA events on the library's stream around %d back-to-back launches" % args.steps}
+        del d_tw, d_idx_tw
+        torch.cuda.empty_cache()
+
     # ---- e2e: host buffers through sj_parse (pinned in, pinned out) ----
     # ParseNDStream keeps several chunks in flight (simdjson_amd64.go:132); here `--inflight`
     # host threads each own a context (= CUDA stream) and their own pinned output buffers, so
@@ -434,6 +471,7 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "stage1_flatten_kernel<ndjson>", "achieved": round(achieved, 2), "peak": peak,
                          "unit": "GB/s", "frac": round(achieved / peak, 4), "peak_kind": peak_kind, "traffic": k1_traffic(n),
+                         "traffic_kind": "static: dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full capture of this command (profiles/k1_traffic.json), not measured in this run",
                          "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": round(t_s1 * 1e3, 4),
                          "input_read_gbs": round(n / t_s1 / 1e9, 2)},
             "roofline_parse": {"bound": "hbm", "what": "whole device-resident step (K1 + K2a-f), algorithmic bytes 2*N_in + 8*N_idx + 8*N_tape + N_strings (SURVEY.md 8d)",
@@ -446,6 +484,8 @@ def main():
                                           "(parse_json_amd64_test.go:134), tape stays in HBM; same in-flight scheme and timer as e2e"},
             "clocks": sampler.summary(),
         }
+        if roof_tw:
+            line["roofline_twitter"] = roof_tw
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))

@@ -181,6 +181,9 @@ int sj_kernel_launches(sj_ctx* ctx, uint64_t* count); /* kernels launched by thi
  * ndjson), raw newline mask (before & ~quote_mask), carry_out odd_backslash, carry_out inside_quote, carry_out
  * pseudo_pred, any-control-character flag }.  Host buffers. */
 int sj_test_block_masks(sj_ctx* ctx, const uint8_t* blocks, size_t nblocks, const uint64_t* carry_in, uint64_t* out);
+/* geometry of the stage-1 kernel, for tests that aim carries at its edges: out = { block bytes (64), step bytes (one
+ * warp pass: 32 blocks), slab bytes (one warp's share of a tile), tile bytes (one CTA iteration = one look-back) } */
+void sj_test_geometry(uint32_t out[4]);
 /* finalize_structurals on caller-provided masks: in[5*i..] = {structurals, whitespace,
  * quote_mask, quote_bits, prev_pseudo}; out[2*i..] = {structurals, prev_pseudo'} */
 int sj_test_finalize(sj_ctx* ctx, const uint64_t* in, size_t n, uint64_t* out);

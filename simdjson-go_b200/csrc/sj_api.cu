@@ -375,6 +375,13 @@ extern "C" int sj_test_block_masks(sj_ctx* c, const uint8_t* blocks, size_t nblo
     return SJ_OK;
 }
 
+extern "C" void sj_test_geometry(uint32_t out[4]) {
+    out[0] = 64;
+    out[1] = S1_STEP_BYTES;
+    out[2] = S1_SLAB_BYTES;
+    out[3] = S1_TILE_BYTES;
+}
+
 extern "C" int sj_test_finalize(sj_ctx* c, const uint64_t* in, size_t n, uint64_t* out) {
     if (!c || n == 0) return SJ_ERR_ARGUMENT;
     SJ_CUDA_CHECK(cudaSetDevice(c->device));

@@ -159,24 +159,62 @@ def test_small_and_boundary_sizes(ctx, oracle_native):
         _check(ctx, oracle_native, doc, False)
 
 
+def _geometry(ctx):
+    import ctypes as C
+    g = (C.c_uint32 * 4)()
+    ctx.L.sj_test_geometry(g)
+    return tuple(int(x) for x in g)  # block, step, slab, tile
+
+
 def test_carries_across_slabs(ctx, oracle_native):
-    """strings, backslash runs and pseudo-structural predecessors straddling 8 KiB slab / 2 KiB step / 64 B block edges"""
+    """Backslash runs, escaped / unescaped quotes and pseudo-structural predecessors straddling every kind of edge of
+    the stage-1 kernel: 64-byte block, 2 KiB step, slab (one warp's share of a tile: the odd-backslash and
+    pseudo-predecessor carries are recovered from the 32 bytes in front of it, runs of 32 and more walk further back)
+    and tile (the in-string state crosses it through look-back chain 1).  The edges come from the kernel's own
+    constants (sj_test_geometry), so a change of geometry moves the test with it.
+    find_subroutines_amd64_test.go:153-198 sweeps the same carry over a 128-byte window."""
+    block, step, slab, tile = _geometry(ctx)
+    assert (block, step) == (64, 2048) and tile % slab == 0 and slab % step == 0
     rng = np.random.default_rng(7)
-    for edge in (64, 2048, 8192, 16384, 8192 * 13):
-        for run in (1, 2, 3, 31, 32, 33, 63, 64, 65, 127, 128, 129, 200):
-            for shift in (0, 1, 2):
-                pre = edge - run + shift
-                if pre < 2:
+    edges = [block, step, slab, 2 * slab, 5 * slab, tile - slab, tile, tile + slab, 2 * tile, 3 * tile + 2 * slab]
+    runs = [1, 2, 3, 4, 5, 30, 31, 32, 33, 34, 35, 62, 63, 64, 65, 66, 95, 96, 97, 127, 128, 129, 200]
+    n = 0
+    for edge in edges:
+        for run in runs:
+            # `a` backslashes of the run sit in front of the edge, run - a behind it
+            for a in sorted({0, 1, 2, run // 2, run - 2, run - 1, run} & set(range(0, run + 1))):
+                pre = edge - 2 - a
+                if pre < 0:
                     continue
-                body = b'["' + b"x" * (pre - 2) + b"\\" * run + b'"q\\\\", "tail",true , 12]'
+                body = b'["' + b"x" * pre + b"\\" * run + b'"q\\\\", "tail",true , 12]'
+                assert body[edge - a:edge - a + run] == b"\\" * run and (edge - a == 0 or body[edge - a - 1:edge - a] != b"\\")
                 _check(ctx, oracle_native, body, False)
-    # a quote exactly at the last byte of a slab, escaped or not
-    for k in (0, 1, 2, 3):
-        pad = 8192 - 3 - k
-        _check(ctx, oracle_native, b'["' + b"y" * pad + b"\\" * k + b'","z"]', False)
-        _check(ctx, oracle_native, b'["' + b"y" * pad + b"\\" * k + b'"  ,  "z"  ]', False)
-    # random soup: every structural / escape class, sizes that leave partial slabs
-    for n in (5000, 8192, 20000, 70000, 300007):
+                n += 1
+    assert n > 1000
+    # a quote exactly at the last byte in front of an edge / the first byte behind it, behind k backslashes
+    # (k >= 32 forces the walk of backslash_run_before for the quote's own escape state too)
+    for edge in (slab, 3 * slab, tile, 2 * tile + slab):
+        for k in (0, 1, 2, 3, 30, 31, 32, 33, 64, 65):
+            for at in (edge - 1, edge):  # position of the quote
+                pad = at - 2 - k
+                _check(ctx, oracle_native, b'["' + b"y" * pad + b"\\" * k + b'","z"]', False)
+                _check(ctx, oracle_native, b'["' + b"y" * pad + b"\\" * k + b'"  ,  "z"  ]', False)
+    # pseudo-structural predecessor across an edge: the byte in front of the edge is whitespace / a structural /
+    # a quote / an ordinary character, the byte behind it starts (or does not start) an atom
+    for edge in (step, slab, tile, tile + 4 * slab):
+        for last in (b" ", b",", b"[", b'"', b"x", b"\n", b":"):
+            for first in (b"t", b"1", b"[", b'"', b" ", b"n"):
+                head = b"[" + b"1," * ((edge - 8) // 2)
+                head = head + b" " * (edge - 1 - len(head)) + last
+                assert len(head) == edge
+                _check(ctx, oracle_native, head + first + b'rue,"k" ]', False)
+                _check(ctx, oracle_native, head + first + b'rue,"k" ]', True)
+    # an open string across one and several tiles (chain 1 carries "in string" over tiles that hold no quote at all)
+    for span in (tile // 2, tile, 3 * tile + 5):
+        _check(ctx, oracle_native, b'{"k":"' + b"s" * span + b'","t":[1,2,{"u":null}]}', False)
+        _check(ctx, oracle_native, b'{"k":"' + b"s" * span + b'\\","t":[1,2,{"u":null}]}', False)  # escaped closing quote: ends in string
+    # random soup: every structural / escape class, sizes that leave partial slabs and partial tiles
+    for n in (5000, slab, 20000, 70000, tile + 1, 300007):
         buf = ALPHABET[rng.integers(0, len(ALPHABET), size=n)].tobytes()
         _check(ctx, oracle_native, buf, False)
         _check(ctx, oracle_native, buf, True)

@@ -310,15 +310,19 @@ def test_large_documents(ctx, oracle_native):
     assert _same_parse(ctx, oracle_native, b"[" + b",".join([ca] * 4) + b"]") == 0
 
 
-@pytest.mark.parametrize("which,limit", [("corpus", 1500), ("go-corpus", 400)])
-def test_g20_fuzz_corpus_differential(ctx, oracle_native, which, limit):
-    """fuzz_test.go:40 FuzzParse seeds: same accept/reject and same tape as the oracle"""
+@pytest.mark.parametrize("which,expect", [("corpus", 8000), ("go-corpus", 300)])
+def test_g20_fuzz_corpus_differential(ctx, oracle_native, which, expect):
+    """fuzz_test.go:40-94 FuzzParse seeds -- ALL of them (8 680 + 356 inputs, no size cap): same accept / reject and the
+    same tape and string buffer as the oracle, as a single document and as NDJSON, and (every 16th seed) with
+    copy_strings off"""
     n = 0
-    for name, data in fuzz_corpus(which, limit=limit, max_size=200_000):
+    for name, data in fuzz_corpus(which):
         for nd in (False, True):
             _same_parse(ctx, oracle_native, data, ndjson=nd)
+        if n % 16 == 0:
+            _same_parse(ctx, oracle_native, data, ndjson=False, copy=False)
         n += 1
-    assert n > 100
+    assert n > expect, n
 
 
 def test_concurrent_contexts(oracle_native):

@@ -1,0 +1,58 @@
+"""Small end-to-end workload for `compute-sanitizer` (memcheck / racecheck / synccheck / initcheck): every kernel of
+the path on inputs small enough for the tool's 10-100x slowdown, each result still checked against the oracle.
+usage: compute-sanitizer --tool racecheck python tools/sanitize_run.py [quick]"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "simdjson-go_b200"))
+import numpy as np
+
+import simdjson_b200 as sj
+from oracle.pyoracle import Oracle
+from tests.util import load_fixture, tricky_ndjson
+
+quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
+ctx = sj.Context(0)
+o = Oracle("native")
+n = 0
+
+
+def same(msg, ndjson=False, copy=True):
+    global n
+    rc_g, tape_g, str_g, win_g = ctx.parse(msg, ndjson=ndjson, copy_strings=copy)
+    rc_o, tape_o, str_o, win_o = o.parse(msg, ndjson=ndjson, copy_strings=copy)
+    assert rc_g == rc_o and win_g == win_o, (rc_g, rc_o)
+    if rc_o == 0:
+        assert np.array_equal(tape_g, tape_o) and str_g == str_o
+    ok_g, d_g = ctx.find_structural_indices(msg, ndjson)
+    ok_o, d_o = o.find_structural_indices(msg, ndjson)
+    assert ok_g == ok_o and (not ok_o or np.array_equal(d_g, d_o))
+    n += 1
+
+
+docs = ["twitter", "twitterescaped", "numbers", "apache_builds", "github_events"] if not quick else ["github_events"]
+for name in docs:
+    d = load_fixture(name).strip()
+    same(d)
+    same(d, copy=False)
+pk = load_fixture("parking-citations").strip()
+same(pk[:120000 if quick else len(pk)].rsplit(b"\n", 1)[0], ndjson=True)
+nd, _ = tricky_ndjson()
+same(nd, ndjson=True)
+assert ctx.parse_count_where(nd, b"Make", b"HOND")[0] == 0
+# carries across slab / tile edges, long strings (warp-cooperative paths), dense brackets, number-heavy
+g = (__import__("ctypes").c_uint32 * 4)()
+ctx.L.sj_test_geometry(g)
+slab, tile = int(g[2]), int(g[3])
+for edge in (slab, tile):
+    for run in (1, 33, 64):
+        same(b'["' + b"x" * (edge - 2 - run // 2) + b"\\" * run + b'"q\\\\", "tail",true , 12]')
+same(b'{"k":"' + b"s" * (tile + 77) + b'","t":[1,2,{"u":null}]}')
+same(b'["' + b"\\u30c6\\u30b9\\ud83d\\ude00\\n" * 300 + b'","' + b"abc" * 200 + b'"]')
+same(b"[" + b"[1," * 3000 + b"1" + b"]" * 3000 + b"]")
+same(b"[" + b",".join(b"%d.%de%d" % (i, i * 7919 % 100000, i % 30 - 15) for i in range(4000)) + b"]")
+same(b'{"a":tru}')
+same(b'["abc\\q"]')
+print("sanitize_run ok: %d documents, %d kernel launches" % (n, ctx.launches()))
