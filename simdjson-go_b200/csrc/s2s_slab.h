@@ -1,0 +1,598 @@
+// s2s_slab.h -- streaming stage 2: what ONE WARP does with one 6 KiB slab, written once for the device (W = DevWarp,
+// stage2_stream.cuh) and for the host emulation (W = FiberWarp, tests/emu/s2s_emu.cpp).  See s2s_core.h for the idea.
+//
+//   s2s_slab<W, false>   K2p: counts of the slab -> SlabAgg
+//   s2s_slab<W, true>    K2r: tape words, Strings.B bytes, bracket records, number list, grammar masks
+//
+// W provides: lane(), ballot(bool), any(bool), shfl / shfl_up (uint32_t), reduce_add(uint32_t), sync(),
+// atomic_and(uint32_t*, uint32_t), atomic_or(uint32_t*, uint32_t), atomic_or_shared(uint32_t*, uint32_t).
+// Every collective is reached by all 32 lanes (warp-uniform control flow around them).
+#pragma once
+#include "s2s_core.h"
+
+namespace sj {
+
+// original message bytes: the slab image in shared memory where it covers the position, global memory elsewhere,
+// 0 beyond the end of the message (the reference reads zero padding there, stage2...go:75-86)
+struct MsgReader {
+    const uint8_t* msg;
+    uint64_t len;
+    const uint8_t* src;   // slab image (swizzled per step)
+    uint64_t slab_start;
+    uint64_t slab_end;    // end of the image that holds message bytes (min(slab_start + slab bytes, len))
+    SJ_HD uint32_t operator()(uint64_t pos) const {
+        if (pos >= slab_start && pos < slab_end) {
+            const uint32_t o = (uint32_t)(pos - slab_start);
+            return src[(o & ~(S2S_STEP_BYTES - 1)) + swz(o & (S2S_STEP_BYTES - 1))];
+        }
+        return pos < len ? msg[pos] : 0u;
+    }
+};
+
+struct GlobalReader {
+    const uint8_t* msg;
+    uint64_t len;
+    SJ_HD uint32_t operator()(uint64_t pos) const { return pos < len ? msg[pos] : 0u; }
+};
+
+// atoms (stage2_build_tape_amd64.go:124-158, 455-476): literal + one following byte that is structural / white / NUL
+SJ_HD bool structural_or_ws_or_nul_p(uint32_t c) {
+    return c == 0 || c == '\t' || c == '\n' || c == '\r' || c == ' ' || c == ',' || c == ':' || c == '[' || c == ']' ||
+           c == '{' || c == '}';
+}
+template <class R>
+SJ_HD bool atom_ok_p(const R& rd, uint64_t pos, uint64_t len, uint32_t type) {
+    const char* lit = type == T_TRUE ? "true" : type == T_FALSE ? "false" : "null";
+    const uint32_t n = type == T_FALSE ? 5 : 4;
+    if (pos + n + 1 > len) return false;  // len(buf) >= n + 1
+    for (uint32_t i = 0; i < n; i++)
+        if (rd(pos + i) != (uint32_t)(uint8_t)lit[i]) return false;
+    return structural_or_ws_or_nul_p(rd(pos + n));
+}
+
+// mark [lo, hi) (bit numbers relative to a block, hi <= 64 + 32) in a 64-bit mask and in the spill word behind it
+SJ_HD void mark_range(uint64_t& m, uint32_t& spill, uint32_t lo, uint32_t hi) {
+    m |= range64(lo, hi < 64 ? hi : 64);
+    if (hi > 64) {
+        const uint32_t a = lo > 64 ? lo - 64 : 0, b = hi - 64;
+        spill |= (uint32_t)range64(a, b);
+    }
+}
+
+// What an escape that starts IN FRONT of position T (a step start) leaves behind it: `drop` = the bytes at T.. that
+// belong to it and carry no output, `nhead` / `head` = its UTF-8 bytes when they live behind the edge (esc_out_pos).
+// Lanes 0..10 each test one of the eleven positions in front of T (a pair is 12 bytes long); original bytes only.
+struct HeadInfo {
+    uint32_t drop;
+    uint32_t nhead;
+    uint32_t head;
+    uint32_t bad;
+};
+template <class W>
+SJ_HD HeadInfo head_info(W& wp, const GlobalReader& g, uint64_t T, bool in_string) {
+    HeadInfo h;
+    h.drop = 0, h.nhead = 0, h.head = 0, h.bad = 0;
+    const uint32_t lane = wp.lane();
+    uint32_t mine = 0;
+    const uint64_t back = (uint64_t)lane + 1;
+    if (lane < 11 && T >= back && in_string) mine = g(T - back) == '\\' ? 1u : 0u;
+    if (!wp.any(mine != 0)) return h;  // no backslash among the last eleven bytes (or not inside a string): nothing straddles
+    uint32_t drop = 0, nhead = 0, head = 0, bad = 0;
+    if (mine) {
+        const uint64_t x = T - back;
+        if ((backslashes_before(g, x) & 1u) == 0) {  // an escape start
+            const EscInfo e = esc_decode(g, x);
+            if (!e.second) {
+                if (!e.valid) {
+                    bad = 1;
+                } else if (x + e.c > T) {
+                    const uint32_t over = (uint32_t)(x + e.c - T);  // bytes of the escape at T..
+                    if (esc_out_pos(x, e.c, e.n, T) == T) {
+                        nhead = e.n;
+                        head = e.bytes;
+                        drop = (uint32_t)range64(e.n, over);
+                    } else {
+                        drop = (uint32_t)range64(0, over);
+                    }
+                }
+            }
+        }
+    }
+    // at most one escape can straddle the edge in a valid document; take the nearest one, OR the error flags
+    const uint32_t have = wp.ballot(drop != 0 || nhead != 0);
+    const uint32_t pick = have ? (uint32_t)(pi::ctz64(have)) : 0;  // lanes count backwards from the edge: the nearest start
+    h.drop = have ? wp.shfl(drop, pick) : 0;
+    h.nhead = have ? wp.shfl(nhead, pick) : 0;
+    h.head = have ? wp.shfl(head, pick) : 0;
+    h.bad = wp.any(bad != 0) ? 1u : 0u;
+    return h;
+}
+
+// length of the run of backslashes that ends just before `end` (32 bytes per round; one round in practice)
+template <class W>
+SJ_HD uint32_t backslash_run_before_p(W& wp, const GlobalReader& g, uint64_t end) {
+    const uint32_t lane = wp.lane();
+    uint32_t run = 0;
+    for (uint64_t off = 0;; off += 32) {
+        const uint64_t back = off + lane + 1;
+        const uint32_t c = back <= end ? g(end - back) : 0x20u;
+        const uint32_t B = wp.ballot(c == '\\');
+        const uint32_t n = B == 0xffffffffu ? 32u : pi::ctz64((uint64_t)(~B));
+        run += n;
+        if (n < 32) return run;
+    }
+}
+
+template <class W, bool EMIT>
+SJ_HD void s2s_slab(W& wp, const S2sParams& p, uint32_t slab, const S2sWarpMem& sm) {
+    const uint32_t lane = wp.lane();
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint64_t slab_start = (uint64_t)slab * S2S_SLAB_BYTES;
+    const uint64_t len16 = (p.len + 15) & ~15ull;
+    const uint64_t slab_end = slab_start + S2S_SLAB_BYTES < p.len ? slab_start + S2S_SLAB_BYTES : p.len;
+    const GlobalReader g{p.msg, p.len};
+
+    // ---- the slab image: 16-byte chunks from global memory, stored XOR-swizzled per step; bytes past the end of the
+    // message read as spaces (find_structural_bits_amd64.s:167) ----
+    for (uint32_t c = lane; c < S2S_SLAB_BYTES / 16; c += 32) {
+        const uint64_t gofs = slab_start + 16ull * c;
+        V16 q{0x20202020u, 0x20202020u, 0x20202020u, 0x20202020u};
+        if (gofs < len16) {
+            q = *reinterpret_cast<const V16*>(p.msg + gofs);
+            if (gofs + 16 > p.len) {  // the chunk that holds the end of the message
+                uint32_t qq[4] = {q.x, q.y, q.z, q.w};
+                for (uint32_t k = 0; k < 16; k++)
+                    if (gofs + k >= p.len) qq[k >> 2] = (qq[k >> 2] & ~(0xffu << (8 * (k & 3)))) | (0x20u << (8 * (k & 3)));
+                q = V16{qq[0], qq[1], qq[2], qq[3]};
+            }
+        }
+        const uint32_t o = 16u * c;
+        *reinterpret_cast<V16*>(sm.src + (o & ~(S2S_STEP_BYTES - 1)) + swz(o & (S2S_STEP_BYTES - 1))) = q;
+    }
+    wp.sync();
+    const MsgReader rd{p.msg, p.len, sm.src, slab_start, slab_end};
+
+    // ---- carries into the slab ----
+    // in-string state: from stage 1 (its look-back chain 1 already resolved it for every slab)
+    uint32_t par = (p.slabpar[slab / p.slabs_per_tile] >> (slab % p.slabs_per_tile)) & 1u;
+    // lane L: the byte at slab_start - 1 - L
+    const uint32_t peekc = slab_start > lane ? g(slab_start - 1 - lane) : 0x20u;
+    const uint32_t peek_bs = wp.ballot(peekc == '\\');
+    const uint32_t prevc = wp.shfl(peekc, 0);
+    uint32_t bsc;  // the slab's first byte is consumed by an escape that starts in front of it
+    if (peek_bs == 0xffffffffu)
+        bsc = backslash_run_before_p(wp, g, slab_start) & 1u;
+    else
+        bsc = pi::ctz64((uint64_t)(~peek_bs)) & 1u;
+    uint32_t prevc_esc = 0;
+    if (prevc == '"') {
+        const uint32_t n = pi::ctz64((uint64_t)(~(peek_bs >> 1)));
+        prevc_esc = n >= 31 ? backslash_run_before_p(wp, g, slab_start - 1) & 1u : n & 1u;
+    }
+    // pseudo-structural predecessor (finalize_structurals_amd64.s:24-27; 1 at the start: stage1_find_marks_amd64.go:54)
+    uint32_t ppc = 1;
+    if (slab > 0) {
+        const uint32_t is_q = prevc == '"' && !prevc_esc;
+        const uint32_t is_ws = prevc == 0x20 || prevc == 0x09 || prevc == 0x0a || prevc == 0x0d;
+        const uint32_t is_st = prevc == '{' || prevc == '}' || prevc == '[' || prevc == ']' || prevc == ':' || prevc == ',';
+        ppc = is_q | is_ws | (is_st & (par ^ 1u));
+    }
+    // NDJSON: is the last structural in front of the slab a newline?  Outside a string that is "the last byte that is
+    // not a blank, tab or CR is a newline" (every other byte is a structural of its own or belongs to a value that
+    // started behind the last newline)
+    uint32_t recc = 0;
+    if (p.ndjson && !par && slab > 0) {
+        for (uint64_t off = 0;; off += 32) {
+            const uint64_t back = off + lane + 1;
+            const uint32_t c = off == 0 ? peekc : (back <= slab_start ? g(slab_start - back) : 0x7fu);
+            const uint32_t solid = wp.ballot(!(c == 0x20 || c == 0x09 || c == 0x0d));
+            if (solid) {
+                recc = wp.shfl(c, pi::ctz64((uint64_t)solid)) == '\n' ? 1u : 0u;
+                break;
+            }
+            if (back + 31 - lane >= slab_start) break;  // reached the start of the message: nothing but blanks
+        }
+    }
+
+    // ---- running totals of the slab (K2p) / running prefixes (K2r) ----
+    SlabAgg run = agg_zero();
+    uint32_t trail = 0, hasq = 0;  // K2p: bytes behind the last quote so far
+    uint32_t partial = 0;          // K2r: bytes the string that is open at the step start has contributed so far
+    uint32_t pr = T_START;         // K2r: refined type of the last event in front of the step
+    uint32_t err = 0;
+    if (EMIT) {
+        run = agg_combine(p.grp_pre[slab >> 10], p.pre[slab]);
+        partial = run.trail & ~TRAIL_HASQ;
+        // the last event in front of the slab, from stage 1's index: inside a string the last structural is that
+        // string's opening quote, whose event (the closing quote) is still to come
+        const uint32_t r = run.ns;
+        const uint32_t back = par ? 2u : 1u;
+        if (r >= back) {
+            const uint32_t t = sm.ctab[g(p.idx[r - back])];
+            uint32_t tp = T_START;
+            if (r >= back + 1) tp = sm.ctab[g(p.idx[r - back - 1])];
+            pr = (t == T_STRING && (tp == T_OBJ_OPEN || tp == T_COMMA)) ? (uint32_t)T_STRING_KEYPOS : t;
+        }
+    }
+
+    for (uint32_t s = 0; s < S2S_STEPS; s++) {
+        const uint64_t step_start = slab_start + (uint64_t)s * S2S_STEP_BYTES;
+        if (step_start >= p.len) break;  // warp-uniform
+        const uint64_t step_end = step_start + S2S_STEP_BYTES;
+        const uint64_t block_pos = step_start + 64ull * lane;
+        const uint8_t* sbase = sm.src + s * S2S_STEP_BYTES;
+
+        // ---------------- A: load + classify ----------------
+        uint32_t w[16];
+        {
+            const uint32_t r = (lane >> 1) & 3;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const V16 q = *reinterpret_cast<const V16*>(sbase + 64 * lane + 16 * ((uint32_t)j ^ r));
+                w[4 * j + 0] = q.x, w[4 * j + 1] = q.y, w[4 * j + 2] = q.z, w[4 * j + 3] = q.w;
+            }
+        }
+        const Class64 m = classify_block2(w);
+
+        // ---------------- B: escape starts, escaped bytes (find_odd_backslash_sequences_amd64.s:24-61) ----------------
+        uint64_t E = 0, C = 0;
+        {
+            const uint32_t hasbs = wp.ballot(m.bs != 0);
+            if (hasbs || bsc) {  // warp-uniform
+                const bool allbs = m.bs == ~0ull;
+                const uint32_t trail_odd = allbs ? 0u : (pi::clz64(~m.bs) & 1u);
+                const uint32_t A = wp.ballot(allbs), F = wp.ballot(trail_odd != 0);
+                const uint32_t below = ~A & lt;
+                const uint32_t cin = below ? (F >> (31 - pi::clz32(below))) & 1u : bsc;
+                const uint32_t nonpass = ~A;
+                bsc = nonpass ? (F >> (31 - pi::clz32(nonpass))) & 1u : bsc;
+                E = escape_starts(m.bs, cin);
+                C = (E << 1) | cin;
+            }
+        }
+        const uint64_t qb = m.qt & ~C;  // real quotes
+        // ---------------- C: quote mask (find_quote_mask_and_bits_amd64.s:49-66) ----------------
+        const bool par_step = par != 0;  // in-string state at the step start
+        uint64_t qm;
+        {
+            const uint32_t P = wp.ballot((pi::popc64(qb) & 1u) != 0);
+            const uint32_t lane_in = par ^ (pi::popc32(P & lt) & 1u);
+            qm = prefix_xor64p(qb) ^ (lane_in ? ~0ull : 0ull);
+            par ^= pi::popc32(P) & 1u;
+        }
+
+        // ---------------- D: escapes inside strings -> dropped bytes ----------------
+        uint64_t D = 0;
+        const uint64_t Ein = E & qm;
+        const HeadInfo hd = head_info(wp, g, step_start, par_step);
+        err |= hd.bad;
+        const bool any_esc = wp.any(Ein != 0);
+        {
+            uint32_t spill = 0;
+            if (any_esc) {
+                uint64_t e = Ein;
+                while (e) {
+                    const uint32_t b = pi::ctz64(e);
+                    e &= e - 1;
+                    const uint64_t x = block_pos + b;
+                    const EscInfo ei = esc_decode(rd, x);
+                    if (ei.second) continue;
+                    if (!ei.valid) {
+                        err = 1;
+                        continue;
+                    }
+                    // all c source bytes are dropped except the n that hold the output (esc_out_pos)
+                    mark_range(D, spill, b, b + ei.c);
+                    const uint32_t ob = (uint32_t)(esc_out_pos(x, ei.c, ei.n, step_end) - block_pos);
+                    if (block_pos + ob < step_end) {  // output in this step: un-drop its n positions
+                        D &= ~range64(ob, ob + ei.n);
+                        if (ob + ei.n > 64) spill &= ~(uint32_t)range64(ob > 64 ? ob - 64 : 0, ob + ei.n - 64);
+                    }
+                }
+            }
+            if (any_esc || hd.drop) {  // warp-uniform
+                uint32_t spin = wp.shfl_up(spill, 1);
+                if (lane == 0) spin = hd.drop;
+                D |= (uint64_t)spin;
+            }
+        }
+        const uint64_t K = qm & ~qb & ~D;  // bytes of Strings.B, at their source positions
+
+        // ---------------- E: structurals (finalize_structurals_amd64.s:19-36), events, counts ----------------
+        const uint64_t brk_m = (m.open | m.close) & ~qm;
+        const uint64_t st_out = brk_m | (m.cc & ~qm);
+        const uint64_t closeq = qb & ~qm;
+        const uint64_t s0 = st_out | qb;
+        uint64_t pseudo;
+        {
+            const uint64_t pred = s0 | m.ws;
+            const uint32_t my_pp = (uint32_t)(pred >> 63);
+            const uint32_t up = wp.shfl_up(my_pp, 1);
+            const uint32_t pp_in = lane == 0 ? ppc : up;
+            ppc = wp.shfl(my_pp, 31);
+            pseudo = ((pred << 1) | pp_in) & ~m.ws & ~qm;
+        }
+        const uint64_t V = pseudo & ~s0;                        // value starts: atoms, numbers, garbage
+        const uint64_t NLS = p.ndjson ? (m.nl & ~qm) : 0ull;    // find_newline_delimiters_amd64.s:17-27
+        const uint64_t S = st_out | (qb & qm) | V | NLS;        // stage 1's structurals
+        const uint64_t EV = st_out | closeq | V | NLS;          // the same with every string moved to its closing quote
+        // record boundaries: the first structural behind a run of newlines, if it is not a newline itself
+        // (stage2...go:200-221).  (T + ~S) carries from the byte behind each newline to the next structural.  They are
+        // counted where stage 1 sees that structural -- for a string at its OPENING quote -- so that the carry into
+        // a slab never depends on what lies in front of an open string.
+        uint64_t recst = 0;
+        if (p.ndjson) {
+            const bool empty = S == 0;
+            const bool gen = !empty && ((NLS >> (63 - pi::clz64(S))) & 1ull);
+            const uint32_t Pm = wp.ballot(empty), G = wp.ballot(gen);
+            const uint32_t below = ~Pm & lt;
+            const uint32_t cin = below ? (G >> (31 - pi::clz32(below))) & 1u : recc;
+            const uint32_t nonp = ~Pm;
+            recc = nonp ? (G >> (31 - pi::clz32(nonp))) & 1u : recc;
+            const uint64_t T = (NLS << 1) | cin;
+            recst = (T + ~S) & S & ~NLS;
+        }
+        const uint32_t n_brk = pi::popc64(brk_m), n_open = pi::popc64(m.open & ~qm);
+        const uint32_t n_str = pi::popc64(closeq), n_num = pi::popc64(V & m.numc), n_atom = pi::popc64(V & m.atomc);
+        const uint32_t n_rec = pi::popc64(recst);
+        const uint32_t w_lane = n_brk + 2 * n_str + 2 * n_num + n_atom + 2 * n_rec;
+        const uint32_t k_lane = pi::popc64(K);
+        const bool q_lane = qb != 0;
+        const uint32_t t_lane = q_lane ? pi::popc64(K & ~below64(64 - pi::clz64(qb))) : k_lane;  // bytes behind the lane's last quote
+
+        if (!EMIT) {
+            run.w += wp.reduce_add(w_lane);
+            run.brk += wp.reduce_add(n_brk);
+            run.rec += wp.reduce_add(n_rec);
+            run.depth += (int32_t)wp.reduce_add(2 * n_open + 64 - n_brk) - 64 * 32;
+            run.ns += wp.reduce_add(pi::popc64(S));
+            run.num += wp.reduce_add(n_num);
+            const uint32_t k_step = wp.reduce_add(k_lane);
+            run.str += k_step;
+            const uint32_t Q = wp.ballot(q_lane);
+            if (Q) {
+                const uint32_t top = 31 - pi::clz32(Q);
+                trail = wp.shfl(t_lane, top) + wp.reduce_add(lane > top ? k_lane : 0u);
+                hasq = 1;
+            } else {
+                trail += k_step;
+            }
+            continue;
+        }
+
+        // =========================== K2r ===========================
+        // exclusive prefixes of the lane inside the step: tape words (13 bits) | string bytes (12) | brackets (12) |
+        // records (11) | depth, biased by 64 per lane (13) in one 64-bit word, numbers in a second one
+        uint32_t w_ex, k_ex, b_ex, r_ex, n_ex;
+        int32_t d_ex;
+        uint32_t w_step, k_step, b_step, r_step, n_step;
+        int32_t d_step;
+        {
+            const uint64_t own = (uint64_t)w_lane | ((uint64_t)k_lane << 13) | ((uint64_t)n_brk << 25) | ((uint64_t)n_rec << 37) |
+                                 ((uint64_t)(2 * n_open + 64 - n_brk) << 48);
+            uint64_t inc = own;
+            uint32_t ninc = n_num;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t tl = wp.shfl_up((uint32_t)inc, d), th = wp.shfl_up((uint32_t)(inc >> 32), d);
+                const uint32_t tn = wp.shfl_up(ninc, d);
+                if ((int)lane >= d) {
+                    inc += mk64u(tl, th);
+                    ninc += tn;
+                }
+            }
+            const uint64_t ex = inc - own;
+            w_ex = (uint32_t)(ex & 0x1fff), k_ex = (uint32_t)((ex >> 13) & 0xfff), b_ex = (uint32_t)((ex >> 25) & 0xfff);
+            r_ex = (uint32_t)((ex >> 37) & 0x7ff);
+            d_ex = (int32_t)(ex >> 48) - 64 * (int32_t)lane;
+            n_ex = ninc - n_num;
+            const uint64_t tot = mk64u(wp.shfl((uint32_t)inc, 31), wp.shfl((uint32_t)(inc >> 32), 31));
+            w_step = (uint32_t)(tot & 0x1fff), k_step = (uint32_t)((tot >> 13) & 0xfff), b_step = (uint32_t)((tot >> 25) & 0xfff);
+            r_step = (uint32_t)((tot >> 37) & 0x7ff);
+            d_step = (int32_t)(tot >> 48) - 64 * 32;
+            n_step = wp.shfl(ninc, 31);
+        }
+        // bytes the string open at the lane's first byte has contributed so far
+        uint32_t part_lane;
+        {
+            const uint32_t Q = wp.ballot(q_lane);
+            const uint32_t v = t_lane - (k_ex + k_lane);  // (wraps; only differences are used)
+            const uint32_t below = Q & lt;
+            const uint32_t got = wp.shfl(v, below ? 31 - pi::clz32(below) : 0);
+            part_lane = below ? k_ex + got : partial + k_ex;
+            if (Q) {
+                const uint32_t top = 31 - pi::clz32(Q);
+                partial = k_step + wp.shfl(v, top);
+            } else {
+                partial += k_step;
+            }
+        }
+
+        // ---------------- Strings.B: byte compaction of the step into the staging area ----------------
+        const uint32_t str_base = run.str;                 // offset of the step's bytes in Strings.B
+        const uint32_t shift = (uint32_t)(reinterpret_cast<uintptr_t>(p.strings + str_base) & 15u);  // staging keeps the destination's 16-byte phase
+        if (k_step) {                                      // warp-uniform
+            uint32_t* st32 = reinterpret_cast<uint32_t*>(sm.sstage);
+            for (uint32_t i = lane; i < S2S_SSTAGE_BYTES / 16; i += 32) reinterpret_cast<V16*>(sm.sstage)[i] = V16{0, 0, 0, 0};
+            wp.sync();
+            if (k_lane) {
+                const uint32_t o = shift + k_ex;           // first output byte of the lane
+                const uint32_t first = o >> 2;
+                uint32_t ptr = first, fill = o & 3u, lo = 0;
+                const uint32_t Klo = (uint32_t)K, Khi = (uint32_t)(K >> 32);
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    const uint32_t m4 = ((k < 8 ? Klo : Khi) >> (4 * (k & 7))) & 15u;
+                    const uint32_t ce = sm.cmptab[m4];  // PRMT selector | kept bytes << 16
+                    const uint32_t cw = pi::byte_perm(w[k], 0, ce & 0xffffu);
+                    const uint32_t cnt = ce >> 16;
+                    lo |= cw << (8 * fill);
+                    const uint32_t hi = pi::funnel_l(cw, 0, 8 * fill);
+                    fill += cnt;
+                    if (fill >= 4) {
+                        if (ptr == first)
+                            wp.atomic_or_shared(st32 + ptr, lo);  // shared with the lane below
+                        else
+                            st32[ptr] = lo;
+                        ptr++;
+                        lo = hi;
+                        fill -= 4;
+                    }
+                }
+                if (fill) wp.atomic_or_shared(st32 + ptr, lo);  // shared with the lane above
+            }
+            wp.sync();
+            // escapes: their UTF-8 bytes over the (meaningless) source bytes the compaction copied into their slots
+            if (any_esc) {
+                uint64_t e = Ein;
+                while (e) {
+                    const uint32_t b = pi::ctz64(e);
+                    e &= e - 1;
+                    const uint64_t x = block_pos + b;
+                    const EscInfo ei = esc_decode(rd, x);
+                    if (ei.second || !ei.valid) continue;
+                    const uint64_t op = esc_out_pos(x, ei.c, ei.n, step_end);
+                    if (op >= step_end) continue;  // the next step patches them (head_info)
+                    // op == x here: the n output slots start in this block (they may run on into the next one, where
+                    // they are kept bytes too, so their ranks are consecutive)
+                    const uint32_t rank = pi::popc64(K & below64(b));
+                    for (uint32_t i = 0; i < ei.n; i++) sm.sstage[shift + k_ex + rank + i] = (uint8_t)(ei.bytes >> (8 * i));
+                }
+            }
+            if (hd.nhead && lane == 0)
+                for (uint32_t i = 0; i < hd.nhead; i++) sm.sstage[shift + i] = (uint8_t)(hd.head >> (8 * i));
+            wp.sync();
+            // copy-out: head and tail bytes one by one, the 16-byte aligned middle as vectors
+            {
+                uint8_t* dst = p.strings + str_base;  // dst + i <-> sstage[shift + i]
+                const uint32_t total = k_step;
+                const uint32_t head_n = shift ? (16 - shift < total ? 16 - shift : total) : 0;
+                if (lane < head_n) dst[lane] = sm.sstage[shift + lane];
+                const uint32_t body = (total - head_n) & ~15u;
+                const V16* s16 = reinterpret_cast<const V16*>(sm.sstage + shift + head_n);
+                V16* d16 = reinterpret_cast<V16*>(dst + head_n);
+                for (uint32_t i = lane; i < body / 16; i += 32) d16[i] = s16[i];
+                const uint32_t tail0 = head_n + body;
+                if (lane < total - tail0) dst[tail0 + lane] = sm.sstage[shift + tail0 + lane];
+            }
+        }
+
+        // ---------------- the lane's events, in order ----------------
+        const bool staged = w_step <= S2S_TSTAGE_WORDS;  // warp-uniform
+        const uint32_t slot0 = 1 + run.w;                // tape slot of the step's first word (slot 0: the first root word)
+        uint64_t* tout = staged ? sm.tstage - slot0 : p.tape;
+        {
+            // refined type of the last event in front of the lane
+            const uint32_t nev = pi::popc64(EV);
+            uint32_t last_b = 0, prev_b = T_INVALID;  // base types of the lane's last event and of the one before it
+            if (nev) {
+                const uint32_t tb = 63 - pi::clz64(EV);
+                last_b = sm.ctab[sbase[swz(64 * lane + tb)]];
+                if (nev > 1) {
+                    const uint64_t rest = EV & ~(1ull << tb);
+                    prev_b = sm.ctab[sbase[swz(64 * lane + 63 - pi::clz64(rest))]];
+                }
+            }
+            const uint32_t HE = wp.ballot(nev != 0);
+            const uint32_t below = HE & lt;
+            const uint32_t src = below ? 31 - pi::clz32(below) : 0;
+            const uint32_t below_last_b = wp.shfl(last_b, src);
+            const uint32_t pr_b = pr == T_STRING_KEYPOS ? (uint32_t)T_STRING : pr;
+            if (nev == 1) prev_b = below ? below_last_b : pr_b;
+            const uint32_t last_ref = (last_b == T_STRING && (prev_b == T_OBJ_OPEN || prev_b == T_COMMA)) ? (uint32_t)T_STRING_KEYPOS : last_b;
+            const uint32_t below_last_ref = wp.shfl(last_ref, src);
+            uint32_t pcur = below ? below_last_ref : pr;
+            if (HE) pr = wp.shfl(last_ref, 31 - pi::clz32(HE));
+
+            uint32_t slot = slot0 + w_ex;
+            uint32_t kb = run.brk + b_ex;
+            int32_t depth = run.depth + d_ex;
+            uint32_t rec = run.rec + r_ex;
+            uint32_t ni = run.num + n_ex;
+            const uint32_t lane_str = str_base + k_ex;  // Strings.B offset of the lane's first kept byte
+            uint32_t acc = 7;
+            const uint64_t openrec = recst & qb & qm;  // (invalid input only: a record that starts with a string)
+            uint64_t ev = EV | openrec;
+            while (ev) {
+                const uint32_t b = pi::ctz64(ev);
+                ev &= ev - 1;
+                if ((recst >> b) & 1ull) {  // record boundary: root close + root open (the words are written by K2f)
+                    p.rootpos[rec + 1] = slot + 1;
+                    rec++;
+                    slot += 2;
+                }
+                if ((openrec >> b) & 1ull) continue;  // only the boundary sits at an opening quote
+                const uint32_t ch = sbase[swz(64 * lane + b)];
+                uint32_t c = sm.ctab[ch];
+                if (c == T_STRING && (pcur == T_OBJ_OPEN || pcur == T_COMMA)) c = T_STRING_KEYPOS;
+                acc &= sm.oktab[pcur * 16 + c];
+                switch (c) {
+                case T_OBJ_OPEN:
+                case T_ARR_OPEN:
+                case T_OBJ_CLOSE:
+                case T_ARR_CLOSE: {
+                    p.brk_tp[kb] = slot;
+                    p.brk_depth[kb] = depth;
+                    p.brk_kind[kb] = (uint8_t)c;
+                    tout[slot] = (uint64_t)ch << 56;  // payload cross-linked after the scope matching
+                    if (acc != 7) wp.atomic_and(p.segmask + (kb >> 2), ~((7u & ~acc) << (8 * (kb & 3))));
+                    acc = 7;
+                    kb++;
+                    depth += c <= T_ARR_OPEN ? 1 : -1;
+                    slot++;
+                    break;
+                }
+                case T_STRING:
+                case T_STRING_KEYPOS: {  // at the closing quote: stage2...go:72-113
+                    const uint32_t rank_b = pi::popc64(K & below64(b));
+                    const uint64_t lower = qb & below64(b);
+                    const uint32_t dl = lower ? rank_b - pi::popc64(K & below64(64 - pi::clz64(lower))) : part_lane + rank_b;
+                    tout[slot] = ((uint64_t)'"' << 56) | (STRINGBUFBIT + (uint64_t)(lane_str + rank_b - dl));
+                    tout[slot + 1] = dl;
+                    slot += 2;
+                    break;
+                }
+                case T_NUMBER: {
+                    NumEntry ne;
+                    ne.pos = (uint32_t)(block_pos + b);
+                    ne.slot = slot;
+                    p.numlist[ni++] = ne;
+                    slot += 2;
+                    break;
+                }
+                case T_TRUE:
+                case T_FALSE:
+                case T_NULL:
+                    if (!atom_ok_p(rd, block_pos + b, p.len, c)) err = 1;
+                    tout[slot] = (uint64_t)ch << 56;
+                    slot++;
+                    break;
+                case T_INVALID: err = 1; break;
+                default: break;  // ':' ',' newline
+                }
+                pcur = c;
+            }
+            if (acc != 7) wp.atomic_and(p.segmask + (kb >> 2), ~((7u & ~acc) << (8 * (kb & 3))));
+        }
+        if (staged) {
+            wp.sync();
+            uint64_t* dst = p.tape + slot0;
+            for (uint32_t i = lane; i < w_step; i += 32) dst[i] = sm.tstage[i];
+            wp.sync();
+        }
+        run.w += w_step;
+        run.str += k_step;
+        run.brk += b_step;
+        run.rec += r_step;
+        run.depth += d_step;
+        run.num += n_step;
+    }
+
+    if (wp.any(err != 0) && lane == 0) wp.atomic_or(p.error, 1u);
+    if (!EMIT && lane == 0) {
+        run.trail = (hasq ? TRAIL_HASQ : 0u) | (trail & ~TRAIL_HASQ);
+        p.agg[slab] = run;
+    }
+}
+
+}  // namespace sj
