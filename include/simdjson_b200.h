@@ -58,6 +58,11 @@ const char* sj_error_string(int rc);
 int sj_ctx_create(int device, sj_ctx** out);
 void sj_ctx_destroy(sj_ctx* ctx);
 
+/* Stage-2 implementation used by this context: 0 (default) = the streaming kernels (one warp per 6 KiB slab of the
+ * message, stage2_stream.cuh) whenever copy_strings is on, 1 = the per-structural kernels (stage2.cuh) always -- the
+ * older implementation, kept as the copy_strings = false path and as a second implementation the tests compare with. */
+int sj_ctx_set_stage2_impl(sj_ctx* ctx, int impl);
+
 /* pinned host memory for callers that want full PCIe speed (optional) */
 void* sj_host_alloc(size_t bytes);
 void sj_host_free(void* p);

@@ -46,10 +46,12 @@ struct sj_ctx {
     // stage 1
     DevBuf msg;      // device copy of the (trimmed) message, padded
     DevBuf idx;      // structural positions (uint32)
-    DevBuf desc;     // K1 look-back descriptors (17 bytes per tile)
+    DevBuf desc;     // K1 look-back descriptors (one 128-byte slot per tile and chain) + per-tile slab in-string bits
+    const uint32_t* last_slabpar = nullptr;  // the in-string bits of the last stage-1 launch (inside desc), or null
     DevBuf result;   // Stage1Result + Stage2Result
     void* host_result = nullptr;  // pinned mirror
     // stage 2
+    int s2_impl = 0;  // stage 2: 0 = streaming kernels (stage2_stream.cuh) when copy_strings is on, 1 = per-structural kernels (stage2.cuh) always
     DevBuf s2a, s2b, s2c, s2d, s2e, s2f, s2g;  // s2a/s2b: stage-2 scratch (before / after the totals are known), s2c: backslash block map
     DevBuf tape, strings;  // device outputs for the host-buffer API
     // tape consumers (consume.cuh): needles + counters, root list of a foreign tape

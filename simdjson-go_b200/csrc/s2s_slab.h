@@ -580,6 +580,7 @@ SJ_HD void s2s_slab(W& wp, const S2sParams& p, uint32_t slab, const S2sWarpMem& 
             for (uint32_t i = lane; i < w_step; i += 32) dst[i] = sm.tstage[i];
             wp.sync();
         }
+        wp.sync();  // both staging areas are reused by the next step
         run.w += w_step;
         run.str += k_step;
         run.brk += b_step;

@@ -12,6 +12,7 @@
 #include "context.cuh"
 #include "stage1.cuh"
 #include "stage2.cuh"
+#include "stage2_stream.cuh"
 #include "consume.cuh"
 
 using namespace sj;
@@ -144,6 +145,10 @@ extern "C" int sj_ctx_create(int device, sj_ctx** out) {
     if (!c) return SJ_ERR_ARGUMENT;
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
+    {
+        const char* e = getenv("SJ_B200_STAGE2");
+        c->s2_impl = (e && strcmp(e, "legacy") == 0) ? 1 : 0;
+    }
     // every failure below leaves through sj_ctx_destroy (stream, events, pinned result block, device scratch)
     const int rc = [&]() -> int {
         SJ_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -160,6 +165,8 @@ extern "C" int sj_ctx_create(int device, sj_ctx** out) {
                                            (int)S1_SMEM_BYTES));
         SJ_CUDA_CHECK(cudaFuncSetAttribute(stage1_flatten_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)S1_SMEM_BYTES));
+        SJ_CUDA_CHECK(cudaFuncSetAttribute(s2s_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S2S_SMEM_COUNT));
+        SJ_CUDA_CHECK(cudaFuncSetAttribute(s2s_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S2S_SMEM_EMIT));
         int per_sm = 0;
         SJ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stage1_flatten_kernel<true, true>, S1_THREADS,
                                                                     S1_SMEM_BYTES));
@@ -189,6 +196,14 @@ extern "C" void sj_ctx_destroy(sj_ctx* c) {
     if (c->ev[1]) cudaEventDestroy(c->ev[1]);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
+}
+
+// stage-2 implementation of a context: 0 = streaming kernels when copy_strings is on (default), 1 = per-structural
+// kernels always.  The environment variable SJ_B200_STAGE2=legacy selects 1 for every new context (A/B runs).
+extern "C" int sj_ctx_set_stage2_impl(sj_ctx* c, int impl) {
+    if (!c || impl < 0 || impl > 1) return SJ_ERR_ARGUMENT;
+    c->s2_impl = impl;
+    return SJ_OK;
 }
 
 extern "C" void* sj_host_alloc(size_t bytes) {
@@ -228,14 +243,15 @@ extern "C" int sj_kernel_launches(sj_ctx* c, uint64_t* count) {
 // stage 1
 // ---------------------------------------------------------------------------------
 static int launch_stage1(sj_ctx* c, const uint8_t* d_msg, size_t len, bool ndjson, bool deltas, uint32_t* d_out,
-                         size_t cap, uint32_t* d_bsmap = nullptr) {
+                         size_t cap, uint32_t* d_bsmap = nullptr, bool want_slabpar = false) {
     if (len == 0 || len > SJ_MAX_MESSAGE) return SJ_ERR_TOO_LARGE;
     if ((reinterpret_cast<uintptr_t>(d_msg) & 15) != 0) return SJ_ERR_ARGUMENT;
     const int ntiles = (int)((len + S1_TILE_BYTES - 1) / S1_TILE_BYTES);
     // descriptor block: [lastp1 u32][chain-1 slots][chain-2 slots]; a slot per tile and chain
     const size_t n16 = ((size_t)ntiles + 15) & ~(size_t)15;
     const size_t off_last = 0, off_par = (n16 * 4 + 127) & ~(size_t)127, off_cnt = off_par + (size_t)ntiles * S1_DESC_STRIDE;
-    const size_t desc_bytes = off_cnt + (size_t)ntiles * S1_DESC_STRIDE;
+    const size_t off_slab = off_cnt + (size_t)ntiles * S1_DESC_STRIDE;  // per tile: in-string bits of its slabs
+    const size_t desc_bytes = off_slab + n16 * 4;
     int rc = c->desc.reserve(desc_bytes);
     if (rc) return rc;
     SJ_CUDA_CHECK(cudaMemsetAsync(c->desc.p, 0, desc_bytes, c->stream));
@@ -251,6 +267,8 @@ static int launch_stage1(sj_ctx* c, const uint8_t* d_msg, size_t len, bool ndjso
     p.result = c->result.as<Stage1Result>();
     p.ntiles = ntiles;
     p.bsmap = d_bsmap;
+    p.slabpar = want_slabpar ? reinterpret_cast<uint32_t*>(c->desc.as<uint8_t>() + off_slab) : nullptr;
+    c->last_slabpar = p.slabpar;
     p.prof = reinterpret_cast<unsigned long long*>(c->result.as<uint8_t>() + 128);
     int grid = ntiles;
     if (grid > c->s1_max_ctas) grid = c->s1_max_ctas;

@@ -293,18 +293,21 @@ static int stage2_verdict(const Stage2Result& r) {
     return SJ_OK;
 }
 
-// stage 1 into the context's index buffer (absolute positions), growing it once if needed
-static int stage1_positions(sj_ctx* c, const uint8_t* d_msg, size_t len, bool ndjson, Stage1Result* r) {
+// stage 1 into the context's index buffer (absolute positions), growing it once if needed.  `stream`: stage 2 will
+// be the streaming kernels (they take the per-slab in-string bits from K1 instead of the per-block backslash map)
+static int stage1_positions(sj_ctx* c, const uint8_t* d_msg, size_t len, bool ndjson, Stage1Result* r, bool stream) {
     size_t dcap = len / 4 + 1024;
     if (c->idx.cap / sizeof(uint32_t) > dcap) dcap = c->idx.cap / sizeof(uint32_t);
     // one bit per 64-byte block, one word per 2 KiB step, rounded up to whole tiles
     const size_t bs_words = ((len + S1_TILE_BYTES - 1) / S1_TILE_BYTES) * (S1_TILE_BYTES / S1_STEP_BYTES) + 64;
-    int rcb = c->s2c.reserve(bs_words * sizeof(uint32_t));
-    if (rcb) return rcb;
+    if (!stream) {
+        int rcb = c->s2c.reserve(bs_words * sizeof(uint32_t));
+        if (rcb) return rcb;
+    }
     for (int attempt = 0; attempt < 2; attempt++) {
         int rc = c->idx.reserve(dcap * sizeof(uint32_t));
         if (rc) return rc;
-        rc = launch_stage1(c, d_msg, len, ndjson, false, c->idx.as<uint32_t>(), dcap, c->s2c.as<uint32_t>());
+        rc = launch_stage1(c, d_msg, len, ndjson, false, c->idx.as<uint32_t>(), dcap, stream ? nullptr : c->s2c.as<uint32_t>(), stream);
         if (rc) return rc;
         rc = fetch_stage1_result(c, r);
         if (rc) return rc;
@@ -312,6 +315,160 @@ static int stage1_positions(sj_ctx* c, const uint8_t* d_msg, size_t len, bool nd
         dcap = (size_t)r->n_idx + 64;
     }
     return SJ_ERR_CAPACITY;
+}
+
+static inline bool use_stream_stage2(const sj_ctx* c, uint32_t flags) {
+    return c->s2_impl == 0 && (flags & SJ_FLAG_COPY_STRINGS) != 0;
+}
+
+// ---------------------------------------------------------------------------------
+// stage 2, streaming kernels (stage2_stream.cuh): K2p count -> K2q scan -> [totals to the host] -> K2r emit ->
+// K2h numbers, K2d scope matching, K2e links + grammar verdict, K2f roots.  copy_strings only (options.go:13 default).
+// ---------------------------------------------------------------------------------
+static int run_stage2_stream(sj_ctx* c, const uint8_t* d_msg, size_t len, const uint32_t* d_idx, uint32_t n, uint32_t flags,
+                             uint64_t* d_tape, size_t tape_cap, uint8_t* d_strings, size_t strings_cap, Stage2Result* out) {
+    const uint32_t nslabs = (uint32_t)((len + S2S_SLAB_BYTES - 1) / S2S_SLAB_BYTES);
+    const uint32_t ngroups = (nslabs + 1023) / 1024;
+    c->last_tape = nullptr;
+    if (!c->last_slabpar) return SJ_ERR_ARGUMENT;  // stage 1 did not run in streaming mode
+    size_t need1 = Carver::need({(size_t)nslabs * sizeof(SlabAgg), (size_t)nslabs * sizeof(SlabAgg), (size_t)ngroups * sizeof(SlabAgg),
+                                 (size_t)ngroups * sizeof(SlabAgg)});
+    int rc = c->s2a.reserve(need1);
+    if (rc) return rc;
+    Carver k1(c->s2a.p);
+    S2sParams p;
+    memset(&p, 0, sizeof p);
+    p.msg = d_msg;
+    p.len = len;
+    p.ndjson = (flags & SJ_FLAG_NDJSON) ? 1 : 0;
+    p.idx = d_idx;
+    p.n_idx = n;
+    p.slabpar = c->last_slabpar;
+    p.slabs_per_tile = S1_WARPS;
+    p.nslabs = nslabs;
+    p.agg = k1.take<SlabAgg>(nslabs);
+    SlabAgg* pre = k1.take<SlabAgg>(nslabs);
+    SlabAgg* grp_sum = k1.take<SlabAgg>(ngroups);
+    SlabAgg* grp_pre = k1.take<SlabAgg>(ngroups);
+    p.pre = pre;
+    p.grp_pre = grp_pre;
+    Stage2Result* d_res = reinterpret_cast<Stage2Result*>(c->result.as<uint8_t>() + 64);
+    p.error = &d_res->error;
+    SJ_CUDA_CHECK(cudaMemsetAsync(d_res, 0, sizeof(Stage2Result), c->stream));
+    const unsigned grid = (nslabs + S2S_WARPS - 1) / S2S_WARPS;
+    s2s_count_kernel<<<grid, S2S_THREADS, S2S_SMEM_COUNT, c->stream>>>(p);
+    s2s_scan_groups_kernel<<<ngroups, 1024, 0, c->stream>>>(p.agg, nslabs, pre, grp_sum);
+    s2s_scan_top_kernel<<<1, 1024, 0, c->stream>>>(grp_sum, ngroups, grp_pre, d_res);
+    c->launches += 3;
+    SJ_CUDA_CHECK(cudaGetLastError());
+    Stage2Result* h_res = reinterpret_cast<Stage2Result*>(reinterpret_cast<uint8_t*>(c->host_result) + 64);
+    SJ_CUDA_CHECK(cudaMemcpyAsync(h_res, d_res, sizeof(Stage2Result), cudaMemcpyDeviceToHost, c->stream));
+    SJ_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    const Stage2Result tot = *h_res;
+    *out = tot;
+
+    if (!d_tape) {
+        rc = c->tape.reserve(tot.tape_len * 8 + 64);
+        if (rc) return rc;
+        rc = c->strings.reserve(tot.strings_len + 64);
+        if (rc) return rc;
+        d_tape = c->tape.as<uint64_t>();
+        tape_cap = tot.tape_len;
+        d_strings = c->strings.as<uint8_t>();
+        strings_cap = tot.strings_len;
+    } else if (tot.tape_len > tape_cap || tot.strings_len > strings_cap) {
+        return SJ_ERR_CAPACITY;
+    }
+    p.tape = d_tape;
+    p.strings = d_strings;
+
+    const size_t nb = (size_t)tot.n_brackets;
+    size_t lvl_total = 0;
+    {
+        size_t sz = nb;
+        while (sz > 32) {
+            sz = (sz + 31) / 32;
+            lvl_total += sz;
+        }
+    }
+    const size_t seg_words = (nb + 1 + 3) / 4;
+    const uint32_t n_num = tot.n_numbers;
+    size_t need2 = Carver::need({nb * 4, nb * 4, nb, nb * 4, (lvl_total + 8) * 4, seg_words * 4, ((size_t)tot.n_records + 2) * 4,
+                                 (size_t)n_num * sizeof(NumEntry)});
+    rc = c->s2b.reserve(need2);
+    if (rc) return rc;
+    Carver k2(c->s2b.p);
+    p.brk_tp = k2.take<uint32_t>(nb);
+    p.brk_depth = k2.take<int32_t>(nb);
+    p.brk_kind = k2.take<uint8_t>(nb);
+    int32_t* par = k2.take<int32_t>(nb);
+    int32_t* lvl_mem = k2.take<int32_t>(lvl_total + 8);
+    p.segmask = k2.take<uint32_t>(seg_words);
+    p.rootpos = k2.take<uint32_t>((size_t)tot.n_records + 2);
+    p.numlist = k2.take<NumEntry>(n_num);
+    SJ_CUDA_CHECK(cudaMemsetAsync(p.segmask, 0xff, seg_words * 4, c->stream));
+
+    s2s_emit_kernel<<<grid, S2S_THREADS, S2S_SMEM_EMIT, c->stream>>>(p);
+    c->launches++;
+    if (n_num) {
+        s2s_numbers_kernel<<<(n_num + S2_THREADS - 1) / S2_THREADS, S2_THREADS, 0, c->stream>>>(d_msg, len, p.numlist, n_num, d_tape, p.error);
+        c->launches++;
+    }
+    if (nb > 0) {
+        AnsvLevels L;
+        memset(&L, 0, sizeof L);
+        L.lv[0] = p.brk_depth;
+        L.n[0] = (uint32_t)nb;
+        L.nlevels = 1;
+        size_t sz = nb;
+        int32_t* next = lvl_mem;
+        while (sz > 32 && L.nlevels < ANSV_MAX_LEVELS) {
+            size_t nsz = (sz + 31) / 32;
+            const unsigned threads = 256;
+            const unsigned blocks = (unsigned)((nsz * 32 + threads - 1) / threads);
+            s2_min32_kernel<<<blocks, threads, 0, c->stream>>>(L.lv[L.nlevels - 1], (uint32_t)sz, next, (uint32_t)nsz);
+            c->launches++;
+            L.lv[L.nlevels] = next;
+            L.n[L.nlevels] = (uint32_t)nsz;
+            L.nlevels++;
+            next += nsz;
+            sz = nsz;
+        }
+        s2_ansv_kernel<<<(unsigned)((nb + S2_THREADS - 1) / S2_THREADS), S2_THREADS, 0, c->stream>>>(L, par);
+        c->launches++;
+    }
+    s2s_link_kernel<<<(unsigned)((nb + 1 + S2_THREADS - 1) / S2_THREADS), S2_THREADS, 0, c->stream>>>(p, par, (uint32_t)nb);
+    {
+        Stage2Params rp;
+        memset(&rp, 0, sizeof rp);
+        rp.rootpos = p.rootpos;
+        rp.tape = d_tape;
+        rp.tape_cap = tape_cap;
+        const uint64_t nrec = tot.n_records;
+        s2_roots_kernel<<<(unsigned)((nrec + 1 + 255) / 256), 256, 0, c->stream>>>(rp, nrec, tot.tape_len);
+    }
+    c->launches += 2;
+    SJ_CUDA_CHECK(cudaGetLastError());
+    SJ_CUDA_CHECK(cudaMemcpyAsync(h_res, d_res, sizeof(Stage2Result), cudaMemcpyDeviceToHost, c->stream));
+    SJ_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    *out = *h_res;
+    if (stage2_verdict(*out) == SJ_OK) {
+        c->last_rootpos = p.rootpos;
+        c->last_records = tot.n_records;
+        c->last_tape = d_tape;
+        c->last_tape_len = tot.tape_len;
+        c->last_strings = d_strings;
+        c->last_msg = d_msg;
+    }
+    return SJ_OK;
+}
+
+// stage 2 by whichever implementation the context and the flags select
+static int run_stage2_any(sj_ctx* c, const uint8_t* d_msg, size_t len, uint32_t n, uint32_t flags, uint64_t* d_tape, size_t tape_cap,
+                          uint8_t* d_strings, size_t strings_cap, Stage2Result* out) {
+    if (use_stream_stage2(c, flags))
+        return run_stage2_stream(c, d_msg, len, c->idx.as<uint32_t>(), n, flags, d_tape, tape_cap, d_strings, strings_cap, out);
+    return run_stage2(c, d_msg, len, c->idx.as<uint32_t>(), n, flags, d_tape, tape_cap, d_strings, strings_cap, out, c->s2c.as<uint32_t>());
 }
 
 extern "C" int sj_parse_device(sj_ctx* c, const uint8_t* d_msg, size_t len, uint32_t flags, uint64_t* d_tape,
@@ -324,14 +481,13 @@ extern "C" int sj_parse_device(sj_ctx* c, const uint8_t* d_msg, size_t len, uint
     if (len > SJ_MAX_MESSAGE) return SJ_ERR_TOO_LARGE;
     SJ_CUDA_CHECK(cudaSetDevice(c->device));
     Stage1Result r1;
-    int rc = stage1_positions(c, d_msg, len, (flags & SJ_FLAG_NDJSON) != 0, &r1);
+    int rc = stage1_positions(c, d_msg, len, (flags & SJ_FLAG_NDJSON) != 0, &r1, use_stream_stage2(c, flags));
     if (rc) return rc;
     // the byte under the last structural comes back with the stage-1 result (stage1_finish_kernel)
     const uint8_t last_char = r1.n_idx && r1.last_pos < len ? (uint8_t)r1.last_char : 0;
     if (!stage1_ok(r1, last_char)) return SJ_ERR_STAGE1;
     Stage2Result r2{};
-    rc = run_stage2(c, d_msg, len, c->idx.as<uint32_t>(), r1.n_idx, flags, d_tape, tape_cap, d_strings, strings_cap, &r2,
-                    c->s2c.as<uint32_t>());
+    rc = run_stage2_any(c, d_msg, len, r1.n_idx, flags, d_tape, tape_cap, d_strings, strings_cap, &r2);
     if (rc == SJ_OK || rc == SJ_ERR_CAPACITY) {  // the required sizes (simdjson_b200.h): only when stage 2 got as far as its totals
         *tape_len = r2.tape_len;
         *strings_len = r2.strings_len;
@@ -357,13 +513,12 @@ extern "C" int sj_parse(sj_ctx* c, const uint8_t* msg, size_t len, uint32_t flag
     int rc = upload_message(c, msg + a, n);
     if (rc) return rc;
     Stage1Result r1;
-    rc = stage1_positions(c, c->msg.as<uint8_t>(), n, (flags & SJ_FLAG_NDJSON) != 0, &r1);
+    rc = stage1_positions(c, c->msg.as<uint8_t>(), n, (flags & SJ_FLAG_NDJSON) != 0, &r1, use_stream_stage2(c, flags));
     if (rc) return rc;
     uint8_t last_char = r1.n_idx && r1.last_pos < n ? msg[a + r1.last_pos] : 0;
     if (!stage1_ok(r1, last_char)) return SJ_ERR_STAGE1;
     Stage2Result r2{};
-    rc = run_stage2(c, c->msg.as<uint8_t>(), n, c->idx.as<uint32_t>(), r1.n_idx, flags, nullptr, 0, nullptr, 0, &r2,
-                    c->s2c.as<uint32_t>());
+    rc = run_stage2_any(c, c->msg.as<uint8_t>(), n, r1.n_idx, flags, nullptr, 0, nullptr, 0, &r2);
     if (rc == SJ_OK || rc == SJ_ERR_CAPACITY) {
         *tape_len = r2.tape_len;
         *strings_len = r2.strings_len;
@@ -395,12 +550,11 @@ static int parse_into_ctx(sj_ctx* c, const uint8_t* msg, size_t len, uint32_t fl
     int rc = upload_message(c, msg + a, n);
     if (rc) return rc;
     Stage1Result r1;
-    rc = stage1_positions(c, c->msg.as<uint8_t>(), n, (flags & SJ_FLAG_NDJSON) != 0, &r1);
+    rc = stage1_positions(c, c->msg.as<uint8_t>(), n, (flags & SJ_FLAG_NDJSON) != 0, &r1, use_stream_stage2(c, flags));
     if (rc) return rc;
     const uint8_t last_char = r1.n_idx && r1.last_pos < n ? msg[a + r1.last_pos] : 0;
     if (!stage1_ok(r1, last_char)) return SJ_ERR_STAGE1;
-    rc = run_stage2(c, c->msg.as<uint8_t>(), n, c->idx.as<uint32_t>(), r1.n_idx, flags, nullptr, 0, nullptr, 0, r2,
-                    c->s2c.as<uint32_t>());
+    rc = run_stage2_any(c, c->msg.as<uint8_t>(), n, r1.n_idx, flags, nullptr, 0, nullptr, 0, r2);
     if (rc) return rc;
     return stage2_verdict(*r2);
 }

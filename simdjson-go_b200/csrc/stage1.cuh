@@ -819,6 +819,7 @@ struct Stage1Params {
     uint8_t* dcnt;       // [ntiles * S1_DESC_STRIDE] zeroed: chain-2 descriptor slots
     uint32_t* lastp1;    // [ntiles] position + 1 of the tile's last structural (0 = none)
     uint32_t* bsmap;     // optional: bit k = 64-byte block k contains a backslash (lets stage 2 skip the string scan)
+    uint32_t* slabpar;   // optional: [ntiles] bit w = "inside a string" in front of slab w of the tile (handed to the streaming stage 2)
     Stage1Result* result;
     int ntiles;
     unsigned long long* prof;  // [8] cycle totals when built with -DSJ_PROFILE_PHASES
@@ -956,7 +957,12 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) stage1_flatten_ker
                     if (lane == 0) st_relaxed_u32(par_slot(p.dpar, tile), DP_VALID | DP_INCL | ((tile_par ^ tin) ? DP_PAR : 0));
                 }
             }
-            if (lane < S1_WARPS) s_parin[lane] = tin ^ (__popc(parbits & lanemask_lt()) & 1);
+            const uint32_t slab_in = tin ^ (__popc(parbits & lanemask_lt()) & 1);
+            if (lane < S1_WARPS) s_parin[lane] = slab_in;
+            if (p.slabpar) {  // (kernel-uniform)
+                const uint32_t inbits = __ballot_sync(FULL, lane < S1_WARPS && slab_in != 0);
+                if (cur && lane == 0) p.slabpar[tile] = inbits;
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_Q);
             SJ_TL(2)

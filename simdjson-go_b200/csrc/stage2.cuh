@@ -17,27 +17,11 @@
 #pragma once
 #include "common.cuh"
 #include "number.cuh"
+#include "s2s_core.h"
 
 namespace sj {
 
-enum : uint8_t {
-    T_INVALID = 0,
-    T_OBJ_OPEN = 1,
-    T_ARR_OPEN = 2,
-    T_OBJ_CLOSE = 3,
-    T_ARR_CLOSE = 4,
-    T_COLON = 5,
-    T_COMMA = 6,
-    T_STRING = 7,
-    T_NUMBER = 8,
-    T_TRUE = 9,
-    T_FALSE = 10,
-    T_NULL = 11,
-    T_NEWLINE = 12,
-    T_START = 13,
-};
-
-constexpr uint64_t STRINGBUFBIT = 0x80000000000000ull;  // parsed_json.go:29
+// structural types, the grammar (transition_ok) and STRINGBUFBIT live in s2s_core.h (shared with the streaming kernels)
 constexpr uint32_t AUX_COPY = 0x80000000u;              // string goes to the string buffer
 constexpr uint32_t AUX_ESC = 0x40000000u;               // string contains escapes (source length != unescaped length)
 constexpr uint32_t AUX_LEN = 0x3fffffffu;
@@ -1217,43 +1201,6 @@ __global__ void __launch_bounds__(S2_THREADS) s2_ansv_kernel(AnsvLevels L, int32
 // ---------------------------------------------------------------------------------
 // K2e: grammar (the state machine's transitions) and bracket cross-links
 // ---------------------------------------------------------------------------------
-enum : uint32_t { CTX_ROOT = 0, CTX_OBJ = 1, CTX_ARR = 2 };
-
-__host__ __device__ constexpr bool is_value_start(uint32_t c) {
-    return c == T_STRING || c == T_NUMBER || c == T_TRUE || c == T_FALSE || c == T_NULL || c == T_OBJ_OPEN ||
-           c == T_ARR_OPEN;
-}
-__host__ __device__ constexpr bool is_scalar_or_close(uint32_t c) {
-    return c == T_NUMBER || c == T_TRUE || c == T_FALSE || c == T_NULL || c == T_OBJ_CLOSE || c == T_ARR_CLOSE;
-}
-
-// stage2_build_tape_amd64.go:176-425, restated as "is c allowed after p (after pp) inside ctx"
-__host__ __device__ constexpr bool transition_ok(uint32_t ctx, uint32_t pp, uint32_t p, uint32_t c) {
-    if (c == T_INVALID) return false;
-    if (ctx == CTX_OBJ) {
-        if (p == T_OBJ_OPEN) return c == T_STRING || c == T_OBJ_CLOSE;                // object_begin :225-240
-        if (p == T_STRING) {
-            const bool is_key = pp == T_OBJ_OPEN || pp == T_COMMA;
-            return is_key ? c == T_COLON : (c == T_COMMA || c == T_OBJ_CLOSE);         // :242-248 / objectContinue :302-324
-        }
-        if (p == T_COLON) return is_value_start(c);                                      // :251-300
-        if (is_scalar_or_close(p)) return c == T_COMMA || c == T_OBJ_CLOSE;             // objectContinue
-        if (p == T_COMMA) return c == T_STRING;                                          // :309-316
-        return false;
-    }
-    if (ctx == CTX_ARR) {
-        if (p == T_ARR_OPEN) return is_value_start(c) || c == T_ARR_CLOSE;             // arrayBegin :347-353
-        if (p == T_STRING || is_scalar_or_close(p)) return c == T_COMMA || c == T_ARR_CLOSE;  // arrayContinue :409-425
-        if (p == T_COMMA) return is_value_start(c);                                      // mainArraySwitch :355-407
-        return false;
-    }
-    // top level
-    if (p == T_START) return c == T_OBJ_OPEN || c == T_ARR_OPEN;                       // continueRoot :176-188
-    if (p == T_OBJ_CLOSE || p == T_ARR_CLOSE) return c == T_NEWLINE;                   // startContinue :196-198
-    if (p == T_NEWLINE) return c == T_NEWLINE || c == T_OBJ_OPEN || c == T_ARR_OPEN;   // :200-221
-    return false;
-}
-
 // transition_ok as a bit table, built at compile time: the previous-previous structural only
 // matters as "was the string before us a key" (pp is '{' or ','), so the index is
 // ((ctx * 2 + is_key) * 14 + p) * 14 + c  -- 1176 bits.  K2e copies it to shared memory and replaces

@@ -44,6 +44,12 @@ class Context:
             raise SjError(rc)
         self.h = h
 
+    def set_stage2_impl(self, impl):
+        """0 = streaming stage-2 kernels whenever copy_strings is on (default), 1 = per-structural kernels always"""
+        rc = self.L.sj_ctx_set_stage2_impl(self.h, int(impl))
+        if rc != OK:
+            raise SjError(rc)
+
     def close(self):
         if getattr(self, "h", None):
             self.L.sj_ctx_destroy(self.h)

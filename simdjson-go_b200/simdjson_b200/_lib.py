@@ -16,7 +16,7 @@ OK, ERR_STAGE1, ERR_STAGE2, ERR_NO_DEVICE, ERR_CAPACITY, ERR_TOO_LARGE, ERR_ARGU
 
 # every symbol include/simdjson_b200.h declares
 EXPORTS = [
-    "sj_supported", "sj_device_count", "sj_error_string", "sj_ctx_create", "sj_ctx_destroy", "sj_host_alloc",
+    "sj_supported", "sj_device_count", "sj_error_string", "sj_ctx_create", "sj_ctx_destroy", "sj_ctx_set_stage2_impl", "sj_host_alloc",
     "sj_host_free", "sj_trim_space", "sj_bounds", "sj_parse", "sj_parse_device", "sj_find_structural_indices", "sj_stage1_device",
     "sj_stage1_launch", "sj_ctx_sync", "sj_event_record", "sj_event_elapsed_ms", "sj_kernel_launches",
     "sj_test_block_masks", "sj_test_geometry", "sj_test_finalize", "sj_test_flatten_bits", "sj_test_parse_strings",
@@ -57,6 +57,10 @@ def load():
     L.sj_ctx_create.argtypes = [i32, C.POINTER(vp)]
     L.sj_ctx_destroy.restype = None
     L.sj_ctx_destroy.argtypes = [vp]
+    L.sj_ctx_set_stage2_impl.restype = i32
+    L.sj_ctx_set_stage2_impl.argtypes = [vp, i32]
+    L.sj_test_geometry.restype = None
+    L.sj_test_geometry.argtypes = [vp]
     L.sj_host_alloc.restype = vp
     L.sj_host_alloc.argtypes = [sz]
     L.sj_host_free.restype = None

@@ -433,3 +433,55 @@ def test_parse_nd_stream_native_errors_and_big_records():
     # chunk (stage-1 failure); the reference skips blank lines (stage2_build_tape_amd64.go:200-205)
     out = list(ParseNDStreamNative(io.BytesIO(b"\n \n" + big + b"\n\n" + big + b"\n"), chunk_bytes=10_000, inflight=2, read_bytes=4096))
     assert sum(sum(1 for _ in pj.Iter().roots()) for pj in out) == 2
+
+
+def test_streaming_and_per_structural_stage2_agree(ctx, oracle_native):
+    """the two stage-2 implementations (streaming kernels, stage2_stream.cuh = the default with copy_strings;
+    per-structural kernels, stage2.cuh) give the same tape and string buffer -- on inputs far larger than the oracle
+    comfortably checks, in every BASELINE shape"""
+    import simdjson_b200 as sj
+    legacy = sj.Context(0)
+    legacy.set_stage2_impl(1)
+    try:
+        docs = []
+        for name, k in (("twitter", 40), ("twitterescaped", 40), ("canada", 10), ("gsoc-2018", 8), ("citm_catalog", 12), ("marine_ik", 6)):
+            d = load_fixture(name).strip()
+            docs.append((b"[" + b",".join([d] * k) + b"]", False))
+        pk = load_fixture("parking-citations").strip()
+        docs.append((b"\n".join([pk] * 60), True))
+        for doc, nd in docs:
+            a = ctx.parse(np.frombuffer(doc, dtype=np.uint8), ndjson=nd)
+            b = legacy.parse(np.frombuffer(doc, dtype=np.uint8), ndjson=nd)
+            assert a[0] == b[0] == 0
+            assert np.array_equal(a[1], b[1]) and a[2] == b[2] and a[3] == b[3]
+        # and both agree with the oracle on a mid-sized one
+        d = load_fixture("twitterescaped").strip()
+        assert _same_parse(ctx, oracle_native, b"[" + b",".join([d] * 6) + b"]") == 0
+        assert _same_parse(legacy, oracle_native, b"[" + b",".join([d] * 6) + b"]") == 0
+    finally:
+        legacy.close()
+
+
+def test_streaming_stage2_edges(ctx, oracle_native):
+    """the emulation suite's edge cases (tests/test_s2s_emulation.py) through the real kernels: escapes and strings
+    straddling block / step / slab edges, invalid escapes, grammar soup, NDJSON corner cases"""
+    import tests.test_s2s_emulation as emu
+    import tests.emu_util as eu
+    orig = eu.same_as_oracle
+    calls = [0]
+
+    def via_gpu(oracle, msg, ndjson=False):
+        calls[0] += 1
+        return _same_parse(ctx, oracle, msg, ndjson=ndjson, copy=True)
+
+    emu.same_as_oracle = via_gpu
+    try:
+        emu.test_escapes_across_every_edge(oracle_native)
+        emu.test_invalid_escapes_and_strings(oracle_native)
+        emu.test_strings_across_edges(oracle_native)
+        emu.test_structure_and_grammar(oracle_native)
+        emu.test_ndjson(oracle_native)
+        emu.test_golden_documents(oracle_native)
+    finally:
+        emu.same_as_oracle = orig
+    assert calls[0] > 3000
