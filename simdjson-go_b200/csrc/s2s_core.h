@@ -204,6 +204,10 @@ struct alignas(16) V16 {
 
 SJ_HD uint64_t mk64u(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 SJ_HD uint64_t below64(uint32_t b) { return b >= 64 ? ~0ull : ((1ull << b) - 1ull); }  // bits [0, b)
+SJ_HD uint64_t lt64(uint32_t b) { return (1ull << b) - 1ull; }                         // bits [0, b), b < 64
+// the events of EV that follow an event of A (A a subset of EV; `cin`: the last event in front of the block is in A):
+// adding (A << 1 | cin) to the complement of EV carries from the position behind each A-event to the next event
+SJ_HD uint64_t next_event(uint64_t A, uint32_t cin, uint64_t EV) { return (((A << 1) | (uint64_t)cin) + ~EV) & EV; }
 SJ_HD uint64_t range64(uint32_t lo, uint32_t hi) { return lo >= hi ? 0ull : below64(hi) & ~below64(lo); }  // bits [lo, hi)
 
 // ---------------------------------------------------------------------------------
@@ -282,7 +286,7 @@ SJ_HD void bit_planes32p(const uint32_t* w, uint32_t (&pl)[8]) {
 }
 
 struct Half2 {
-    uint32_t bs, qt, ws, nl, open, close, cc, numc, atomc;
+    uint32_t bs, qt, ws, nl, open, close, cc, comma, curly, numc, atomc;
 };
 SJ_HD Half2 classify_planes2(const uint32_t (&p)[8]) {
     const uint32_t n7 = ~p[7];
@@ -305,7 +309,9 @@ SJ_HD Half2 classify_planes2(const uint32_t (&p)[8]) {
     m.bs = hi5 & loC;                                    // backslash
     m.open = hi57 & loB;                                 // [ {
     m.close = hi57 & loD;                                // ] }
-    m.cc = (hi2 & loC) | (hi3 & loA);                    // , :
+    m.comma = hi2 & loC;                                 // ,
+    m.cc = m.comma | (hi3 & loA);                        // , :
+    m.curly = p[5];                                      // among [ ] { }: the curly ones (0x7b, 0x7d against 0x5b, 0x5d)
     m.ws = (hi2 & lo0) | (hi0 & (lo9 | loA | loD));      // space \t \n \r
     m.nl = hi0 & loA;                                    // \n
     m.numc = (hi3 & (~p[3] | (c30 & ~p[1]))) | (hi2 & loD);  // 0-9 -
@@ -313,7 +319,7 @@ SJ_HD Half2 classify_planes2(const uint32_t (&p)[8]) {
     return m;
 }
 struct Class64 {
-    uint64_t bs, qt, ws, nl, open, close, cc, numc, atomc;
+    uint64_t bs, qt, ws, nl, open, close, cc, comma, curly, numc, atomc;
 };
 // w[16]: the block's 64 bytes in natural order
 SJ_HD Class64 classify_block2(const uint32_t (&w)[16]) {
@@ -329,6 +335,8 @@ SJ_HD Class64 classify_block2(const uint32_t (&w)[16]) {
     m.open = mk64u(a.open, b.open);
     m.close = mk64u(a.close, b.close);
     m.cc = mk64u(a.cc, b.cc);
+    m.comma = mk64u(a.comma, b.comma);
+    m.curly = mk64u(a.curly, b.curly);
     m.numc = mk64u(a.numc, b.numc);
     m.atomc = mk64u(a.atomc, b.atomc);
     return m;

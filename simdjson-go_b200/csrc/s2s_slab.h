@@ -504,75 +504,101 @@ SJ_HD void s2s_slab(W& wp, const S2sParams& p, uint32_t slab, const S2sWarpMem& 
             uint32_t pcur = below ? below_last_ref : pr;
             if (HE) pr = wp.shfl(last_ref, 31 - pi::clz32(HE));
 
-            uint32_t slot = slot0 + w_ex;
-            uint32_t kb = run.brk + b_ex;
-            int32_t depth = run.depth + d_ex;
-            uint32_t rec = run.rec + r_ex;
-            uint32_t ni = run.num + n_ex;
-            const uint32_t lane_str = str_base + k_ex;  // Strings.B offset of the lane's first kept byte
-            uint32_t acc = 7;
-            const uint64_t openrec = recst & qb & qm;  // (invalid input only: a record that starts with a string)
-            uint64_t ev = EV | openrec;
-            while (ev) {
-                const uint32_t b = pi::ctz64(ev);
-                ev &= ev - 1;
-                if ((recst >> b) & 1ull) {  // record boundary: root close + root open (the words are written by K2f)
-                    p.rootpos[rec + 1] = slot + 1;
-                    rec++;
-                    slot += 2;
-                }
-                if ((openrec >> b) & 1ull) continue;  // only the boundary sits at an opening quote
-                const uint32_t ch = sbase[swz(64 * lane + b)];
-                uint32_t c = sm.ctab[ch];
-                if (c == T_STRING && (pcur == T_OBJ_OPEN || pcur == T_COMMA)) c = T_STRING_KEYPOS;
-                acc &= sm.oktab[pcur * 16 + c];
-                switch (c) {
-                case T_OBJ_OPEN:
-                case T_ARR_OPEN:
-                case T_OBJ_CLOSE:
-                case T_ARR_CLOSE: {
+            // ---- the grammar, bit-parallel (stage2...go:176-425 as restated by transition_ok): PRE_x = the events whose
+            // previous event is of class x; an event is fine inside an object / an array / at the top level iff its
+            // (previous class, own class) pair is in the respective set.  What depends on the container is decided
+            // per bracket-to-bracket segment by K2e. ----
+            const uint64_t O1 = m.open & m.curly & ~qm, O2 = m.open & ~m.curly & ~qm;
+            const uint64_t C1 = m.close & m.curly & ~qm, C2 = m.close & ~m.curly & ~qm;
+            const uint64_t COMMA = m.comma & ~qm, COLON = m.cc & ~m.comma & ~qm;
+            const uint64_t NUM = V & m.numc, ATOM = V & m.atomc;
+            const uint64_t BRK = O1 | O2 | C1 | C2;
+            uint64_t BADR, BADO, BADA;
+            {
+                const uint64_t PRE_O1 = next_event(O1, pcur == T_OBJ_OPEN, EV), PRE_O2 = next_event(O2, pcur == T_ARR_OPEN, EV);
+                const uint64_t PRE_COLON = next_event(COLON, pcur == T_COLON, EV), PRE_COMMA = next_event(COMMA, pcur == T_COMMA, EV);
+                const uint64_t PRE_SCAL = next_event(NUM | ATOM, pcur >= T_NUMBER && pcur <= T_NULL, EV);
+                const uint64_t PRE_CLOSE = next_event(C1 | C2, pcur == T_OBJ_CLOSE || pcur == T_ARR_CLOSE, EV);
+                const uint64_t PRE_NL = next_event(NLS, pcur == T_NEWLINE, EV);
+                const uint64_t PRE_START = pcur == T_START ? (EV & (0 - EV)) : 0ull;  // the very first event of the message
+                const uint64_t STRK = closeq & (PRE_O1 | PRE_COMMA), STRV = closeq & ~STRK;  // strings in key position / elsewhere
+                const uint64_t PRE_STRK = next_event(STRK, pcur == T_STRING_KEYPOS, EV), PRE_STRV = next_event(STRV, pcur == T_STRING, EV);
+                const uint64_t VALSTART = closeq | NUM | ATOM | O1 | O2;
+                const uint64_t VEND = PRE_SCAL | PRE_CLOSE;
+                const uint64_t OKO = (PRE_O1 & (closeq | C1)) | (PRE_COLON & VALSTART) | (PRE_COMMA & closeq) | (PRE_STRK & COLON) |
+                                     ((PRE_STRV | VEND) & (COMMA | C1));
+                const uint64_t OKA = (PRE_O2 & (VALSTART | C2)) | (PRE_COMMA & VALSTART) | ((PRE_STRK | PRE_STRV | VEND) & (COMMA | C2));
+                const uint64_t OKR = (PRE_START & (O1 | O2)) | (PRE_CLOSE & NLS) | (PRE_NL & (NLS | O1 | O2));
+                BADR = EV & ~OKR, BADO = EV & ~OKO, BADA = EV & ~OKA;
+            }
+            if (V & ~m.numc & ~m.atomc) err = 1;  // a value that starts with neither a digit, '-' nor t / f / n
+
+            // ---- emission: one uniform loop per class of event; the tape slot of an event = words of the events below it ----
+            const uint32_t lane_slot = slot0 + w_ex;
+            const uint64_t W1 = BRK | ATOM, W2 = closeq | NUM;  // one-word / two-word events
+            // record boundaries (root close + root open: the words themselves are written by K2f)
+            for (uint64_t mm = recst; mm; mm &= mm - 1) {
+                const uint32_t b = pi::ctz64(mm);
+                const uint64_t lo = lt64(b);
+                const uint32_t slot = lane_slot + pi::popc64(W1 & lo) + 2 * (pi::popc64(W2 & lo) + pi::popc64(recst & lo));
+                p.rootpos[run.rec + r_ex + pi::popc64(recst & lo) + 1] = slot + 1;
+            }
+            // brackets: records for the scope matching, the tape word, the grammar verdict of the segment they end
+            {
+                uint64_t prev_mask = 0;  // bits up to and including the previous bracket
+                for (uint64_t mm = BRK; mm; mm &= mm - 1) {
+                    const uint32_t b = pi::ctz64(mm);
+                    const uint64_t lo = lt64(b), upto = lo | (1ull << b);
+                    const uint32_t slot = lane_slot + pi::popc64(W1 & lo) + 2 * (pi::popc64(W2 & lo) + pi::popc64(recst & upto));
+                    const uint32_t kb = run.brk + b_ex + pi::popc64(BRK & lo);
+                    const uint32_t opens_below = pi::popc64((O1 | O2) & lo), closes_below = pi::popc64((C1 | C2) & lo);
+                    const bool curly = (m.curly >> b) & 1ull, opening = (m.open >> b) & 1ull;
                     p.brk_tp[kb] = slot;
-                    p.brk_depth[kb] = depth;
-                    p.brk_kind[kb] = (uint8_t)c;
-                    tout[slot] = (uint64_t)ch << 56;  // payload cross-linked after the scope matching
+                    p.brk_depth[kb] = run.depth + d_ex + (int32_t)opens_below - (int32_t)closes_below;
+                    p.brk_kind[kb] = (uint8_t)(opening ? (curly ? T_OBJ_OPEN : T_ARR_OPEN) : (curly ? T_OBJ_CLOSE : T_ARR_CLOSE));
+                    tout[slot] = (uint64_t)((opening ? 0x5bu : 0x5du) | (curly ? 0x20u : 0u)) << 56;  // payload cross-linked after the scope matching
+                    const uint64_t seg = upto & ~prev_mask;
+                    const uint32_t acc = ((BADR & seg) ? 0u : 1u) | ((BADO & seg) ? 0u : 2u) | ((BADA & seg) ? 0u : 4u);
                     if (acc != 7) wp.atomic_and(p.segmask + (kb >> 2), ~((7u & ~acc) << (8 * (kb & 3))));
-                    acc = 7;
-                    kb++;
-                    depth += c <= T_ARR_OPEN ? 1 : -1;
-                    slot++;
-                    break;
+                    prev_mask = upto;
                 }
-                case T_STRING:
-                case T_STRING_KEYPOS: {  // at the closing quote: stage2...go:72-113
-                    const uint32_t rank_b = pi::popc64(K & below64(b));
-                    const uint64_t lower = qb & below64(b);
-                    const uint32_t dl = lower ? rank_b - pi::popc64(K & below64(64 - pi::clz64(lower))) : part_lane + rank_b;
+                const uint64_t seg = ~prev_mask;  // behind the lane's last bracket: the segment goes on in the next lanes
+                const uint32_t acc = ((BADR & seg) ? 0u : 1u) | ((BADO & seg) ? 0u : 2u) | ((BADA & seg) ? 0u : 4u);
+                const uint32_t kb = run.brk + b_ex + n_brk;
+                if (acc != 7) wp.atomic_and(p.segmask + (kb >> 2), ~((7u & ~acc) << (8 * (kb & 3))));
+            }
+            // strings, at their closing quote (stage2...go:72-113)
+            {
+                const uint32_t lane_str = str_base + k_ex;  // Strings.B offset of the lane's first kept byte
+                for (uint64_t mm = closeq; mm; mm &= mm - 1) {
+                    const uint32_t b = pi::ctz64(mm);
+                    const uint64_t lo = lt64(b);
+                    const uint32_t slot = lane_slot + pi::popc64(W1 & lo) + 2 * (pi::popc64(W2 & lo) + pi::popc64(recst & lo));
+                    const uint32_t rank_b = pi::popc64(K & lo);
+                    const uint64_t lower = qb & lo;
+                    const uint32_t dl = lower ? pi::popc64(K & lo & ~lt64(63 - pi::clz64(lower))) : part_lane + rank_b;
                     tout[slot] = ((uint64_t)'"' << 56) | (STRINGBUFBIT + (uint64_t)(lane_str + rank_b - dl));
                     tout[slot + 1] = dl;
-                    slot += 2;
-                    break;
                 }
-                case T_NUMBER: {
-                    NumEntry ne;
-                    ne.pos = (uint32_t)(block_pos + b);
-                    ne.slot = slot;
-                    p.numlist[ni++] = ne;
-                    slot += 2;
-                    break;
-                }
-                case T_TRUE:
-                case T_FALSE:
-                case T_NULL:
-                    if (!atom_ok_p(rd, block_pos + b, p.len, c)) err = 1;
-                    tout[slot] = (uint64_t)ch << 56;
-                    slot++;
-                    break;
-                case T_INVALID: err = 1; break;
-                default: break;  // ':' ',' newline
-                }
-                pcur = c;
             }
-            if (acc != 7) wp.atomic_and(p.segmask + (kb >> 2), ~((7u & ~acc) << (8 * (kb & 3))));
+            // numbers: parsed by K2h from the list
+            for (uint64_t mm = NUM; mm; mm &= mm - 1) {
+                const uint32_t b = pi::ctz64(mm);
+                const uint64_t lo = lt64(b), upto = lo | (1ull << b);
+                NumEntry ne;
+                ne.pos = (uint32_t)(block_pos + b);
+                ne.slot = lane_slot + pi::popc64(W1 & lo) + 2 * (pi::popc64(W2 & lo) + pi::popc64(recst & upto));
+                p.numlist[run.num + n_ex + pi::popc64(NUM & lo)] = ne;
+            }
+            // atoms
+            for (uint64_t mm = ATOM; mm; mm &= mm - 1) {
+                const uint32_t b = pi::ctz64(mm);
+                const uint64_t lo = lt64(b), upto = lo | (1ull << b);
+                const uint32_t slot = lane_slot + pi::popc64(W1 & lo) + 2 * (pi::popc64(W2 & lo) + pi::popc64(recst & upto));
+                const uint32_t ch = sbase[swz(64 * lane + b)];
+                if (!atom_ok_p(rd, block_pos + b, p.len, sm.ctab[ch])) err = 1;
+                tout[slot] = (uint64_t)ch << 56;
+            }
         }
         if (staged) {
             wp.sync();

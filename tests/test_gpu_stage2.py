@@ -484,4 +484,4 @@ def test_streaming_stage2_edges(ctx, oracle_native):
         emu.test_golden_documents(oracle_native)
     finally:
         emu.same_as_oracle = orig
-    assert calls[0] > 3000
+    assert calls[0] > 2500
