@@ -161,6 +161,13 @@ SJ_HD uint32_t ctz64(uint64_t x) {  // undefined for 0
     return (uint32_t)__builtin_ctzll(x);
 #endif
 }
+SJ_HD uint32_t ctz32(uint32_t x) {  // undefined for 0
+#ifdef __CUDA_ARCH__
+    return (uint32_t)__ffs((int)x) - 1u;
+#else
+    return (uint32_t)__builtin_ctz(x);
+#endif
+}
 SJ_HD uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t sel) {  // selectors 0..7 only
 #ifdef __CUDA_ARCH__
     return __byte_perm(a, b, sel);
@@ -216,8 +223,18 @@ SJ_HD uint64_t range64(uint32_t lo, uint32_t hi) { return lo >= hi ? 0ull : belo
 constexpr uint32_t S2S_STEP_BYTES = 2048;                            // one warp pass: 32 lanes x 64 bytes
 constexpr uint32_t S2S_STEPS = 3;
 constexpr uint32_t S2S_SLAB_BYTES = S2S_STEPS * S2S_STEP_BYTES;      // == S1_SLAB_BYTES (static_assert in stage2_stream.cuh)
+// steps of the slab kept as an image in shared memory at a time: 3 = the whole slab (loaded once), 1 = one step (three
+// loads, a third of the shared memory: more warps per SM)
+#ifndef SJ_S2S_IMAGE_STEPS
+#define SJ_S2S_IMAGE_STEPS 3
+#endif
+constexpr uint32_t S2S_IMAGE_STEPS = SJ_S2S_IMAGE_STEPS;
+constexpr uint32_t S2S_IMAGE_BYTES = S2S_IMAGE_STEPS * S2S_STEP_BYTES;
 constexpr uint32_t S2S_SSTAGE_BYTES = S2S_STEP_BYTES + 32;           // compacted string bytes of one step (+ alignment shift)
-constexpr uint32_t S2S_TSTAGE_WORDS = 640;                           // tape words of one step staged in shared memory (denser steps go straight to global memory)
+#ifndef SJ_S2S_TSTAGE_WORDS
+#define SJ_S2S_TSTAGE_WORDS 640
+#endif
+constexpr uint32_t S2S_TSTAGE_WORDS = SJ_S2S_TSTAGE_WORDS;                           // tape words of one step staged in shared memory (denser steps go straight to global memory)
 
 // per-slab aggregate (K2p) / exclusive prefix (K2q).  `trail`: string-buffer bytes behind the last real quote of
 // the slab (all of them if the slab holds no quote) -- scanned with the segmented operator below it gives, for a

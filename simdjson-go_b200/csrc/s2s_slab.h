@@ -132,25 +132,28 @@ SJ_HD void s2s_slab(W& wp, const S2sParams& p, uint32_t slab, const S2sWarpMem& 
     const uint64_t slab_end = slab_start + S2S_SLAB_BYTES < p.len ? slab_start + S2S_SLAB_BYTES : p.len;
     const GlobalReader g{p.msg, p.len};
 
-    // ---- the slab image: 16-byte chunks from global memory, stored XOR-swizzled per step; bytes past the end of the
-    // message read as spaces (find_structural_bits_amd64.s:167) ----
-    for (uint32_t c = lane; c < S2S_SLAB_BYTES / 16; c += 32) {
-        const uint64_t gofs = slab_start + 16ull * c;
-        V16 q{0x20202020u, 0x20202020u, 0x20202020u, 0x20202020u};
-        if (gofs < len16) {
-            q = *reinterpret_cast<const V16*>(p.msg + gofs);
-            if (gofs + 16 > p.len) {  // the chunk that holds the end of the message
-                uint32_t qq[4] = {q.x, q.y, q.z, q.w};
-                for (uint32_t k = 0; k < 16; k++)
-                    if (gofs + k >= p.len) qq[k >> 2] = (qq[k >> 2] & ~(0xffu << (8 * (k & 3)))) | (0x20u << (8 * (k & 3)));
-                q = V16{qq[0], qq[1], qq[2], qq[3]};
+    // ---- the image of the slab (or of one step of it) in shared memory: 16-byte chunks from global memory, stored
+    // XOR-swizzled per step; bytes past the end of the message read as spaces (find_structural_bits_amd64.s:167) ----
+    auto fill_image = [&](uint64_t first, uint32_t nbytes) {
+        for (uint32_t c = lane; c < nbytes / 16; c += 32) {
+            const uint64_t gofs = first + 16ull * c;
+            V16 q{0x20202020u, 0x20202020u, 0x20202020u, 0x20202020u};
+            if (gofs < len16) {
+                q = *reinterpret_cast<const V16*>(p.msg + gofs);
+                if (gofs + 16 > p.len) {  // the chunk that holds the end of the message
+                    uint32_t qq[4] = {q.x, q.y, q.z, q.w};
+                    for (uint32_t k = 0; k < 16; k++)
+                        if (gofs + k >= p.len) qq[k >> 2] = (qq[k >> 2] & ~(0xffu << (8 * (k & 3)))) | (0x20u << (8 * (k & 3)));
+                    q = V16{qq[0], qq[1], qq[2], qq[3]};
+                }
             }
+            const uint32_t o = 16u * c;
+            *reinterpret_cast<V16*>(sm.src + (o & ~(S2S_STEP_BYTES - 1)) + swz(o & (S2S_STEP_BYTES - 1))) = q;
         }
-        const uint32_t o = 16u * c;
-        *reinterpret_cast<V16*>(sm.src + (o & ~(S2S_STEP_BYTES - 1)) + swz(o & (S2S_STEP_BYTES - 1))) = q;
-    }
-    wp.sync();
-    const MsgReader rd{p.msg, p.len, sm.src, slab_start, slab_end};
+        wp.sync();
+    };
+    if (S2S_IMAGE_STEPS == S2S_STEPS) fill_image(slab_start, S2S_SLAB_BYTES);
+    MsgReader rd{p.msg, p.len, sm.src, slab_start, slab_end};
 
     // ---- carries into the slab ----
     // in-string state: from stage 1 (its look-back chain 1 already resolved it for every slab)
@@ -220,7 +223,13 @@ SJ_HD void s2s_slab(W& wp, const S2sParams& p, uint32_t slab, const S2sWarpMem& 
         if (step_start >= p.len) break;  // warp-uniform
         const uint64_t step_end = step_start + S2S_STEP_BYTES;
         const uint64_t block_pos = step_start + 64ull * lane;
-        const uint8_t* sbase = sm.src + s * S2S_STEP_BYTES;
+        if (S2S_IMAGE_STEPS != S2S_STEPS) {  // one step at a time
+            wp.sync();  // (the previous step's readers are done)
+            fill_image(step_start, S2S_STEP_BYTES);
+            rd.slab_start = step_start;
+            rd.slab_end = step_end < p.len ? step_end : p.len;
+        }
+        const uint8_t* sbase = sm.src + (S2S_IMAGE_STEPS == S2S_STEPS ? s * S2S_STEP_BYTES : 0);
 
         // ---------------- A: load + classify ----------------
         uint32_t w[16];
@@ -533,72 +542,89 @@ SJ_HD void s2s_slab(W& wp, const S2sParams& p, uint32_t slab, const S2sWarpMem& 
             }
             if (V & ~m.numc & ~m.atomc) err = 1;  // a value that starts with neither a digit, '-' nor t / f / n
 
-            // ---- emission: one uniform loop per class of event; the tape slot of an event = words of the events below it ----
-            const uint32_t lane_slot = slot0 + w_ex;
+            // ---- emission: one uniform loop per class of event; the tape slot of an event = words of the events below
+            // it.  The block is handled as two 32-bit halves so that every mask operation is a single-register one. ----
             const uint64_t W1 = BRK | ATOM, W2 = closeq | NUM;  // one-word / two-word events
-            // record boundaries (root close + root open: the words themselves are written by K2f)
-            for (uint64_t mm = recst; mm; mm &= mm - 1) {
-                const uint32_t b = pi::ctz64(mm);
-                const uint64_t lo = lt64(b);
-                const uint32_t slot = lane_slot + pi::popc64(W1 & lo) + 2 * (pi::popc64(W2 & lo) + pi::popc64(recst & lo));
-                p.rootpos[run.rec + r_ex + pi::popc64(recst & lo) + 1] = slot + 1;
-            }
-            // brackets: records for the scope matching, the tape word, the grammar verdict of the segment they end
-            {
-                uint64_t prev_mask = 0;  // bits up to and including the previous bracket
-                for (uint64_t mm = BRK; mm; mm &= mm - 1) {
-                    const uint32_t b = pi::ctz64(mm);
-                    const uint64_t lo = lt64(b), upto = lo | (1ull << b);
-                    const uint32_t slot = lane_slot + pi::popc64(W1 & lo) + 2 * (pi::popc64(W2 & lo) + pi::popc64(recst & upto));
-                    const uint32_t kb = run.brk + b_ex + pi::popc64(BRK & lo);
-                    const uint32_t opens_below = pi::popc64((O1 | O2) & lo), closes_below = pi::popc64((C1 | C2) & lo);
-                    const bool curly = (m.curly >> b) & 1ull, opening = (m.open >> b) & 1ull;
-                    p.brk_tp[kb] = slot;
-                    p.brk_depth[kb] = run.depth + d_ex + (int32_t)opens_below - (int32_t)closes_below;
-                    p.brk_kind[kb] = (uint8_t)(opening ? (curly ? T_OBJ_OPEN : T_ARR_OPEN) : (curly ? T_OBJ_CLOSE : T_ARR_CLOSE));
-                    tout[slot] = (uint64_t)((opening ? 0x5bu : 0x5du) | (curly ? 0x20u : 0u)) << 56;  // payload cross-linked after the scope matching
-                    const uint64_t seg = upto & ~prev_mask;
-                    const uint32_t acc = ((BADR & seg) ? 0u : 1u) | ((BADO & seg) ? 0u : 2u) | ((BADA & seg) ? 0u : 4u);
-                    if (acc != 7) wp.atomic_and(p.segmask + (kb >> 2), ~((7u & ~acc) << (8 * (kb & 3))));
-                    prev_mask = upto;
+            const uint64_t OPENS = O1 | O2;
+            const uint32_t lane_str = str_base + k_ex;          // Strings.B offset of the lane's first kept byte
+            uint32_t words_b = slot0 + w_ex;                     // tape slot of the half's first word
+            uint32_t kb_b = run.brk + b_ex, rec_b = run.rec + r_ex, num_b = run.num + n_ex, rank_b = 0;
+            int32_t depth_b = run.depth + d_ex;
+            uint32_t pre_dl = part_lane;                         // bytes the string open at the start of the half has contributed
+            uint32_t segbad = 0;                                 // contexts ruled out since the last bracket (bit 0 root, 1 object, 2 array)
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const uint32_t w1 = (uint32_t)(W1 >> (32 * h)), w2 = (uint32_t)(W2 >> (32 * h)), rs = (uint32_t)(recst >> (32 * h));
+                const uint32_t kk = (uint32_t)(K >> (32 * h)), qq = (uint32_t)(qb >> (32 * h)), cq = (uint32_t)(closeq >> (32 * h));
+                const uint32_t brk = (uint32_t)(BRK >> (32 * h)), opn = (uint32_t)(OPENS >> (32 * h)), cur = (uint32_t)(m.curly >> (32 * h));
+                const uint32_t num = (uint32_t)(NUM >> (32 * h)), atm = (uint32_t)(ATOM >> (32 * h));
+                const uint32_t bdr = (uint32_t)(BADR >> (32 * h)), bdo = (uint32_t)(BADO >> (32 * h)), bda = (uint32_t)(BADA >> (32 * h));
+                const uint64_t half_pos = block_pos + 32 * h;
+                // record boundaries (root close + root open: the words themselves are written by K2f)
+                for (uint32_t mm = rs; mm; mm &= mm - 1) {
+                    const uint32_t lo = (1u << pi::ctz32(mm)) - 1u;
+                    const uint32_t below = pi::popc32(rs & lo);
+                    p.rootpos[rec_b + below + 1] = words_b + pi::popc32(w1 & lo) + 2 * (pi::popc32(w2 & lo) + below) + 1;
                 }
-                const uint64_t seg = ~prev_mask;  // behind the lane's last bracket: the segment goes on in the next lanes
-                const uint32_t acc = ((BADR & seg) ? 0u : 1u) | ((BADO & seg) ? 0u : 2u) | ((BADA & seg) ? 0u : 4u);
-                const uint32_t kb = run.brk + b_ex + n_brk;
-                if (acc != 7) wp.atomic_and(p.segmask + (kb >> 2), ~((7u & ~acc) << (8 * (kb & 3))));
-            }
-            // strings, at their closing quote (stage2...go:72-113)
-            {
-                const uint32_t lane_str = str_base + k_ex;  // Strings.B offset of the lane's first kept byte
-                for (uint64_t mm = closeq; mm; mm &= mm - 1) {
-                    const uint32_t b = pi::ctz64(mm);
-                    const uint64_t lo = lt64(b);
-                    const uint32_t slot = lane_slot + pi::popc64(W1 & lo) + 2 * (pi::popc64(W2 & lo) + pi::popc64(recst & lo));
-                    const uint32_t rank_b = pi::popc64(K & lo);
-                    const uint64_t lower = qb & lo;
-                    const uint32_t dl = lower ? pi::popc64(K & lo & ~lt64(63 - pi::clz64(lower))) : part_lane + rank_b;
-                    tout[slot] = ((uint64_t)'"' << 56) | (STRINGBUFBIT + (uint64_t)(lane_str + rank_b - dl));
+                // brackets: records for the scope matching, the tape word, the grammar verdict of the segment they end
+                {
+                    uint32_t prevm = 0;  // bits up to and including the previous bracket of the half
+                    for (uint32_t mm = brk; mm; mm &= mm - 1) {
+                        const uint32_t j = pi::ctz32(mm), bit = 1u << j, lo = bit - 1u, upto = lo | bit;
+                        const uint32_t slot = words_b + pi::popc32(w1 & lo) + 2 * (pi::popc32(w2 & lo) + pi::popc32(rs & upto));
+                        const uint32_t kb = kb_b + pi::popc32(brk & lo);
+                        const bool curly = (cur & bit) != 0, opening = (opn & bit) != 0;
+                        p.brk_tp[kb] = slot;
+                        p.brk_depth[kb] = depth_b + (int32_t)pi::popc32(opn & lo) - (int32_t)pi::popc32(brk & ~opn & lo);
+                        p.brk_kind[kb] = (uint8_t)(opening ? (curly ? T_OBJ_OPEN : T_ARR_OPEN) : (curly ? T_OBJ_CLOSE : T_ARR_CLOSE));
+                        tout[slot] = (uint64_t)((opening ? 0x5bu : 0x5du) | (curly ? 0x20u : 0u)) << 56;  // payload cross-linked after the scope matching
+                        const uint32_t seg = upto & ~prevm;
+                        const uint32_t bad = segbad | ((bdr & seg) ? 1u : 0u) | ((bdo & seg) ? 2u : 0u) | ((bda & seg) ? 4u : 0u);
+                        if (bad) wp.atomic_and(p.segmask + (kb >> 2), ~(bad << (8 * (kb & 3))));
+                        segbad = 0;
+                        prevm = upto;
+                    }
+                    const uint32_t seg = ~prevm;  // behind the half's last bracket: the segment goes on
+                    segbad |= ((bdr & seg) ? 1u : 0u) | ((bdo & seg) ? 2u : 0u) | ((bda & seg) ? 4u : 0u);
+                }
+                // strings, at their closing quote (stage2...go:72-113)
+                for (uint32_t mm = cq; mm; mm &= mm - 1) {
+                    const uint32_t lo = (1u << pi::ctz32(mm)) - 1u;
+                    const uint32_t slot = words_b + pi::popc32(w1 & lo) + 2 * (pi::popc32(w2 & lo) + pi::popc32(rs & lo));
+                    const uint32_t kbelow = pi::popc32(kk & lo);
+                    const uint32_t lower = qq & lo;  // the opening quote is the highest quote below, if it is in this half
+                    const uint32_t dl = lower ? pi::popc32(kk & lo & ~((1u << (31 - pi::clz32(lower))) - 1u)) : pre_dl + kbelow;
+                    tout[slot] = ((uint64_t)'"' << 56) | (STRINGBUFBIT + (uint64_t)(lane_str + rank_b + kbelow - dl));
                     tout[slot + 1] = dl;
                 }
+                // numbers: parsed by K2h from the list
+                for (uint32_t mm = num; mm; mm &= mm - 1) {
+                    const uint32_t j = pi::ctz32(mm), bit = 1u << j, lo = bit - 1u;
+                    NumEntry ne;
+                    ne.pos = (uint32_t)(half_pos + j);
+                    ne.slot = words_b + pi::popc32(w1 & lo) + 2 * (pi::popc32(w2 & lo) + pi::popc32(rs & (lo | bit)));
+                    p.numlist[num_b + pi::popc32(num & lo)] = ne;
+                }
+                // atoms
+                for (uint32_t mm = atm; mm; mm &= mm - 1) {
+                    const uint32_t j = pi::ctz32(mm), bit = 1u << j, lo = bit - 1u;
+                    const uint32_t slot = words_b + pi::popc32(w1 & lo) + 2 * (pi::popc32(w2 & lo) + pi::popc32(rs & (lo | bit)));
+                    const uint32_t ch = sbase[swz(64 * lane + 32 * h + j)];
+                    if (!atom_ok_p(rd, half_pos + j, p.len, sm.ctab[ch])) err = 1;
+                    tout[slot] = (uint64_t)ch << 56;
+                }
+                // totals of the half
+                const uint32_t nk = pi::popc32(kk), nopn = pi::popc32(opn), nbr = pi::popc32(brk);
+                words_b += pi::popc32(w1) + 2 * (pi::popc32(w2) + pi::popc32(rs));
+                kb_b += nbr;
+                depth_b += (int32_t)nopn - (int32_t)(nbr - nopn);
+                rec_b += pi::popc32(rs);
+                num_b += pi::popc32(num);
+                pre_dl = qq ? pi::popc32(kk & ~((2u << (31 - pi::clz32(qq))) - 1u)) : pre_dl + nk;
+                rank_b += nk;
             }
-            // numbers: parsed by K2h from the list
-            for (uint64_t mm = NUM; mm; mm &= mm - 1) {
-                const uint32_t b = pi::ctz64(mm);
-                const uint64_t lo = lt64(b), upto = lo | (1ull << b);
-                NumEntry ne;
-                ne.pos = (uint32_t)(block_pos + b);
-                ne.slot = lane_slot + pi::popc64(W1 & lo) + 2 * (pi::popc64(W2 & lo) + pi::popc64(recst & upto));
-                p.numlist[run.num + n_ex + pi::popc64(NUM & lo)] = ne;
-            }
-            // atoms
-            for (uint64_t mm = ATOM; mm; mm &= mm - 1) {
-                const uint32_t b = pi::ctz64(mm);
-                const uint64_t lo = lt64(b), upto = lo | (1ull << b);
-                const uint32_t slot = lane_slot + pi::popc64(W1 & lo) + 2 * (pi::popc64(W2 & lo) + pi::popc64(recst & upto));
-                const uint32_t ch = sbase[swz(64 * lane + b)];
-                if (!atom_ok_p(rd, block_pos + b, p.len, sm.ctab[ch])) err = 1;
-                tout[slot] = (uint64_t)ch << 56;
-            }
+            // the segment behind the lane's last bracket goes on in the next lanes
+            if (segbad) wp.atomic_and(p.segmask + (kb_b >> 2), ~(segbad << (8 * (kb_b & 3))));
         }
         if (staged) {
             wp.sync();

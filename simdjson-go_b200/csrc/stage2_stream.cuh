@@ -34,8 +34,8 @@ static_assert(S1_WARPS <= 32, "one bit per slab of a tile");
 constexpr int S2S_WARPS = SJ_S2S_WARPS;  // slabs per CTA
 constexpr int S2S_THREADS = S2S_WARPS * 32;
 constexpr uint32_t S2S_SSTAGE_PAD = (S2S_SSTAGE_BYTES + 15u) & ~15u;
-constexpr uint32_t S2S_WARP_SMEM_COUNT = S2S_SLAB_BYTES;
-constexpr uint32_t S2S_WARP_SMEM_EMIT = S2S_SLAB_BYTES + S2S_SSTAGE_PAD + S2S_TSTAGE_WORDS * 8;
+constexpr uint32_t S2S_WARP_SMEM_COUNT = S2S_IMAGE_BYTES;
+constexpr uint32_t S2S_WARP_SMEM_EMIT = S2S_IMAGE_BYTES + S2S_SSTAGE_PAD + S2S_TSTAGE_WORDS * 8;
 constexpr size_t S2S_SMEM_COUNT = (size_t)S2S_WARPS * S2S_WARP_SMEM_COUNT;
 constexpr size_t S2S_SMEM_EMIT = (size_t)S2S_WARPS * S2S_WARP_SMEM_EMIT;
 #ifndef SJ_S2S_EMIT_MIN_BLOCKS
@@ -105,8 +105,8 @@ __global__ void __launch_bounds__(S2S_THREADS, SJ_S2S_EMIT_MIN_BLOCKS) s2s_emit_
     S2sWarpMem sm;
     uint8_t* base = s2s_smem + (size_t)warp * S2S_WARP_SMEM_EMIT;
     sm.src = base;
-    sm.sstage = base + S2S_SLAB_BYTES;
-    sm.tstage = reinterpret_cast<uint64_t*>(base + S2S_SLAB_BYTES + S2S_SSTAGE_PAD);
+    sm.sstage = base + S2S_IMAGE_BYTES;
+    sm.tstage = reinterpret_cast<uint64_t*>(base + S2S_IMAGE_BYTES + S2S_SSTAGE_PAD);
     sm.ctab = tabs.ctab;
     sm.oktab = tabs.oktab;
     sm.cmptab = tabs.cmptab;

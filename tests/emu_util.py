@@ -7,7 +7,8 @@ import numpy as np
 
 _DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu")
 _SRC = os.path.join(_DIR, "s2s_emu.cpp")
-_LIB = os.path.join(_DIR, "libs2semu.so")
+_FLAGS = os.environ.get("S2S_EMU_FLAGS", "").split()  # e.g. -DSJ_S2S_IMAGE_STEPS=1: the other shared-memory layout
+_LIB = os.path.join(_DIR, "libs2semu%s.so" % ("_" + "_".join(f.strip("-").replace("=", "") for f in _FLAGS) if _FLAGS else ""))
 _CSRC = os.path.join(os.path.dirname(_DIR), "..", "simdjson-go_b200", "csrc")
 _lib = None
 
@@ -15,7 +16,7 @@ _lib = None
 def build(force=False):
     deps = [_SRC] + [os.path.join(_CSRC, f) for f in ("s2s_core.h", "s2s_slab.h")]
     if force or not os.path.exists(_LIB) or any(os.path.getmtime(d) > os.path.getmtime(_LIB) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-shared", "-fPIC", "-Wall", "-Wno-unknown-pragmas", "-o", _LIB, _SRC])
+        subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-shared", "-fPIC", "-Wall", "-Wno-unknown-pragmas"] + _FLAGS + ["-o", _LIB, _SRC])
 
 
 def lib():
