@@ -243,6 +243,9 @@ def main():
 
     ctx = sj.Context(local_rank)
     L = ctx.L
+    # host threads and pinned buffers of this rank on the NUMA node its GPU hangs off (the e2e leg moves 1.8 GB per step
+    # through them; with 8 ranks on two sockets the remote half would cross the socket link)
+    numa_node = L.sj_bind_to_device_numa(local_rank)
     batch = make_batch(args.batch_mib << 20)
     n = len(batch)
     flags = _lib.FLAG_NDJSON | _lib.FLAG_COPY_STRINGS
@@ -262,10 +265,32 @@ def main():
     d_strings = torch.empty(string_bytes + 64, dtype=torch.uint8, device=dev)
     tl, sl = C.c_size_t(0), C.c_size_t(0)
 
+    # N > 1: every rank's batch is one shard of ONE NDJSON stream (shards joined by a newline) and the N tapes are the
+    # slices of ONE ParsedJson (simdjson_amd64.go:82-93): counting half -> all-gather of the shard totals + exclusive
+    # prefix, enqueued on the same stream (no host round trip) -> emitting half with the bases read from device memory
+    if world > 1:
+        from simdjson_b200.parallel import ShardedParse
+        L.sj_ctx_set_stream(ctx.h, torch.cuda.current_stream().cuda_stream)
+        sp = ShardedParse(ctx)
+        my_tot = torch.zeros(4, dtype=torch.int64, device=dev)
+        all_tot = torch.zeros(world * 4, dtype=torch.int64, device=dev)
+        bases = torch.zeros(3, dtype=torch.int64, device=dev)
+        sep = torch.tensor([rank, 0, 0], dtype=torch.int64, device=dev)  # one '\n' between consecutive shards of the message
+
     def step_device():
-        r = L.sj_parse_device(ctx.h, d_msg.data_ptr(), n, flags, d_tape.data_ptr(), d_tape.numel(), C.byref(tl),
-                              d_strings.data_ptr(), d_strings.numel(), C.byref(sl))
+        if world == 1:
+            r = L.sj_parse_device(ctx.h, d_msg.data_ptr(), n, flags, d_tape.data_ptr(), d_tape.numel(), C.byref(tl),
+                                  d_strings.data_ptr(), d_strings.numel(), C.byref(sl))
+            assert r == 0, r
+            return
+        r, tot = sp.count(d_msg.data_ptr(), n, True, my_tot.data_ptr())
         assert r == 0, r
+        dist.all_gather_into_tensor(all_tot, my_tot)          # 4 integers per rank: the path's only exchange
+        torch.sum(all_tot.view(world, 4)[:rank, :3], dim=0, out=bases)
+        bases.add_(sep)
+        r = sp.emit(0, 0, 0, d_tape.data_ptr(), d_tape.numel(), d_strings.data_ptr(), d_strings.numel(), bases.data_ptr())
+        assert r == 0, r
+        tl.value, sl.value = tot[1], tot[2]
 
     def barrier():
         torch.cuda.synchronize()
@@ -280,21 +305,9 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    def exchange_totals():
-        """the only data-path collective: 3 x uint64 per rank (shard bytes, tape words, string bytes)
-        -> exclusive prefix = where this shard's tape / strings / message would be rebased to"""
-        if world == 1:
-            return (0, 0, 0)
-        mine = torch.tensor([n, tl.value, sl.value], dtype=torch.int64, device=dev)
-        allv = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(allv, mine)
-        base = torch.stack(allv[:rank]).sum(0) if rank else torch.zeros_like(mine)
-        return tuple(int(x) for x in base.tolist())
-
     # ---- value: device resident ----
     for _ in range(args.warmup):
         step_device()
-        exchange_totals()  # the collective is part of a step: warm its communicator up too
     ms = C.c_float(0)
     launches0 = ctx.launches()
     sampler = ClockSampler(local_rank)
@@ -303,13 +316,18 @@ def main():
     L.sj_event_record(ctx.h, 0)
     for _ in range(args.steps):
         step_device()
-        exchange_totals()
     L.sj_event_record(ctx.h, 1)
     L.sj_event_elapsed_ms(ctx.h, C.byref(ms))
     barrier()
     launches = ctx.launches() - launches0
     t_dev = reduce_max(ms.value / 1e3)
     assert tl.value == tape_words and sl.value == string_bytes
+    if world > 1:
+        # the slice is rebased: its first word is this shard's first root, chained to the next one in WHOLE-tape indices
+        b_host = [int(x) for x in bases.tolist()]
+        first = int(d_tape[0].item()) & ((1 << 56) - 1)
+        assert b_host[1] == rank * tape_words and first == b_host[1] + (int(tape_h[0]) & ((1 << 56) - 1)), (b_host, first)
+        L.sj_ctx_set_stream(ctx.h, None)
 
     # ---- roofline: stage1_flatten alone on the same batch ----
     info = sj.Stage1Info()
@@ -376,16 +394,18 @@ def main():
         workers.append({"ctx": wctx, "tape": torch.empty(tape_words + 64, dtype=torch.int64).pin_memory(),
                         "strings": torch.empty(string_bytes + 64, dtype=torch.uint8).pin_memory()})
 
-    def step_host(w):
+    def step_host(w, fl=flags, want_strings=None):
         tl2, sl2, mo, ml = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0), C.c_size_t(0)
-        r = L.sj_parse(w["ctx"].h, h_in.data_ptr(), n, flags, w["tape"].data_ptr(), w["tape"].numel(), C.byref(tl2),
+        r = L.sj_parse(w["ctx"].h, h_in.data_ptr(), n, fl, w["tape"].data_ptr(), w["tape"].numel(), C.byref(tl2),
                        w["strings"].data_ptr(), w["strings"].numel(), C.byref(sl2), C.byref(mo), C.byref(ml))
         assert r == 0 and tl2.value == tape_words, r
+        if want_strings is not None:
+            assert sl2.value == want_strings, sl2.value
 
-    def run_host_steps(count):
+    def run_host_steps(count, fl=flags, want_strings=None):
         from concurrent.futures import ThreadPoolExecutor
         with ThreadPoolExecutor(max_workers=len(workers)) as ex:
-            futs = [ex.submit(lambda k=k: [step_host(workers[k]) for _ in range(k, count, len(workers))])
+            futs = [ex.submit(lambda k=k: [step_host(workers[k], fl, want_strings) for _ in range(k, count, len(workers))])
                     for k in range(len(workers))]
             for f in futs:
                 f.result()
@@ -399,6 +419,19 @@ def main():
     barrier()
     for w in workers[: min(len(workers), args.steps)]:
         assert np.array_equal(w["tape"][:tape_words].numpy().view(np.uint64), tape_h)
+
+    # the same call with WithCopyStrings(false) (options.go:13): strings stay in the message unless they hold escapes, so
+    # only the tape travels back (this stream has no escapes: Strings.B is empty)
+    fl_nc = _lib.FLAG_NDJSON
+    rc_nc, tape_nc, strings_nc, _ = ctx.parse(np.frombuffer(batch, dtype=np.uint8), ndjson=True, copy_strings=False)
+    assert rc_nc == 0 and len(tape_nc) == tape_words
+    run_host_steps(max(args.warmup, len(workers)), fl_nc, len(strings_nc))
+    barrier()
+    t0 = time.perf_counter()
+    run_host_steps(args.steps, fl_nc, len(strings_nc))
+    torch.cuda.synchronize()
+    t_e2e_nc = reduce_max(time.perf_counter() - t0)
+    barrier()
 
     # ---- tape consumer on the device: parseMessage + countWhere("Make", "HOND"), the reference's
     # BenchmarkNdjsonColdCountStarWithWhere (parse_json_amd64_test.go:134): host input, only two counts come back ----
@@ -464,17 +497,21 @@ def main():
             "config": {"workload": WORKLOAD,
                        "batch_bytes_per_gpu": n, "records_per_batch": batch.count(b"\n") + 1, "tape_words": tape_words,
                        "string_bytes": string_bytes, "inputs_larger_than_l2": True, "parallelism": "ndjson-shard x%d" % world,
-                       "collective": "all_gather of 3 x int64 per rank per step (shard offsets)" if world > 1 else "none"},
+                       "collective": "all_gather of 4 x int64 per rank per step (shard totals -> bases of ONE ParsedJson), enqueued on the parse's stream between sj_parse_nd_sharded_count and _emit" if world > 1 else "none",
+                       "numa_node_bound": int(numa_node)},
             "e2e": {"value": round(total_bytes / t_e2e / 1e9, 3), "unit": "GB/s", "h2d_bytes_per_step": n,
                     "d2h_bytes_per_step": tape_words * 8 + string_bytes, "ms_per_step": round(t_e2e / args.steps * 1e3, 3),
                     "calls_in_flight": len(workers), "timer": "host wall clock around the in-flight calls, device synchronised on both sides"},
+            "e2e_nocopy": {"value": round(total_bytes / t_e2e_nc / 1e9, 3), "unit": "GB/s", "h2d_bytes_per_step": n,
+                           "d2h_bytes_per_step": tape_words * 8 + len(strings_nc), "ms_per_step": round(t_e2e_nc / args.steps * 1e3, 3),
+                           "what": "the same sj_parse calls with WithCopyStrings(false) (options.go:13): the tape alone travels back"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "stage1_flatten_kernel<ndjson>", "achieved": round(achieved, 2), "peak": peak,
                          "unit": "GB/s", "frac": round(achieved / peak, 4), "peak_kind": peak_kind, "traffic": k1_traffic(n),
                          "traffic_kind": "static: dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full capture of this command (profiles/k1_traffic.json), not measured in this run",
                          "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": round(t_s1 * 1e3, 4),
                          "input_read_gbs": round(n / t_s1 / 1e9, 2)},
-            "roofline_parse": {"bound": "hbm", "what": "whole device-resident step (K1 + K2a-f), algorithmic bytes 2*N_in + 8*N_idx + 8*N_tape + N_strings (SURVEY.md 8d)",
+            "roofline_parse": {"bound": "hbm", "what": "whole device-resident step (K1 + K2p/q/r + numbers, scope matching, links, roots), algorithmic bytes 2*N_in + 8*N_idx + 8*N_tape + N_strings (SURVEY.md 8d)",
                                "achieved": round((2 * n + 8 * int(info.n_idx) + 8 * tape_words + string_bytes) * world * args.steps / t_dev / 1e9, 2),
                                "peak": peak, "unit": "GB/s",
                                "frac": round((2 * n + 8 * int(info.n_idx) + 8 * tape_words + string_bytes) * args.steps / t_dev / 1e9 / peak, 4)},

@@ -63,6 +63,11 @@ void sj_ctx_destroy(sj_ctx* ctx);
  * older implementation, kept as the copy_strings = false path and as a second implementation the tests compare with. */
 int sj_ctx_set_stage2_impl(sj_ctx* ctx, int impl);
 
+/* Host side of a rank: bind the calling thread (and its future children) to the CPUs of the NUMA node `device` hangs
+ * off and prefer that node for memory, so that pinned buffers allocated afterwards sit next to the GPU.  Returns the
+ * node, or -1 when the topology is not exposed / nothing was changed. */
+int sj_bind_to_device_numa(int device);
+
 /* pinned host memory for callers that want full PCIe speed (optional) */
 void* sj_host_alloc(size_t bytes);
 void sj_host_free(void* p);
@@ -95,6 +100,40 @@ int sj_parse(sj_ctx* ctx, const uint8_t* msg, size_t len, uint32_t flags, uint64
  */
 int sj_parse_device(sj_ctx* ctx, const uint8_t* d_msg, size_t len, uint32_t flags, uint64_t* d_tape, size_t tape_cap,
                     size_t* tape_len, uint8_t* d_strings, size_t strings_cap, size_t* strings_len);
+
+/*
+ * ParseND sharded over several GPUs (one process per GPU).  ParseND returns ONE ParsedJson
+ * whose roots are chained through the whole tape (simdjson_amd64.go:82-93, stage2_build_tape_amd64.go:190-221).
+ * Every rank parses a shard of the stream that was cut at record boundaries (every raw '\n' of a valid stream is one:
+ * find_quote_mask_and_bits_amd64.s:69-80 rejects control characters inside strings) and passes it TRIMMED, device
+ * resident, like sj_parse_device.
+ *   1. sj_parse_nd_sharded_count: stage 1 + the counting half of stage 2 on the shard; *totals = its contribution.
+ *   2. the ranks exchange the totals (one all-gather of four integers per rank -- NCCL in the caller) and take the
+ *      exclusive prefix: msg_base (offset of the shard's trimmed window inside the whole trimmed message; only no-copy
+ *      strings use it), tape_base, strings_base.
+ *   3. sj_parse_nd_sharded_emit: the emitting half writes the shard's slice of the whole tape / Strings.B into
+ *      d_tape[0 .. tape_words) / d_strings[0 .. string_bytes) with every root / scope pointer and string offset
+ *      already shifted by the bases: the slices of all ranks, laid end to end, ARE the reference's ParsedJson
+ *      (there is no separate rebasing pass over the tape).
+ * With one rank and all bases 0 the pair is sj_parse_device.
+ */
+typedef struct {
+    uint64_t msg_bytes;     /* length of the shard as passed in */
+    uint64_t tape_words;
+    uint64_t string_bytes;
+    uint64_t records;       /* roots in the shard */
+} sj_shard_totals;
+/* d_totals (optional): device memory for the same four integers, written on the context's stream.
+ * d_bases (optional): device memory holding { msg_base, tape_base, strings_base }, read by the emitting kernels instead of
+ * the three scalar arguments.  With both, and the context running on the caller's stream (sj_ctx_set_stream), the
+ * exchange (all-gather + prefix) is enqueued on that stream between the two calls and costs no host round trip. */
+int sj_parse_nd_sharded_count(sj_ctx* ctx, const uint8_t* d_msg, size_t len, uint32_t flags, sj_shard_totals* totals,
+                              uint64_t* d_totals);
+int sj_parse_nd_sharded_emit(sj_ctx* ctx, uint64_t msg_base, uint64_t tape_base, uint64_t strings_base, const uint64_t* d_bases,
+                             uint64_t* d_tape, size_t tape_cap, uint8_t* d_strings, size_t strings_cap);
+/* Run this context's work on the caller's CUDA stream (a cudaStream_t passed as void*; NULL: back to the context's own
+ * stream).  For callers that order the parse against their own kernels / collectives without host synchronisation. */
+int sj_ctx_set_stream(sj_ctx* ctx, void* cuda_stream);
 
 /*
  * Device-side tape consumers: the reference's NDJSON workloads walk

@@ -40,7 +40,8 @@ struct sj_ctx {
     int device = 0;
     int sm_count = 0;
     int s1_max_ctas = 0;  // co-resident CTAs of the stage-1 kernel (cooperative launch bound)
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;      // the stream the work runs on
+    cudaStream_t own_stream = nullptr;  // the context's own one (sj_ctx_set_stream may point `stream` elsewhere)
     cudaEvent_t ev[2] = {nullptr, nullptr};
     uint64_t launches = 0;
     // stage 1
@@ -51,6 +52,7 @@ struct sj_ctx {
     DevBuf result;   // Stage1Result + Stage2Result
     void* host_result = nullptr;  // pinned mirror
     // stage 2
+    void* pending = nullptr;  // S2Pending (sj_parse.inl): state between the counting and the emitting half of stage 2
     int s2_impl = 0;  // stage 2: 0 = streaming kernels (stage2_stream.cuh) when copy_strings is on, 1 = per-structural kernels (stage2.cuh) always
     DevBuf s2a, s2b, s2c, s2d, s2e, s2f, s2g;  // s2a/s2b: stage-2 scratch (before / after the totals are known), s2c: backslash block map
     DevBuf tape, strings;  // device outputs for the host-buffer API

@@ -558,7 +558,15 @@ struct S2sParams {
     uint32_t* rootpos;        // [records + 1] tape slot of each record's root-open word
     NumEntry* numlist;        // [numbers] in document order
     uint32_t* error;          // any stage-2 failure
+    // NDJSON shards of ONE ParsedJson (simdjson_amd64.go:82-93): this parse's tape / Strings.B are the slices that
+    // start at these offsets of the whole, so every index written INTO the tape is shifted by them
+    // (root / scope pointers by tape_base, string offsets by str_base); both 0 for a stand-alone parse
+    uint64_t tape_base, str_base;
+    const uint64_t* bases_dev;  // optional: { msg_base, tape_base, str_base } in device memory (written by the ranks' exchange
+                                // on the same stream, so no host round trip sits between the two halves); overrides the two above
 };
+SJ_HD uint64_t s2s_tape_base(const S2sParams& p) { return p.bases_dev ? p.bases_dev[1] : p.tape_base; }
+SJ_HD uint64_t s2s_str_base(const S2sParams& p) { return p.bases_dev ? p.bases_dev[2] : p.str_base; }
 
 // per-warp working memory (shared memory on the device)
 struct S2sWarpMem {

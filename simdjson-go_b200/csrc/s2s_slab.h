@@ -152,12 +152,27 @@ SJ_HD void s2s_slab(W& wp, const S2sParams& p, uint32_t slab, const S2sWarpMem& 
         }
         wp.sync();
     };
+    // what the slab needs from global memory besides its own bytes is asked for first, so that these (dependent)
+    // loads are in flight under the image fill
+    uint32_t par = (p.slabpar[slab / p.slabs_per_tile] >> (slab % p.slabs_per_tile)) & 1u;  // in-string state in front of the slab (stage 1's chain 1)
+    SlabAgg run = agg_zero();
+    const uint64_t out_str_base = EMIT ? s2s_str_base(p) : 0;  // offset of this parse's Strings.B inside the whole (sharded ParseND)
+    uint32_t pc1 = 0, pc2 = 0;   // K2r: the bytes under the last two events in front of the slab (0: none)
+    bool have1 = false, have2 = false;
+    if (EMIT) {
+        run = agg_combine(p.grp_pre[slab >> 10], p.pre[slab]);
+        // from stage 1's index: inside a string the last structural is that string's opening quote, whose event
+        // (the closing quote) is still to come
+        const uint32_t r = run.ns, back = par ? 2u : 1u;
+        have1 = r >= back, have2 = r >= back + 1;
+        const uint32_t i1 = have1 ? p.idx[r - back] : 0u, i2 = have2 ? p.idx[r - back - 1] : 0u;
+        pc1 = have1 ? g(i1) : 0u;
+        pc2 = have2 ? g(i2) : 0u;
+    }
     if (S2S_IMAGE_STEPS == S2S_STEPS) fill_image(slab_start, S2S_SLAB_BYTES);
     MsgReader rd{p.msg, p.len, sm.src, slab_start, slab_end};
 
     // ---- carries into the slab ----
-    // in-string state: from stage 1 (its look-back chain 1 already resolved it for every slab)
-    uint32_t par = (p.slabpar[slab / p.slabs_per_tile] >> (slab % p.slabs_per_tile)) & 1u;
     // lane L: the byte at slab_start - 1 - L
     const uint32_t peekc = slab_start > lane ? g(slab_start - 1 - lane) : 0x20u;
     const uint32_t peek_bs = wp.ballot(peekc == '\\');
@@ -198,22 +213,14 @@ SJ_HD void s2s_slab(W& wp, const S2sParams& p, uint32_t slab, const S2sWarpMem& 
     }
 
     // ---- running totals of the slab (K2p) / running prefixes (K2r) ----
-    SlabAgg run = agg_zero();
     uint32_t trail = 0, hasq = 0;  // K2p: bytes behind the last quote so far
     uint32_t partial = 0;          // K2r: bytes the string that is open at the step start has contributed so far
     uint32_t pr = T_START;         // K2r: refined type of the last event in front of the step
     uint32_t err = 0;
     if (EMIT) {
-        run = agg_combine(p.grp_pre[slab >> 10], p.pre[slab]);
         partial = run.trail & ~TRAIL_HASQ;
-        // the last event in front of the slab, from stage 1's index: inside a string the last structural is that
-        // string's opening quote, whose event (the closing quote) is still to come
-        const uint32_t r = run.ns;
-        const uint32_t back = par ? 2u : 1u;
-        if (r >= back) {
-            const uint32_t t = sm.ctab[g(p.idx[r - back])];
-            uint32_t tp = T_START;
-            if (r >= back + 1) tp = sm.ctab[g(p.idx[r - back - 1])];
+        if (have1) {
+            const uint32_t t = sm.ctab[pc1], tp = have2 ? (uint32_t)sm.ctab[pc2] : (uint32_t)T_START;
             pr = (t == T_STRING && (tp == T_OBJ_OPEN || tp == T_COMMA)) ? (uint32_t)T_STRING_KEYPOS : t;
         }
     }
@@ -594,7 +601,7 @@ SJ_HD void s2s_slab(W& wp, const S2sParams& p, uint32_t slab, const S2sWarpMem& 
                     const uint32_t kbelow = pi::popc32(kk & lo);
                     const uint32_t lower = qq & lo;  // the opening quote is the highest quote below, if it is in this half
                     const uint32_t dl = lower ? pi::popc32(kk & lo & ~((1u << (31 - pi::clz32(lower))) - 1u)) : pre_dl + kbelow;
-                    tout[slot] = ((uint64_t)'"' << 56) | (STRINGBUFBIT + (uint64_t)(lane_str + rank_b + kbelow - dl));
+                    tout[slot] = ((uint64_t)'"' << 56) | (STRINGBUFBIT + out_str_base + (uint64_t)(lane_str + rank_b + kbelow - dl));
                     tout[slot + 1] = dl;
                 }
                 // numbers: parsed by K2h from the list

@@ -5,8 +5,13 @@
 // sm_100a kernels of stage1.cuh / stage2.cuh.  There is NO CPU fallback: without a CUDA
 // device every entry point returns SJ_ERR_NO_DEVICE.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
+
+#include <sched.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 #include "../../include/simdjson_b200.h"
 #include "context.cuh"
@@ -151,7 +156,8 @@ extern "C" int sj_ctx_create(int device, sj_ctx** out) {
     }
     // every failure below leaves through sj_ctx_destroy (stream, events, pinned result block, device scratch)
     const int rc = [&]() -> int {
-        SJ_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        SJ_CUDA_CHECK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+        c->stream = c->own_stream;
         SJ_CUDA_CHECK(cudaEventCreate(&c->ev[0]));
         SJ_CUDA_CHECK(cudaEventCreate(&c->ev[1]));
         SJ_CUDA_CHECK(cudaHostAlloc(&c->host_result, 256, cudaHostAllocDefault));
@@ -192,9 +198,10 @@ extern "C" void sj_ctx_destroy(sj_ctx* c) {
                       &c->tc_small, &c->tc_roots};
     for (DevBuf* b : bufs) b->release();
     if (c->host_result) cudaFreeHost(c->host_result);
+    free(c->pending);
     if (c->ev[0]) cudaEventDestroy(c->ev[0]);
     if (c->ev[1]) cudaEventDestroy(c->ev[1]);
-    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
 
@@ -203,6 +210,68 @@ extern "C" void sj_ctx_destroy(sj_ctx* c) {
 extern "C" int sj_ctx_set_stage2_impl(sj_ctx* c, int impl) {
     if (!c || impl < 0 || impl > 1) return SJ_ERR_ARGUMENT;
     c->s2_impl = impl;
+    return SJ_OK;
+}
+
+// Host side of a rank: run the calling thread (and the threads it starts later) on the CPUs of the NUMA node the device
+// hangs off, and prefer that node for its memory -- pinned staging buffers allocated afterwards (cudaHostAlloc,
+// sj_host_alloc, the stream slots) then sit next to the GPU's PCIe root instead of across the socket link.  Reads
+// /sys/bus/pci/devices/<bus id>/numa_node and /sys/devices/system/node/node<k>/cpulist; returns the node, or -1 when
+// the topology is not exposed (single-node hosts, containers without sysfs) -- never an error.
+extern "C" int sj_bind_to_device_numa(int device) {
+    char bus[64] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    for (char* q = bus; *q; q++)
+        if (*q >= 'A' && *q <= 'Z') *q = (char)(*q - 'A' + 'a');
+    char path[256];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE* f = fopen(path, "r");
+    if (!f) return -1;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    if (node < 0) return -1;
+    snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+    f = fopen(path, "r");
+    if (!f) return -1;
+    char list[4096] = {0};
+    const size_t got = fread(list, 1, sizeof list - 1, f);
+    fclose(f);
+    list[got] = 0;
+    cpu_set_t allowed, want;
+    CPU_ZERO(&want);
+    if (sched_getaffinity(0, sizeof allowed, &allowed) != 0) return -1;
+    int any = 0;
+    for (char* tok = strtok(list, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+        int a = 0, b = 0;
+        const int k = sscanf(tok, "%d-%d", &a, &b);
+        if (k < 1) continue;
+        if (k == 1) b = a;
+        for (int cpu = a; cpu <= b && cpu < CPU_SETSIZE; cpu++)
+            if (CPU_ISSET(cpu, &allowed)) {
+                CPU_SET(cpu, &want);
+                any = 1;
+            }
+    }
+    if (!any) return -1;  // the node's CPUs are outside this process's cpuset: leave everything as it is
+    sched_setaffinity(0, sizeof want, &want);
+#ifdef SYS_set_mempolicy
+    if (node < 64) {
+        unsigned long mask = 1ul << node;
+        syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, &mask, sizeof(mask) * 8 + 1);
+    }
+#endif
+    return node;
+}
+
+extern "C" int sj_ctx_set_stream(sj_ctx* c, void* cuda_stream) {
+    if (!c) return SJ_ERR_ARGUMENT;
+    SJ_CUDA_CHECK(cudaSetDevice(c->device));
+    SJ_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    c->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : c->own_stream;
     return SJ_OK;
 }
 

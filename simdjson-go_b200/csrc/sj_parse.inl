@@ -142,9 +142,31 @@ struct Carver {  // sub-allocates one DevBuf
 // ---------------------------------------------------------------------------------
 static int stage2_verdict(const Stage2Result& r);
 
-static int run_stage2(sj_ctx* c, const uint8_t* d_msg, size_t len, const uint32_t* d_idx, uint32_t n, uint32_t flags,
-                      uint64_t* d_tape, size_t tape_cap, uint8_t* d_strings, size_t strings_cap, Stage2Result* out,
-                      const uint32_t* d_bsmap) {
+// what the counting half of stage 2 leaves for the emitting half (between them the totals are on the host: output
+// buffers are sized, and the shards of a multi-GPU ParseND exchange their totals)
+struct S2Pending {
+    bool valid, stream;
+    Stage2Result tot;
+    Stage2Params lp;   // per-structural kernels
+    S2sParams sp;      // streaming kernels
+};
+static S2Pending* pending_of(sj_ctx* c) {
+    if (!c->pending) {
+        c->pending = calloc(1, sizeof(S2Pending));
+    }
+    return reinterpret_cast<S2Pending*>(c->pending);
+}
+struct ParseBases {
+    uint64_t msg, tape, str;
+    const uint64_t* dev;  // or: the three of them in device memory
+};
+
+// per-structural kernels, counting half: K2a classify / measure, K2b scans, totals to the host
+static int legacy_count(sj_ctx* c, const uint8_t* d_msg, size_t len, const uint32_t* d_idx, uint32_t n, uint32_t flags,
+                        const uint32_t* d_bsmap, Stage2Result* out, uint64_t* d_totals = nullptr) {
+    S2Pending* pd = pending_of(c);
+    if (!pd) return SJ_ERR_ARGUMENT;
+    pd->valid = false;
     const uint32_t ntiles = (n + S2_TILE - 1) / S2_TILE;
     const uint32_t ngroups = (ntiles + 1023) / 1024;
     c->last_tape = nullptr;  // the device-side results of the previous parse are about to be overwritten
@@ -179,14 +201,38 @@ static int run_stage2(sj_ctx* c, const uint8_t* d_msg, size_t len, const uint32_
 
     s2_classify_measure_kernel<<<ntiles, S2_THREADS, 0, c->stream>>>(p);
     s2_scan_groups_kernel<<<ngroups, 1024, 0, c->stream>>>(p.tile_sum, ntiles, p.tile_pre, p.grp_sum);
-    s2_scan_top_kernel<<<1, 1024, 0, c->stream>>>(p.grp_sum, ngroups, p.grp_pre, d_res);
+    s2_scan_top_kernel<<<1, 1024, 0, c->stream>>>(p.grp_sum, ngroups, p.grp_pre, d_res, d_totals, (uint64_t)len);
     c->launches += 3;
     SJ_CUDA_CHECK(cudaGetLastError());
     Stage2Result* h_res = reinterpret_cast<Stage2Result*>(reinterpret_cast<uint8_t*>(c->host_result) + 64);
     SJ_CUDA_CHECK(cudaMemcpyAsync(h_res, d_res, sizeof(Stage2Result), cudaMemcpyDeviceToHost, c->stream));
     SJ_CUDA_CHECK(cudaStreamSynchronize(c->stream));
-    Stage2Result tot = *h_res;
-    *out = tot;
+    pd->tot = *h_res;
+    pd->lp = p;
+    pd->stream = false;
+    pd->valid = true;
+    *out = pd->tot;
+    return SJ_OK;
+}
+
+// per-structural kernels, emitting half
+static int legacy_emit(sj_ctx* c, uint64_t* d_tape, size_t tape_cap, uint8_t* d_strings, size_t strings_cap, const ParseBases& bases,
+                       Stage2Result* out) {
+    S2Pending* pd = pending_of(c);
+    if (!pd || !pd->valid || pd->stream) return SJ_ERR_ARGUMENT;
+    pd->valid = false;
+    Stage2Params p = pd->lp;
+    const Stage2Result tot = pd->tot;
+    const uint32_t n = p.n, ntiles = p.ntiles;
+    const uint8_t* d_msg = p.msg;
+    Stage2Result* d_res = p.result;
+    Stage2Result* h_res = reinterpret_cast<Stage2Result*>(reinterpret_cast<uint8_t*>(c->host_result) + 64);
+    int rc;
+    p.tape_base = bases.tape;
+    p.str_base = bases.str;
+    p.bases_dev = bases.dev;
+    p.msg_base = bases.msg;
+    p.bases_dev = bases.dev;
 
     // ---- outputs ----
     if (!d_tape) {
@@ -276,7 +322,7 @@ static int run_stage2(sj_ctx* c, const uint8_t* d_msg, size_t len, const uint32_
     SJ_CUDA_CHECK(cudaMemcpyAsync(h_res, d_res, sizeof(Stage2Result), cudaMemcpyDeviceToHost, c->stream));
     SJ_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     *out = *h_res;
-    if (stage2_verdict(*out) == SJ_OK) {  // what the tape consumers (sj_consume.inl) may read until the next call
+    if (stage2_verdict(*out) == SJ_OK && bases.tape == 0 && !bases.dev) {  // what the tape consumers (sj_consume.inl) may read until the next call
         c->last_rootpos = p.rootpos;
         c->last_records = tot.n_records;
         c->last_tape = d_tape;
@@ -325,8 +371,11 @@ static inline bool use_stream_stage2(const sj_ctx* c, uint32_t flags) {
 // stage 2, streaming kernels (stage2_stream.cuh): K2p count -> K2q scan -> [totals to the host] -> K2r emit ->
 // K2h numbers, K2d scope matching, K2e links + grammar verdict, K2f roots.  copy_strings only (options.go:13 default).
 // ---------------------------------------------------------------------------------
-static int run_stage2_stream(sj_ctx* c, const uint8_t* d_msg, size_t len, const uint32_t* d_idx, uint32_t n, uint32_t flags,
-                             uint64_t* d_tape, size_t tape_cap, uint8_t* d_strings, size_t strings_cap, Stage2Result* out) {
+static int stream_count(sj_ctx* c, const uint8_t* d_msg, size_t len, const uint32_t* d_idx, uint32_t n, uint32_t flags, Stage2Result* out,
+                        uint64_t* d_totals = nullptr) {
+    S2Pending* pd = pending_of(c);
+    if (!pd) return SJ_ERR_ARGUMENT;
+    pd->valid = false;
     const uint32_t nslabs = (uint32_t)((len + S2S_SLAB_BYTES - 1) / S2S_SLAB_BYTES);
     const uint32_t ngroups = (nslabs + 1023) / 1024;
     c->last_tape = nullptr;
@@ -358,14 +407,36 @@ static int run_stage2_stream(sj_ctx* c, const uint8_t* d_msg, size_t len, const 
     const unsigned grid = (nslabs + S2S_WARPS - 1) / S2S_WARPS;
     s2s_count_kernel<<<grid, S2S_THREADS, S2S_SMEM_COUNT, c->stream>>>(p);
     s2s_scan_groups_kernel<<<ngroups, 1024, 0, c->stream>>>(p.agg, nslabs, pre, grp_sum);
-    s2s_scan_top_kernel<<<1, 1024, 0, c->stream>>>(grp_sum, ngroups, grp_pre, d_res);
+    s2s_scan_top_kernel<<<1, 1024, 0, c->stream>>>(grp_sum, ngroups, grp_pre, d_res, d_totals, (uint64_t)len);
     c->launches += 3;
     SJ_CUDA_CHECK(cudaGetLastError());
     Stage2Result* h_res = reinterpret_cast<Stage2Result*>(reinterpret_cast<uint8_t*>(c->host_result) + 64);
     SJ_CUDA_CHECK(cudaMemcpyAsync(h_res, d_res, sizeof(Stage2Result), cudaMemcpyDeviceToHost, c->stream));
     SJ_CUDA_CHECK(cudaStreamSynchronize(c->stream));
-    const Stage2Result tot = *h_res;
-    *out = tot;
+    pd->tot = *h_res;
+    pd->sp = p;
+    pd->stream = true;
+    pd->valid = true;
+    *out = pd->tot;
+    return SJ_OK;
+}
+
+static int stream_emit(sj_ctx* c, uint64_t* d_tape, size_t tape_cap, uint8_t* d_strings, size_t strings_cap, const ParseBases& bases,
+                       Stage2Result* out) {
+    S2Pending* pd = pending_of(c);
+    if (!pd || !pd->valid || !pd->stream) return SJ_ERR_ARGUMENT;
+    pd->valid = false;
+    S2sParams p = pd->sp;
+    const Stage2Result tot = pd->tot;
+    const uint8_t* d_msg = p.msg;
+    const size_t len = p.len;
+    const unsigned grid = (p.nslabs + S2S_WARPS - 1) / S2S_WARPS;
+    Stage2Result* d_res = reinterpret_cast<Stage2Result*>(c->result.as<uint8_t>() + 64);
+    Stage2Result* h_res = reinterpret_cast<Stage2Result*>(reinterpret_cast<uint8_t*>(c->host_result) + 64);
+    int rc;
+    p.tape_base = bases.tape;
+    p.str_base = bases.str;
+    p.bases_dev = bases.dev;
 
     if (!d_tape) {
         rc = c->tape.reserve(tot.tape_len * 8 + 64);
@@ -444,6 +515,8 @@ static int run_stage2_stream(sj_ctx* c, const uint8_t* d_msg, size_t len, const 
         rp.rootpos = p.rootpos;
         rp.tape = d_tape;
         rp.tape_cap = tape_cap;
+        rp.tape_base = bases.tape;
+        rp.bases_dev = bases.dev;
         const uint64_t nrec = tot.n_records;
         s2_roots_kernel<<<(unsigned)((nrec + 1 + 255) / 256), 256, 0, c->stream>>>(rp, nrec, tot.tape_len);
     }
@@ -452,7 +525,7 @@ static int run_stage2_stream(sj_ctx* c, const uint8_t* d_msg, size_t len, const 
     SJ_CUDA_CHECK(cudaMemcpyAsync(h_res, d_res, sizeof(Stage2Result), cudaMemcpyDeviceToHost, c->stream));
     SJ_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     *out = *h_res;
-    if (stage2_verdict(*out) == SJ_OK) {
+    if (stage2_verdict(*out) == SJ_OK && bases.tape == 0 && !bases.dev) {
         c->last_rootpos = p.rootpos;
         c->last_records = tot.n_records;
         c->last_tape = d_tape;
@@ -463,12 +536,24 @@ static int run_stage2_stream(sj_ctx* c, const uint8_t* d_msg, size_t len, const 
     return SJ_OK;
 }
 
-// stage 2 by whichever implementation the context and the flags select
+// stage 2 by whichever implementation the context and the flags select: counting half, emitting half
+static int stage2_count_any(sj_ctx* c, const uint8_t* d_msg, size_t len, uint32_t n, uint32_t flags, Stage2Result* out,
+                            uint64_t* d_totals = nullptr) {
+    if (use_stream_stage2(c, flags)) return stream_count(c, d_msg, len, c->idx.as<uint32_t>(), n, flags, out, d_totals);
+    return legacy_count(c, d_msg, len, c->idx.as<uint32_t>(), n, flags, c->s2c.as<uint32_t>(), out, d_totals);
+}
+static int stage2_emit_any(sj_ctx* c, uint64_t* d_tape, size_t tape_cap, uint8_t* d_strings, size_t strings_cap, const ParseBases& bases,
+                           Stage2Result* out) {
+    S2Pending* pd = pending_of(c);
+    if (!pd || !pd->valid) return SJ_ERR_ARGUMENT;
+    return pd->stream ? stream_emit(c, d_tape, tape_cap, d_strings, strings_cap, bases, out)
+                      : legacy_emit(c, d_tape, tape_cap, d_strings, strings_cap, bases, out);
+}
 static int run_stage2_any(sj_ctx* c, const uint8_t* d_msg, size_t len, uint32_t n, uint32_t flags, uint64_t* d_tape, size_t tape_cap,
                           uint8_t* d_strings, size_t strings_cap, Stage2Result* out) {
-    if (use_stream_stage2(c, flags))
-        return run_stage2_stream(c, d_msg, len, c->idx.as<uint32_t>(), n, flags, d_tape, tape_cap, d_strings, strings_cap, out);
-    return run_stage2(c, d_msg, len, c->idx.as<uint32_t>(), n, flags, d_tape, tape_cap, d_strings, strings_cap, out, c->s2c.as<uint32_t>());
+    int rc = stage2_count_any(c, d_msg, len, n, flags, out);
+    if (rc) return rc;
+    return stage2_emit_any(c, d_tape, tape_cap, d_strings, strings_cap, ParseBases{0, 0, 0, nullptr}, out);
 }
 
 extern "C" int sj_parse_device(sj_ctx* c, const uint8_t* d_msg, size_t len, uint32_t flags, uint64_t* d_tape,
@@ -492,6 +577,47 @@ extern "C" int sj_parse_device(sj_ctx* c, const uint8_t* d_msg, size_t len, uint
         *tape_len = r2.tape_len;
         *strings_len = r2.strings_len;
     }
+    if (rc) return rc;
+    return stage2_verdict(r2);
+}
+
+// ---------------------------------------------------------------------------------
+// ParseND sharded over several GPUs (simdjson_amd64.go:82-93 returns ONE ParsedJson).  Every rank
+// owns a newline-delimited shard of the message.  The counting half of stage 2 ends with the shard's totals on the host
+// anyway (that is where output buffers are sized); the ranks exchange them (one all-gather of four integers, NCCL in
+// the caller), and the emitting half then writes the shard's tape / Strings.B as the slice of the WHOLE result that
+// starts at the exclusive prefix of the totals: root chaining, scope pointers and string offsets are written with the
+// bases already added, so there is no separate rebasing pass.
+// ---------------------------------------------------------------------------------
+extern "C" int sj_parse_nd_sharded_count(sj_ctx* c, const uint8_t* d_msg, size_t len, uint32_t flags, sj_shard_totals* totals,
+                                         uint64_t* d_totals) {
+    if (!c || !totals) return SJ_ERR_ARGUMENT;
+    memset(totals, 0, sizeof *totals);
+    if (len == 0) return SJ_ERR_STAGE1;
+    if (len > SJ_MAX_MESSAGE) return SJ_ERR_TOO_LARGE;
+    flags |= SJ_FLAG_NDJSON;
+    SJ_CUDA_CHECK(cudaSetDevice(c->device));
+    Stage1Result r1;
+    int rc = stage1_positions(c, d_msg, len, true, &r1, use_stream_stage2(c, flags));
+    if (rc) return rc;
+    const uint8_t last_char = r1.n_idx && r1.last_pos < len ? (uint8_t)r1.last_char : 0;
+    if (!stage1_ok(r1, last_char)) return SJ_ERR_STAGE1;
+    Stage2Result r2{};
+    rc = stage2_count_any(c, d_msg, len, r1.n_idx, flags, &r2, d_totals);
+    if (rc) return rc;
+    totals->msg_bytes = len;
+    totals->tape_words = r2.tape_len;
+    totals->string_bytes = r2.strings_len;
+    totals->records = r2.n_records + 1;
+    return SJ_OK;
+}
+
+extern "C" int sj_parse_nd_sharded_emit(sj_ctx* c, uint64_t msg_base, uint64_t tape_base, uint64_t strings_base, const uint64_t* d_bases,
+                                        uint64_t* d_tape, size_t tape_cap, uint8_t* d_strings, size_t strings_cap) {
+    if (!c || !d_tape || !d_strings) return SJ_ERR_ARGUMENT;
+    SJ_CUDA_CHECK(cudaSetDevice(c->device));
+    Stage2Result r2{};
+    int rc = stage2_emit_any(c, d_tape, tape_cap, d_strings, strings_cap, ParseBases{msg_base, tape_base, strings_base, d_bases}, &r2);
     if (rc) return rc;
     return stage2_verdict(r2);
 }

@@ -288,7 +288,13 @@ struct Stage2Params {
     uint8_t* strings;
     uint64_t strings_cap;
     Stage2Result* result;
+    // this parse as a shard of ONE ParsedJson (see S2sParams): offsets added to every index written into the tape
+    uint64_t tape_base, str_base, msg_base;
+    const uint64_t* bases_dev;  // optional { msg_base, tape_base, str_base } in device memory: overrides the three above
 };
+__device__ __forceinline__ uint64_t s2_msg_base(const Stage2Params& p) { return p.bases_dev ? p.bases_dev[0] : p.msg_base; }
+__device__ __forceinline__ uint64_t s2_tape_base(const Stage2Params& p) { return p.bases_dev ? p.bases_dev[1] : p.tape_base; }
+__device__ __forceinline__ uint64_t s2_str_base(const Stage2Params& p) { return p.bases_dev ? p.bases_dev[2] : p.str_base; }
 
 // ---------------------------------------------------------------------------------
 // atoms (stage2_build_tape_amd64.go:124-158, 455-476)
@@ -912,7 +918,7 @@ __global__ void __launch_bounds__(1024) s2_scan_groups_kernel(const ScanVal* in,
 
 // single block: exclusive scan of all group totals (looping), grand total into result
 __global__ void __launch_bounds__(1024) s2_scan_top_kernel(const ScanVal* in, uint32_t n, ScanVal* pre,
-                                                           Stage2Result* res) {
+                                                           Stage2Result* res, uint64_t* totals_out, uint64_t msg_bytes) {
     ScanVal carry = sv_zero();
     for (uint32_t base = 0; base < n; base += 1024) {
         const uint32_t i = base + threadIdx.x;
@@ -928,6 +934,12 @@ __global__ void __launch_bounds__(1024) s2_scan_top_kernel(const ScanVal* in, ui
         res->n_brackets = carry.brk;
         res->n_records = carry.rec;
         res->final_depth = carry.depth;
+        if (totals_out) {
+            totals_out[0] = msg_bytes;
+            totals_out[1] = (uint64_t)carry.w + 2;
+            totals_out[2] = carry.str;
+            totals_out[3] = (uint64_t)carry.rec + 1;
+        }
     }
 }
 
@@ -978,7 +990,7 @@ __global__ void __launch_bounds__(S2_THREADS, SJ_S2_EMIT_MIN_BLOCKS) s2_emit_ker
         case T_STRING: {
             const uint32_t dl = aux & AUX_LEN;
             if (aux & AUX_COPY) {
-                p.tape[tp] = ((uint64_t)'"' << 56) | (STRINGBUFBIT + e.str);
+                p.tape[tp] = ((uint64_t)'"' << 56) | (STRINGBUFBIT + s2_str_base(p) + e.str);
                 if ((uint64_t)e.str + dl <= p.strings_cap) {
                     if (aux & AUX_ESC) {
                         if (dl >= S2_COOP_MIN) {
@@ -994,7 +1006,7 @@ __global__ void __launch_bounds__(S2_THREADS, SJ_S2_EMIT_MIN_BLOCKS) s2_emit_ker
                     atomicOr(&p.result->overflow, 1u);
                 }
             } else {
-                p.tape[tp] = ((uint64_t)'"' << 56) | (pos + 1);  // stage2...go:90-92
+                p.tape[tp] = ((uint64_t)'"' << 56) | (s2_msg_base(p) + pos + 1);  // stage2...go:90-92
             }
             p.tape[tp + 1] = dl;
             break;
@@ -1301,8 +1313,8 @@ __global__ void __launch_bounds__(S2_THREADS) s2_grammar_kernel(const Stage2Para
             const int32_t enclosing = p.enc_after[k];  // k exists: a close cannot follow T_START in a valid transition
             const uint32_t open_tp = p.brk_tp[enclosing], close_tp = p.brk_tp[k + 1];
             if (close_tp < p.tape_cap) {
-                p.tape[open_tp] = ((uint64_t)(cj == T_OBJ_CLOSE ? '{' : '[') << 56) | ((uint64_t)close_tp + 1);
-                p.tape[close_tp] = ((uint64_t)(cj == T_OBJ_CLOSE ? '}' : ']') << 56) | open_tp;
+                p.tape[open_tp] = ((uint64_t)(cj == T_OBJ_CLOSE ? '{' : '[') << 56) | (s2_tape_base(p) + close_tp + 1);
+                p.tape[close_tp] = ((uint64_t)(cj == T_OBJ_CLOSE ? '}' : ']') << 56) | (s2_tape_base(p) + open_tp);
             }
         }
         if (cj >= T_OBJ_OPEN && cj <= T_ARR_CLOSE) before++;
@@ -1322,8 +1334,8 @@ __global__ void s2_roots_kernel(const Stage2Params p, uint64_t n_records, uint64
     const uint64_t open = r == 0 ? 0 : p.rootpos[r];
     const uint64_t next_open = r == n_records ? tape_len : p.rootpos[r + 1];
     if (next_open > p.tape_cap || next_open == 0) return;
-    p.tape[open] = R | next_open;
-    p.tape[next_open - 1] = R | open;
+    p.tape[open] = R | (s2_tape_base(p) + next_open);
+    p.tape[next_open - 1] = R | (s2_tape_base(p) + open);
 }
 
 }  // namespace sj

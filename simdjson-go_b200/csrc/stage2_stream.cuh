@@ -170,7 +170,8 @@ __global__ void __launch_bounds__(1024) s2s_scan_groups_kernel(const SlabAgg* in
     if (threadIdx.x == 0) group_total[blockIdx.x] = total;
 }
 
-__global__ void __launch_bounds__(1024) s2s_scan_top_kernel(const SlabAgg* in, uint32_t n, SlabAgg* pre, Stage2Result* res) {
+__global__ void __launch_bounds__(1024) s2s_scan_top_kernel(const SlabAgg* in, uint32_t n, SlabAgg* pre, Stage2Result* res,
+                                                            uint64_t* totals_out, uint64_t msg_bytes) {
     SlabAgg carry = agg_zero();
     for (uint32_t base = 0; base < n; base += 1024) {
         const uint32_t i = base + threadIdx.x;
@@ -187,6 +188,12 @@ __global__ void __launch_bounds__(1024) s2s_scan_top_kernel(const SlabAgg* in, u
         res->n_records = carry.rec;
         res->final_depth = carry.depth;
         res->n_numbers = carry.num;
+        if (totals_out) {  // sj_shard_totals in device memory, for an exchange that stays on the stream
+            totals_out[0] = msg_bytes;
+            totals_out[1] = (uint64_t)carry.w + 2;
+            totals_out[2] = carry.str;
+            totals_out[3] = (uint64_t)carry.rec + 1;
+        }
     }
 }
 
@@ -215,6 +222,7 @@ __global__ void __launch_bounds__(S2_THREADS) s2s_numbers_kernel(const uint8_t* 
 __global__ void __launch_bounds__(S2_THREADS) s2s_link_kernel(const S2sParams p, const int32_t* par, uint32_t nb) {
     const uint32_t k = blockIdx.x * S2_THREADS + threadIdx.x;
     if (k > nb) return;
+    const uint64_t tape_base = s2s_tape_base(p);
     uint32_t ctx = CTX_ROOT;
     if (k > 0) {
         const uint32_t kd = p.brk_kind[k - 1];
@@ -235,8 +243,8 @@ __global__ void __launch_bounds__(S2_THREADS) s2s_link_kernel(const S2sParams p,
             const int32_t m = par[k];
             if (m >= 0) {
                 const uint32_t otp = p.brk_tp[m], ctp = p.brk_tp[k];
-                p.tape[otp] = ((uint64_t)(kd == T_OBJ_CLOSE ? '{' : '[') << 56) | ((uint64_t)ctp + 1);
-                p.tape[ctp] = ((uint64_t)(kd == T_OBJ_CLOSE ? '}' : ']') << 56) | otp;
+                p.tape[otp] = ((uint64_t)(kd == T_OBJ_CLOSE ? '{' : '[') << 56) | (tape_base + ctp + 1);
+                p.tape[ctp] = ((uint64_t)(kd == T_OBJ_CLOSE ? '}' : ']') << 56) | (tape_base + otp);
             }
         }
     }

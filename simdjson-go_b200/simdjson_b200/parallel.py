@@ -72,6 +72,45 @@ def rebase_shard_tape(tape, tape_base, strings_base, msg_base):
     return out
 
 
+def trimmed_window(buf, a, b):
+    """[a, b) shrunk by the ASCII blanks at both ends (shards are cut behind a newline; the parse wants the trimmed
+    window, parse_json_amd64.go:55).  Shard boundaries are ASCII newlines, so the ASCII rule is exact here."""
+    ws = b" \t\n\v\f\r"
+    while a < b and buf[a] in ws:
+        a += 1
+    while b > a and buf[b - 1] in ws:
+        b -= 1
+    return a, b
+
+
+class ShardedParse:
+    """ParseND over the ranks of a process group: the two halves of sj_parse_nd_sharded_* around ONE all-gather of the
+    shard totals.  Each rank ends up with its slice of the single ParsedJson the reference returns
+    (simdjson_amd64.go:82-93), already rebased: rank r's slice starts at tape word `tape_base` / Strings.B byte
+    `strings_base` of the whole.  Buffers are device pointers (integers); this class owns none."""
+
+    def __init__(self, ctx, group=None, device=None):
+        self.ctx, self.group, self.device = ctx, group, device
+
+    def count(self, d_msg, n, copy_strings=True, d_totals=None):
+        """d_totals: optional device pointer that receives the same four integers on the context's stream"""
+        import ctypes as C
+        from . import _lib
+        t = _lib.ShardTotals()
+        flags = _lib.FLAG_NDJSON | (_lib.FLAG_COPY_STRINGS if copy_strings else 0)
+        rc = self.ctx.L.sj_parse_nd_sharded_count(self.ctx.h, d_msg, n, flags, C.byref(t), d_totals)
+        return rc, (int(t.msg_bytes), int(t.tape_words), int(t.string_bytes), int(t.records))
+
+    def emit(self, msg_base, tape_base, strings_base, d_tape, tape_cap, d_strings, strings_cap, d_bases=None):
+        """d_bases: optional device pointer to { msg_base, tape_base, strings_base } (then the three scalars are ignored)"""
+        return self.ctx.L.sj_parse_nd_sharded_emit(self.ctx.h, msg_base, tape_base, strings_base, d_bases, d_tape, tape_cap,
+                                                   d_strings, strings_cap)
+
+    def exchange(self, totals):
+        """all-gather of this rank's (msg_bytes, tape_words, string_bytes): (exclusive prefix, every rank's totals)"""
+        return exchange_totals(totals[:3], self.group, self.device)
+
+
 def reduce_counts(local, group=None, device=None):
     """countWhere / countObjects over a sharded stream (consume.cuh): records are independent, so the
     answer for the whole stream is the sum of the per-shard (roots, matches) -- one all_reduce of

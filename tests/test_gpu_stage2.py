@@ -485,3 +485,47 @@ def test_streaming_stage2_edges(ctx, oracle_native):
     finally:
         emu.same_as_oracle = orig
     assert calls[0] > 2500
+
+
+@pytest.mark.parametrize("copy", [True, False])
+@pytest.mark.parametrize("world", [2, 3])
+def test_parse_nd_sharded_is_one_parsed_json(oracle_native, copy, world):
+    """sj_parse_nd_sharded_count / _emit: the shards' slices, laid end to end, are bit for bit the tape and
+    string buffer the reference's ParseND returns for the whole stream (simdjson_amd64.go:82-93; root chaining
+    stage2_build_tape_amd64.go:190-221) -- `world` contexts on this GPU stand in for the ranks, the exchange of the totals
+    is done by hand (over NCCL it is parallel.ShardedParse.exchange)"""
+    import torch
+    import simdjson_b200 as sj
+    from simdjson_b200.parallel import ShardedParse, split_at_newlines, trimmed_window
+    pk = load_fixture("parking-citations").strip()
+    stream = b"\n".join([pk] * 7) + b"\n\n" + b'{"esc":"a\\u00e9\\n","n":[1,2.5,-3],"t":true}\n' + pk[:30000].rsplit(b"\n", 1)[0]
+    rc, tape_o, str_o, (off_o, len_o) = oracle_native.parse(stream, ndjson=True, copy_strings=copy)
+    assert rc == 0
+    dev = torch.device("cuda:0")
+    ranks = []
+    for a, b in split_at_newlines(stream, world):
+        a, b = trimmed_window(stream, a, b)
+        c = sj.Context(0)
+        d_msg = torch.full((b - a + 256,), 0x20, dtype=torch.uint8, device=dev)
+        d_msg[: b - a] = torch.frombuffer(bytearray(stream[a:b]), dtype=torch.uint8).to(dev)
+        sp = ShardedParse(c)
+        rc, tot = sp.count(d_msg.data_ptr(), b - a, copy)
+        assert rc == 0
+        ranks.append((c, sp, d_msg, a, tot))
+    tapes, strs = [], []
+    tb = sb = 0
+    for c, sp, d_msg, a, tot in ranks:
+        d_tape = torch.empty(tot[1] + 8, dtype=torch.int64, device=dev)
+        d_str = torch.empty(tot[2] + 64, dtype=torch.uint8, device=dev)
+        assert sp.emit(a - off_o, tb, sb, d_tape.data_ptr(), d_tape.numel(), d_str.data_ptr(), d_str.numel()) == 0
+        tapes.append(d_tape[: tot[1]].cpu().numpy().view(np.uint64))
+        strs.append(d_str[: tot[2]].cpu().numpy().tobytes())
+        tb += tot[1]
+        sb += tot[2]
+    assert sum(t[4][3] for t in ranks) == stream.count(b"\n{") + 1
+    got = np.concatenate(tapes)
+    assert len(got) == len(tape_o)
+    assert np.array_equal(got, tape_o), int(np.nonzero(got != tape_o)[0][0])
+    assert b"".join(strs) == str_o
+    for c, *_ in ranks:
+        c.close()
