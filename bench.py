@@ -16,7 +16,7 @@ every rank parses its own shard of the stream; record boundaries are shard bound
             (N_in + 4 * N_idx) / CUDA-event time, against the measured HBM peak
   cpu_baseline / --impl reference
             the reference cannot be built here (no Go toolchain), so the CPU arm is the
-            oracle port (C restatement with the AVX2+PCLMUL mask routines) run
+            oracle port (C restatement; AVX-512BW mask routines when the host has them, else AVX2+PCLMUL) run
             ParseNDStream-style on all host threads (10 MiB newline-aligned chunks)
 """
 import argparse
@@ -114,6 +114,7 @@ class ClockSampler(threading.Thread):
 # CPU arm: the oracle port, ParseNDStream-shaped (simdjson_amd64.go:116-215)
 # --------------------------------------------------------------------------------------
 _cpu_pool = None
+_cpu_isa = "?"
 _cpu_local = threading.local()
 
 
@@ -125,7 +126,9 @@ def cpu_parse_stream(buf, threads, chunk=10 << 20, count_where=None):
     global _cpu_pool
     from concurrent.futures import ThreadPoolExecutor
     from oracle.pyoracle import FLAG_COPY_STRINGS, FLAG_NDJSON, Oracle
-    o = Oracle("native")
+    o = Oracle("best")  # AVX-512BW mask routines when the host has them (the reference's choice, stage1_find_marks_amd64.go:42), else AVX2
+    global _cpu_isa
+    _cpu_isa = o.isa
     if _cpu_pool is None or _cpu_pool._max_workers != threads:
         _cpu_pool = ThreadPoolExecutor(max_workers=threads)
     arr = np.frombuffer(buf, dtype=np.uint8)
@@ -188,7 +191,8 @@ def run_reference(args, rank, world):
         "config": {"workload": WORKLOAD, "cpu_arm": "ParseNDStream-style 10 MiB newline-aligned chunks on all host threads",
                    "batch_bytes": len(sample)},
         "cpu_baseline": {"value": round(gbs, 4), "unit": "GB/s", "cores": threads, "kind": "port",
-                         "sample": "%d MiB per step, oracle port (C restatement, AVX2+PCLMUL stage 1; the Go reference cannot be built: no Go toolchain) %s" % (len(sample) >> 20, quota)},
+                         "isa": _cpu_isa,
+                         "sample": "%d MiB per step, oracle port (C restatement of the reference's path, %s mask routines; the Go reference cannot be built: no Go toolchain) %s" % (len(sample) >> 20, _cpu_isa, quota)},
         "e2e": {"value": round(gbs, 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -483,8 +487,8 @@ def main():
             nb += n2
             reps += 1
         t_c, n_c = cpu_parse_stream(sample, threads, count_where=(b"Make", b"HOND"))
-        cpu = {"value": round(nb / secs / 1e9, 4), "unit": "GB/s", "cores": threads, "kind": "port",
-               "sample": "%d x %d MiB of the same NDJSON stream, 10 MiB chunks on all host threads (oracle port; the Go reference cannot be built here) %s" % (reps, len(sample) >> 20, quota),
+        cpu = {"value": round(nb / secs / 1e9, 4), "unit": "GB/s", "cores": threads, "kind": "port", "isa": _cpu_isa,
+               "sample": "%d x %d MiB of the same NDJSON stream, 10 MiB chunks on all host threads (oracle port, %s mask routines; the Go reference cannot be built here) %s" % (reps, len(sample) >> 20, _cpu_isa, quota),
                "parse_count_where": round(n_c / t_c / 1e9, 4)}
 
     if rank == 0:

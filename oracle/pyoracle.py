@@ -14,7 +14,7 @@ FLAG_COPY_STRINGS = 2
 
 u32p = C.POINTER(C.c_uint32)
 u64p = C.POINTER(C.c_uint64)
-_LIBS = ("libsjoracle.so", "libsjoracle_native.so")
+_LIBS = ("libsjoracle.so", "libsjoracle_native.so", "libsjoracle_avx512.so")
 
 
 def build(force=False):
@@ -27,6 +27,18 @@ def build(force=False):
         subprocess.check_call(["make", "-C", _DIR, "-s", "-B"])
 
 
+def host_has_avx512():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.startswith("flags"):
+                    fl = set(ln.split(":", 1)[1].split())
+                    return {"avx512f", "avx512bw", "avx512vl", "pclmulqdq"} <= fl
+    except OSError:
+        pass
+    return False
+
+
 def _buf(b):
     b = bytes(b)
     return (C.c_uint8 * max(1, len(b))).from_buffer_copy(b if len(b) else b"\0")
@@ -35,8 +47,12 @@ def _buf(b):
 class Oracle:
     def __init__(self, variant="scalar"):
         build()
-        name = "libsjoracle.so" if variant == "scalar" else "libsjoracle_native.so"
+        if variant == "best":  # the widest mask routines this host can run (the reference picks AVX-512 the same way)
+            variant = "avx512" if host_has_avx512() else "native"
+        name = {"scalar": "libsjoracle.so", "native": "libsjoracle_native.so", "avx512": "libsjoracle_avx512.so"}[variant]
         L = self.lib = C.CDLL(os.path.join(_DIR, name))
+        L.sjo_isa.restype = C.c_char_p
+        self.isa = L.sjo_isa().decode()
         L.sjo_find_odd_backslash_sequences.restype = C.c_uint64
         L.sjo_find_odd_backslash_sequences.argtypes = [C.c_void_p, u64p]
         L.sjo_find_quote_mask_and_bits.restype = C.c_uint64

@@ -21,12 +21,19 @@
 #include <stdlib.h>
 #include <string.h>
 
-#if defined(__AVX2__) && defined(__PCLMUL__) && !defined(SJO_FORCE_SCALAR)
+#if defined(__AVX512BW__) && defined(__AVX512F__) && defined(__PCLMUL__) && !defined(SJO_FORCE_SCALAR) && defined(SJO_WANT_AVX512)
+#include <immintrin.h>
+#define SJO_SIMD 2 /* 64-byte ZMM loads, compares straight into k-mask registers: the reference's *_avx512 routines
+                      (find_structural_bits_avx512_amd64.s:51-164, selected at stage1_find_marks_amd64.go:42) */
+#elif defined(__AVX2__) && defined(__PCLMUL__) && !defined(SJO_FORCE_SCALAR)
 #include <immintrin.h>
 #define SJO_SIMD 1
 #else
 #define SJO_SIMD 0
 #endif
+
+/* which mask routines this build uses (bench.py prints it next to the CPU arm's number) */
+const char *sjo_isa(void) { return SJO_SIMD == 2 ? "avx512bw+pclmul" : SJO_SIMD == 1 ? "avx2+pclmul" : "scalar"; }
 
 /* ======================================================================= */
 /* stage 1: per-64-byte mask routines                                       */
@@ -38,7 +45,12 @@ static inline uint64_t mask_eq_scalar(const uint8_t *in, uint8_t c) {
     return m;
 }
 
-#if SJO_SIMD
+#if SJO_SIMD == 2
+/* VPCMPEQB zmm -> k (find_quote_mask_and_bits_amd64.s:117, find_odd_backslash_sequences_amd64.s:84-88) */
+static inline uint64_t mask_eq(const uint8_t *in, uint8_t c) {
+    return (uint64_t)_mm512_cmpeq_epi8_mask(_mm512_loadu_si512((const void *)in), _mm512_set1_epi8((char)c));
+}
+#elif SJO_SIMD
 static inline uint64_t mask_eq(const uint8_t *in, uint8_t c) {
     __m256i lo = _mm256_loadu_si256((const __m256i *)in);
     __m256i hi = _mm256_loadu_si256((const __m256i *)(in + 32));
@@ -88,7 +100,11 @@ static inline uint64_t prefix_xor(uint64_t x) {
 }
 
 static inline uint64_t mask_le_1f(const uint8_t *in) {
-#if SJO_SIMD
+#if SJO_SIMD == 2
+    /* find_quote_mask_and_bits_amd64.s:127-128: VPXORD 0x80, VPCMPGTB against 0xA0 into a k register */
+    __m512i v = _mm512_xor_si512(_mm512_loadu_si512((const void *)in), _mm512_set1_epi8((char)0x80));
+    return (uint64_t)_mm512_cmpgt_epi8_mask(_mm512_set1_epi8((char)0xA0), v);
+#elif SJO_SIMD
     /* :67-80  (in ^ 0x80) <s 0xA0 */
     __m256i lo = _mm256_loadu_si256((const __m256i *)in);
     __m256i hi = _mm256_loadu_si256((const __m256i *)(in + 32));
@@ -122,7 +138,17 @@ static const uint8_t HI_NIBBLE[16] = {8, 0, 18, 4, 0, 1, 0, 1, 0, 0, 0, 3, 2, 1,
 
 void sjo_find_whitespace_and_structurals(const uint8_t *in, uint64_t *whitespace, uint64_t *structurals) {
     uint64_t ws = 0, st = 0;
-#if SJO_SIMD
+#if SJO_SIMD == 2
+    /* find_whitespace_and_structurals_amd64.s:136-148: two VPSHUFB zmm look-ups, VPANDD, VPCMPEQB against zero -> k, KNOTQ */
+    const __m512i lo_tbl = _mm512_broadcast_i32x4(_mm_setr_epi8(16, 0, 0, 0, 0, 0, 0, 0, 0, 8, 12, 1, 2, 9, 0, 0));
+    const __m512i hi_tbl = _mm512_broadcast_i32x4(_mm_setr_epi8(8, 0, 18, 4, 0, 1, 0, 1, 0, 0, 0, 3, 2, 1, 0, 0));
+    const __m512i v = _mm512_loadu_si512((const void *)in);
+    const __m512i l = _mm512_shuffle_epi8(lo_tbl, v);
+    const __m512i hn = _mm512_and_si512(_mm512_srli_epi32(v, 4), _mm512_set1_epi8(0x7f));
+    const __m512i c = _mm512_and_si512(l, _mm512_shuffle_epi8(hi_tbl, hn));
+    st = (uint64_t)_mm512_test_epi8_mask(c, _mm512_set1_epi8(0x07));
+    ws = (uint64_t)_mm512_test_epi8_mask(c, _mm512_set1_epi8(0x18));
+#elif SJO_SIMD
     __m256i lo_tbl = _mm256_setr_epi8(16, 0, 0, 0, 0, 0, 0, 0, 0, 8, 12, 1, 2, 9, 0, 0, 16, 0, 0, 0, 0, 0, 0, 0, 0, 8, 12, 1,
                                       2, 9, 0, 0);
     __m256i hi_tbl = _mm256_setr_epi8(8, 0, 18, 4, 0, 1, 0, 1, 0, 0, 0, 3, 2, 1, 0, 0, 8, 0, 18, 4, 0, 1, 0, 1, 0, 0, 0, 3, 2,

@@ -88,6 +88,7 @@ size_t sjo_stage1_count(const uint8_t *msg, size_t len, int ndjson, int *ok);
 uint64_t sjo_count_where(const uint64_t *tape, size_t tape_len, const uint8_t *strings, const uint8_t *msg,
                          const uint8_t *key, size_t klen, const uint8_t *value, size_t vlen, uint64_t *roots);
 
+const char *sjo_isa(void);
 #ifdef __cplusplus
 }
 #endif

@@ -14,8 +14,15 @@ from tests.util import SMALL_FILES, TAPE_FILES, golden, load_fixture, tricky_ndj
 M64 = (1 << 64) - 1
 
 
-@pytest.fixture(params=["scalar", "native"])
+@pytest.fixture(params=["scalar", "native", "avx512"])
 def o(request, oracle, oracle_native):
+    """the three builds of the oracle: scalar restatement, AVX2+PCLMUL mask routines, AVX-512BW mask routines (the
+    reference's *_avx512 path; skipped on hosts without AVX-512BW)"""
+    if request.param == "avx512":
+        from oracle.pyoracle import Oracle, host_has_avx512
+        if not host_has_avx512():
+            pytest.skip("host CPU has no AVX-512BW")
+        return Oracle("avx512")
     return oracle if request.param == "scalar" else oracle_native
 
 
