@@ -160,6 +160,13 @@ struct ParseBases {
     uint64_t msg, tape, str;
     const uint64_t* dev;  // or: the three of them in device memory
 };
+// host destinations of the host-buffer API: copied behind the last kernel, in front of the call's one final sync
+struct HostOut {
+    uint64_t* tape;
+    size_t tape_cap;
+    uint8_t* strings;
+    size_t strings_cap;
+};
 
 // per-structural kernels, counting half: K2a classify / measure, K2b scans, totals to the host
 static int legacy_count(sj_ctx* c, const uint8_t* d_msg, size_t len, const uint32_t* d_idx, uint32_t n, uint32_t flags,
@@ -217,7 +224,7 @@ static int legacy_count(sj_ctx* c, const uint8_t* d_msg, size_t len, const uint3
 
 // per-structural kernels, emitting half
 static int legacy_emit(sj_ctx* c, uint64_t* d_tape, size_t tape_cap, uint8_t* d_strings, size_t strings_cap, const ParseBases& bases,
-                       Stage2Result* out) {
+                       Stage2Result* out, const HostOut* host = nullptr) {
     S2Pending* pd = pending_of(c);
     if (!pd || !pd->valid || pd->stream) return SJ_ERR_ARGUMENT;
     pd->valid = false;
@@ -235,6 +242,10 @@ static int legacy_emit(sj_ctx* c, uint64_t* d_tape, size_t tape_cap, uint8_t* d_
     p.bases_dev = bases.dev;
 
     // ---- outputs ----
+    if (host && (tot.tape_len > host->tape_cap || tot.strings_len > host->strings_cap)) {
+        *out = tot;
+        return SJ_ERR_CAPACITY;
+    }
     if (!d_tape) {
         rc = c->tape.reserve(tot.tape_len * 8 + 64);
         if (rc) return rc;
@@ -319,6 +330,10 @@ static int legacy_emit(sj_ctx* c, uint64_t* d_tape, size_t tape_cap, uint8_t* d_
     }
     c->launches += 2;
     SJ_CUDA_CHECK(cudaGetLastError());
+    if (host) {  // (on a stage-2 failure the copied words are meaningless; the verdict below says so)
+        SJ_CUDA_CHECK(cudaMemcpyAsync(host->tape, d_tape, tot.tape_len * 8, cudaMemcpyDeviceToHost, c->stream));
+        if (tot.strings_len) SJ_CUDA_CHECK(cudaMemcpyAsync(host->strings, d_strings, tot.strings_len, cudaMemcpyDeviceToHost, c->stream));
+    }
     SJ_CUDA_CHECK(cudaMemcpyAsync(h_res, d_res, sizeof(Stage2Result), cudaMemcpyDeviceToHost, c->stream));
     SJ_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     *out = *h_res;
@@ -410,8 +425,9 @@ static int stream_count(sj_ctx* c, const uint8_t* d_msg, size_t len, const uint3
     s2s_scan_top_kernel<<<1, 1024, 0, c->stream>>>(grp_sum, ngroups, grp_pre, d_res, d_totals, (uint64_t)len);
     c->launches += 3;
     SJ_CUDA_CHECK(cudaGetLastError());
+    // one read-back for both stages: the stage-1 result block sits in front of the stage-2 totals, and K1 ran on the same stream
     Stage2Result* h_res = reinterpret_cast<Stage2Result*>(reinterpret_cast<uint8_t*>(c->host_result) + 64);
-    SJ_CUDA_CHECK(cudaMemcpyAsync(h_res, d_res, sizeof(Stage2Result), cudaMemcpyDeviceToHost, c->stream));
+    SJ_CUDA_CHECK(cudaMemcpyAsync(c->host_result, c->result.p, 64 + sizeof(Stage2Result), cudaMemcpyDeviceToHost, c->stream));
     SJ_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     pd->tot = *h_res;
     pd->sp = p;
@@ -422,7 +438,7 @@ static int stream_count(sj_ctx* c, const uint8_t* d_msg, size_t len, const uint3
 }
 
 static int stream_emit(sj_ctx* c, uint64_t* d_tape, size_t tape_cap, uint8_t* d_strings, size_t strings_cap, const ParseBases& bases,
-                       Stage2Result* out) {
+                       Stage2Result* out, const HostOut* host = nullptr) {
     S2Pending* pd = pending_of(c);
     if (!pd || !pd->valid || !pd->stream) return SJ_ERR_ARGUMENT;
     pd->valid = false;
@@ -438,6 +454,10 @@ static int stream_emit(sj_ctx* c, uint64_t* d_tape, size_t tape_cap, uint8_t* d_
     p.str_base = bases.str;
     p.bases_dev = bases.dev;
 
+    if (host && (tot.tape_len > host->tape_cap || tot.strings_len > host->strings_cap)) {
+        *out = tot;
+        return SJ_ERR_CAPACITY;
+    }
     if (!d_tape) {
         rc = c->tape.reserve(tot.tape_len * 8 + 64);
         if (rc) return rc;
@@ -522,6 +542,10 @@ static int stream_emit(sj_ctx* c, uint64_t* d_tape, size_t tape_cap, uint8_t* d_
     }
     c->launches += 2;
     SJ_CUDA_CHECK(cudaGetLastError());
+    if (host) {  // (on a stage-2 failure the copied words are meaningless; the verdict below says so)
+        SJ_CUDA_CHECK(cudaMemcpyAsync(host->tape, d_tape, tot.tape_len * 8, cudaMemcpyDeviceToHost, c->stream));
+        if (tot.strings_len) SJ_CUDA_CHECK(cudaMemcpyAsync(host->strings, d_strings, tot.strings_len, cudaMemcpyDeviceToHost, c->stream));
+    }
     SJ_CUDA_CHECK(cudaMemcpyAsync(h_res, d_res, sizeof(Stage2Result), cudaMemcpyDeviceToHost, c->stream));
     SJ_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     *out = *h_res;
@@ -543,19 +567,47 @@ static int stage2_count_any(sj_ctx* c, const uint8_t* d_msg, size_t len, uint32_
     return legacy_count(c, d_msg, len, c->idx.as<uint32_t>(), n, flags, c->s2c.as<uint32_t>(), out, d_totals);
 }
 static int stage2_emit_any(sj_ctx* c, uint64_t* d_tape, size_t tape_cap, uint8_t* d_strings, size_t strings_cap, const ParseBases& bases,
-                           Stage2Result* out) {
+                           Stage2Result* out, const HostOut* host = nullptr) {
     S2Pending* pd = pending_of(c);
     if (!pd || !pd->valid) return SJ_ERR_ARGUMENT;
-    return pd->stream ? stream_emit(c, d_tape, tape_cap, d_strings, strings_cap, bases, out)
-                      : legacy_emit(c, d_tape, tape_cap, d_strings, strings_cap, bases, out);
-}
-static int run_stage2_any(sj_ctx* c, const uint8_t* d_msg, size_t len, uint32_t n, uint32_t flags, uint64_t* d_tape, size_t tape_cap,
-                          uint8_t* d_strings, size_t strings_cap, Stage2Result* out) {
-    int rc = stage2_count_any(c, d_msg, len, n, flags, out);
-    if (rc) return rc;
-    return stage2_emit_any(c, d_tape, tape_cap, d_strings, strings_cap, ParseBases{0, 0, 0, nullptr}, out);
+    return pd->stream ? stream_emit(c, d_tape, tape_cap, d_strings, strings_cap, bases, out, host)
+                      : legacy_emit(c, d_tape, tape_cap, d_strings, strings_cap, bases, out, host);
 }
 
+// Stage 1 and the counting half of stage 2.  With the streaming kernels nothing between K1 and the totals needs the
+// host, so K1, K2p and K2q are enqueued back to back and ONE read-back delivers the stage-1 verdict and the totals
+// (a document of a few hundred KB is launch- and synchronisation-bound: this halves its host round trips).
+static int front_half(sj_ctx* c, const uint8_t* d_msg, size_t len, uint32_t flags, Stage1Result* r1, Stage2Result* r2, uint64_t* d_totals = nullptr) {
+    const bool ndjson = (flags & SJ_FLAG_NDJSON) != 0;
+    if (!use_stream_stage2(c, flags)) {
+        int rc = stage1_positions(c, d_msg, len, ndjson, r1, false);
+        if (rc) return rc;
+        const uint8_t last_char = r1->n_idx && r1->last_pos < len ? (uint8_t)r1->last_char : 0;
+        if (!stage1_ok(*r1, last_char)) return SJ_ERR_STAGE1;
+        return stage2_count_any(c, d_msg, len, r1->n_idx, flags, r2, d_totals);
+    }
+    size_t dcap = len / 4 + 1024;
+    if (c->idx.cap / sizeof(uint32_t) > dcap) dcap = c->idx.cap / sizeof(uint32_t);
+    for (int attempt = 0; attempt < 2; attempt++) {
+        int rc = c->idx.reserve(dcap * sizeof(uint32_t));
+        if (rc) return rc;
+        rc = launch_stage1(c, d_msg, len, ndjson, false, c->idx.as<uint32_t>(), dcap, nullptr, true);
+        if (rc) return rc;
+        rc = stream_count(c, d_msg, len, c->idx.as<uint32_t>(), 0, flags, r2, d_totals);  // (its read-back brings the stage-1 block too)
+        if (rc) return rc;
+        memcpy(r1, c->host_result, sizeof(Stage1Result));
+        if (!r1->overflow) {
+            const uint8_t last_char = r1->n_idx && r1->last_pos < len ? (uint8_t)r1->last_char : 0;
+            if (!stage1_ok(*r1, last_char)) {
+                pending_of(c)->valid = false;
+                return SJ_ERR_STAGE1;
+            }
+            return SJ_OK;
+        }
+        dcap = (size_t)r1->n_idx + 64;  // the index buffer was too small (more than one structural in four bytes): once more
+    }
+    return SJ_ERR_CAPACITY;
+}
 extern "C" int sj_parse_device(sj_ctx* c, const uint8_t* d_msg, size_t len, uint32_t flags, uint64_t* d_tape,
                                size_t tape_cap, size_t* tape_len, uint8_t* d_strings, size_t strings_cap,
                                size_t* strings_len) {
@@ -566,14 +618,11 @@ extern "C" int sj_parse_device(sj_ctx* c, const uint8_t* d_msg, size_t len, uint
     if (len > SJ_MAX_MESSAGE) return SJ_ERR_TOO_LARGE;
     SJ_CUDA_CHECK(cudaSetDevice(c->device));
     Stage1Result r1;
-    int rc = stage1_positions(c, d_msg, len, (flags & SJ_FLAG_NDJSON) != 0, &r1, use_stream_stage2(c, flags));
-    if (rc) return rc;
-    // the byte under the last structural comes back with the stage-1 result (stage1_finish_kernel)
-    const uint8_t last_char = r1.n_idx && r1.last_pos < len ? (uint8_t)r1.last_char : 0;
-    if (!stage1_ok(r1, last_char)) return SJ_ERR_STAGE1;
     Stage2Result r2{};
-    rc = run_stage2_any(c, d_msg, len, r1.n_idx, flags, d_tape, tape_cap, d_strings, strings_cap, &r2);
-    if (rc == SJ_OK || rc == SJ_ERR_CAPACITY) {  // the required sizes (simdjson_b200.h): only when stage 2 got as far as its totals
+    int rc = front_half(c, d_msg, len, flags, &r1, &r2);
+    if (rc) return rc;
+    rc = stage2_emit_any(c, d_tape, tape_cap, d_strings, strings_cap, ParseBases{0, 0, 0, nullptr}, &r2);
+    if (rc == SJ_OK || rc == SJ_ERR_CAPACITY) {  // the required sizes (simdjson_b200.h): stage 2 got as far as its totals
         *tape_len = r2.tape_len;
         *strings_len = r2.strings_len;
     }
@@ -598,12 +647,8 @@ extern "C" int sj_parse_nd_sharded_count(sj_ctx* c, const uint8_t* d_msg, size_t
     flags |= SJ_FLAG_NDJSON;
     SJ_CUDA_CHECK(cudaSetDevice(c->device));
     Stage1Result r1;
-    int rc = stage1_positions(c, d_msg, len, true, &r1, use_stream_stage2(c, flags));
-    if (rc) return rc;
-    const uint8_t last_char = r1.n_idx && r1.last_pos < len ? (uint8_t)r1.last_char : 0;
-    if (!stage1_ok(r1, last_char)) return SJ_ERR_STAGE1;
     Stage2Result r2{};
-    rc = stage2_count_any(c, d_msg, len, r1.n_idx, flags, &r2, d_totals);
+    int rc = front_half(c, d_msg, len, flags, &r1, &r2, d_totals);
     if (rc) return rc;
     totals->msg_bytes = len;
     totals->tape_words = r2.tape_len;
@@ -639,25 +684,18 @@ extern "C" int sj_parse(sj_ctx* c, const uint8_t* msg, size_t len, uint32_t flag
     int rc = upload_message(c, msg + a, n);
     if (rc) return rc;
     Stage1Result r1;
-    rc = stage1_positions(c, c->msg.as<uint8_t>(), n, (flags & SJ_FLAG_NDJSON) != 0, &r1, use_stream_stage2(c, flags));
-    if (rc) return rc;
-    uint8_t last_char = r1.n_idx && r1.last_pos < n ? msg[a + r1.last_pos] : 0;
-    if (!stage1_ok(r1, last_char)) return SJ_ERR_STAGE1;
     Stage2Result r2{};
-    rc = run_stage2_any(c, c->msg.as<uint8_t>(), n, r1.n_idx, flags, nullptr, 0, nullptr, 0, &r2);
+    rc = front_half(c, c->msg.as<uint8_t>(), n, flags, &r1, &r2);
+    if (rc) return rc;
+    // the emitting half, the copies of tape and strings into the caller's buffers and the verdict: one synchronisation
+    const HostOut host{tape, tape_cap, strings, strings_cap};
+    rc = stage2_emit_any(c, nullptr, 0, nullptr, 0, ParseBases{0, 0, 0, nullptr}, &r2, &host);
     if (rc == SJ_OK || rc == SJ_ERR_CAPACITY) {
         *tape_len = r2.tape_len;
         *strings_len = r2.strings_len;
     }
     if (rc) return rc;
-    rc = stage2_verdict(r2);
-    if (rc) return rc;
-    if (r2.tape_len > tape_cap || r2.strings_len > strings_cap) return SJ_ERR_CAPACITY;
-    SJ_CUDA_CHECK(cudaMemcpyAsync(tape, c->tape.p, r2.tape_len * 8, cudaMemcpyDeviceToHost, c->stream));
-    if (r2.strings_len)
-        SJ_CUDA_CHECK(cudaMemcpyAsync(strings, c->strings.p, r2.strings_len, cudaMemcpyDeviceToHost, c->stream));
-    SJ_CUDA_CHECK(cudaStreamSynchronize(c->stream));
-    return SJ_OK;
+    return stage2_verdict(r2);
 }
 
 // parseMessage up to the point where tape and strings sit in the context's device buffers
@@ -676,11 +714,9 @@ static int parse_into_ctx(sj_ctx* c, const uint8_t* msg, size_t len, uint32_t fl
     int rc = upload_message(c, msg + a, n);
     if (rc) return rc;
     Stage1Result r1;
-    rc = stage1_positions(c, c->msg.as<uint8_t>(), n, (flags & SJ_FLAG_NDJSON) != 0, &r1, use_stream_stage2(c, flags));
+    rc = front_half(c, c->msg.as<uint8_t>(), n, flags, &r1, r2);
     if (rc) return rc;
-    const uint8_t last_char = r1.n_idx && r1.last_pos < n ? msg[a + r1.last_pos] : 0;
-    if (!stage1_ok(r1, last_char)) return SJ_ERR_STAGE1;
-    rc = run_stage2_any(c, c->msg.as<uint8_t>(), n, r1.n_idx, flags, nullptr, 0, nullptr, 0, r2);
+    rc = stage2_emit_any(c, nullptr, 0, nullptr, 0, ParseBases{0, 0, 0, nullptr}, r2);
     if (rc) return rc;
     return stage2_verdict(*r2);
 }
