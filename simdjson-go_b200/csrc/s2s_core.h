@@ -437,10 +437,12 @@ SJ_HD uint32_t backslashes_before(const R& rd, uint64_t x) {
     while (x > k && rd(x - 1 - k) == '\\') k++;
     return k;
 }
-// is there a "\uD8xx".."\uDBxx" escape STARTING at y (a backslash at an even offset of its run)?
+// is there a "\uD8xx".."\uDBxx" escape STARTING at y (a backslash at an even offset of its run)?  Cheapest tests first:
+// almost every "\u" escape is preceded by something that is not a high surrogate, and the third byte says so
 template <class R>
 SJ_HD bool high_escape_at(const R& rd, uint64_t y) {
-    if (rd(y) != '\\' || rd(y + 1) != 'u') return false;
+    const uint32_t c0 = rd(y), c1 = rd(y + 1), c2 = rd(y + 2);
+    if (c0 != '\\' || c1 != 'u' || (c2 | 0x20u) != 'd') return false;
     const uint32_t v = hex4_at(rd, y + 2);
     if (v == 0xffffffffu || (v & 0xFC00u) != 0xD800u) return false;
     return (backslashes_before(rd, y) & 1u) == 0;
@@ -458,8 +460,10 @@ SJ_HD uint32_t utf8_pack(uint32_t cp, uint32_t n) {
 // half is an escape start of its own, recognised by walking the chain of high surrogates in front of it: it is a
 // second half iff an odd number of them precede it back to back (the reference does not range-check the low half,
 // so "\ud800𐀀" is pair + lone low surrogate: parse_string_amd64.s:200-229).
-template <class R>
-SJ_HD EscInfo esc_decode(const R& rd, uint64_t x) {
+// rd: the bytes at and behind x (the escape's own; may come from the shared-memory image), back: the bytes in FRONT of x
+// (always the original message: the image is patched in place as escapes are decoded)
+template <class R, class B>
+SJ_HD EscInfo esc_decode(const R& rd, const B& back, uint64_t x) {
     EscInfo r;
     r.c = 2, r.n = 1, r.bytes = 0, r.valid = true, r.second = false;
     const uint32_t e = rd(x + 1);
@@ -472,7 +476,7 @@ SJ_HD EscInfo esc_decode(const R& rd, uint64_t x) {
     {
         uint32_t k = 0;
         uint64_t y = x;
-        while (y >= 6 && high_escape_at(rd, y - 6)) {
+        while (y >= 6 && high_escape_at(back, y - 6)) {
             k++;
             y -= 6;
         }

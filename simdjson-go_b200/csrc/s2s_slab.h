@@ -81,7 +81,7 @@ SJ_HD HeadInfo head_info(W& wp, const GlobalReader& g, uint64_t T, bool in_strin
     if (mine) {
         const uint64_t x = T - back;
         if ((backslashes_before(g, x) & 1u) == 0) {  // an escape start
-            const EscInfo e = esc_decode(g, x);
+            const EscInfo e = esc_decode(g, g, x);
             if (!e.second) {
                 if (!e.valid) {
                     bad = 1;
@@ -291,7 +291,7 @@ SJ_HD void s2s_slab(W& wp, const S2sParams& p, uint32_t slab, const S2sWarpMem& 
                     const uint32_t b = pi::ctz64(e);
                     e &= e - 1;
                     const uint64_t x = block_pos + b;
-                    const EscInfo ei = esc_decode(rd, x);
+                    const EscInfo ei = esc_decode(rd, g, x);
                     if (ei.second) continue;
                     if (!ei.valid) {
                         err = 1;
@@ -303,6 +303,12 @@ SJ_HD void s2s_slab(W& wp, const S2sParams& p, uint32_t slab, const S2sWarpMem& 
                     if (block_pos + ob < step_end) {  // output in this step: un-drop its n positions
                         D &= ~range64(ob, ob + ei.n);
                         if (ob + ei.n > 64) spill &= ~(uint32_t)range64(ob > 64 ? ob - 64 : 0, ob + ei.n - 64);
+                        if (EMIT) {
+                            // the UTF-8 bytes go straight into the image, over the escape's own first bytes: nobody reads
+                            // those again (escapes in FRONT of a position are looked at in the original message only)
+                            uint8_t* img = const_cast<uint8_t*>(sbase);
+                            for (uint32_t i = 0; i < ei.n; i++) img[swz(64 * lane + ob + i)] = (uint8_t)(ei.bytes >> (8 * i));
+                        }
                     }
                 }
             }
@@ -313,6 +319,19 @@ SJ_HD void s2s_slab(W& wp, const S2sParams& p, uint32_t slab, const S2sWarpMem& 
             }
         }
         const uint64_t K = qm & ~qb & ~D;  // bytes of Strings.B, at their source positions
+        if (EMIT && (any_esc || hd.nhead)) {  // warp-uniform: the image was patched, the compaction wants the patched words
+            if (hd.nhead && lane == 0) {
+                uint8_t* img = const_cast<uint8_t*>(sbase);
+                for (uint32_t i = 0; i < hd.nhead; i++) img[swz(i)] = (uint8_t)(hd.head >> (8 * i));
+            }
+            wp.sync();
+            const uint32_t r = (lane >> 1) & 3;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const V16 q = *reinterpret_cast<const V16*>(sbase + 64 * lane + 16 * ((uint32_t)j ^ r));
+                w[4 * j + 0] = q.x, w[4 * j + 1] = q.y, w[4 * j + 2] = q.z, w[4 * j + 3] = q.w;
+            }
+        }
 
         // ---------------- E: structurals (finalize_structurals_amd64.s:19-36), events, counts ----------------
         const uint64_t brk_m = (m.open | m.close) & ~qm;
@@ -458,25 +477,6 @@ SJ_HD void s2s_slab(W& wp, const S2sParams& p, uint32_t slab, const S2sWarpMem& 
                 if (fill) wp.atomic_or_shared(st32 + ptr, lo);  // shared with the lane above
             }
             wp.sync();
-            // escapes: their UTF-8 bytes over the (meaningless) source bytes the compaction copied into their slots
-            if (any_esc) {
-                uint64_t e = Ein;
-                while (e) {
-                    const uint32_t b = pi::ctz64(e);
-                    e &= e - 1;
-                    const uint64_t x = block_pos + b;
-                    const EscInfo ei = esc_decode(rd, x);
-                    if (ei.second || !ei.valid) continue;
-                    const uint64_t op = esc_out_pos(x, ei.c, ei.n, step_end);
-                    if (op >= step_end) continue;  // the next step patches them (head_info)
-                    // op == x here: the n output slots start in this block (they may run on into the next one, where
-                    // they are kept bytes too, so their ranks are consecutive)
-                    const uint32_t rank = pi::popc64(K & below64(b));
-                    for (uint32_t i = 0; i < ei.n; i++) sm.sstage[shift + k_ex + rank + i] = (uint8_t)(ei.bytes >> (8 * i));
-                }
-            }
-            if (hd.nhead && lane == 0)
-                for (uint32_t i = 0; i < hd.nhead; i++) sm.sstage[shift + i] = (uint8_t)(hd.head >> (8 * i));
             wp.sync();
             // copy-out: head and tail bytes one by one, the 16-byte aligned middle as vectors
             {

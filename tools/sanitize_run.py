@@ -14,18 +14,21 @@ from oracle.pyoracle import Oracle
 from tests.util import load_fixture, tricky_ndjson
 
 quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
-ctx = sj.Context(0)
+ctx = sj.Context(0)          # streaming stage 2 (default with copy_strings)
+ctx_legacy = sj.Context(0)   # per-structural stage 2
+ctx_legacy.set_stage2_impl(1)
 o = Oracle("native")
 n = 0
 
 
 def same(msg, ndjson=False, copy=True):
     global n
-    rc_g, tape_g, str_g, win_g = ctx.parse(msg, ndjson=ndjson, copy_strings=copy)
     rc_o, tape_o, str_o, win_o = o.parse(msg, ndjson=ndjson, copy_strings=copy)
-    assert rc_g == rc_o and win_g == win_o, (rc_g, rc_o)
-    if rc_o == 0:
-        assert np.array_equal(tape_g, tape_o) and str_g == str_o
+    for cx in (ctx, ctx_legacy):
+        rc_g, tape_g, str_g, win_g = cx.parse(msg, ndjson=ndjson, copy_strings=copy)
+        assert rc_g == rc_o and win_g == win_o, (rc_g, rc_o)
+        if rc_o == 0:
+            assert np.array_equal(tape_g, tape_o) and str_g == str_o
     ok_g, d_g = ctx.find_structural_indices(msg, ndjson)
     ok_o, d_o = o.find_structural_indices(msg, ndjson)
     assert ok_g == ok_o and (not ok_o or np.array_equal(d_g, d_o))
