@@ -222,6 +222,9 @@ def main():
     ap.add_argument("--cpu-sample-mib", type=int, default=1024)
     ap.add_argument("--inflight", type=int, default=3, help="host-API calls kept in flight for the e2e number")
     ap.add_argument("--twitter-mib", type=int, default=1024, help="size of the twitter.json-shaped document of roofline_twitter (0: skip)")
+    ap.add_argument("--stream-gib", type=int, default=64, help="GiB pushed through sj_stream_* per GPU-SET (split over the ranks); 0: skip")
+    ap.add_argument("--stream-ring-mib", type=int, default=1024, help="size of the pinned ring of generated records each rank cycles over")
+    ap.add_argument("--stream-chunk-mib", type=int, default=256, help="chunk size of the library's stream pipeline")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs under ncu)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -437,6 +440,85 @@ def main():
     t_e2e_nc = reduce_max(time.perf_counter() - t0)
     barrier()
 
+    # ---- stream: BASELINE configs[4] as the reference runs it -- ParseNDStream (simdjson_amd64.go:116-215) -- through the
+    # LIBRARY's own pipeline (sj_stream_*: chunks cut at record boundaries, pinned staging, one context + worker per
+    # slot, ordered delivery), not through Python threads.  The records come from K0 (gen_ndjson): record g = template
+    # line g mod 1000 with Ticket := g, so every record of this rank's ring is different; `--stream-gib` GiB per GPU-set
+    # (64) are pushed by cycling over the ring. ----
+    stream_line = None
+    if args.stream_gib > 0:
+        tmpl = load_records() + b"\n"
+        ring_cap = args.stream_ring_mib << 20
+        n_rec = max(1000, (ring_cap // len(tmpl)) * 1000)
+        d_ring = torch.empty(ring_cap + (4 << 20), dtype=torch.uint8, device=dev)
+        glen = C.c_size_t(0)
+        r = L.sj_gen_ndjson_device(ctx.h, tmpl, len(tmpl), rank * n_rec, n_rec, d_ring.data_ptr(), d_ring.numel(), C.byref(glen))
+        assert r == 0, r
+        ring_len = glen.value + 1
+        d_ring[glen.value] = 0x0A  # the ring ends with a newline, so it can be pushed round and round
+        h_ring = torch.empty(ring_len, dtype=torch.uint8).pin_memory()
+        h_ring.copy_(d_ring[:ring_len])
+        torch.cuda.synchronize()
+        first = bytes(h_ring[:40].numpy().tobytes())
+        assert first.startswith(b'{"Ticket":"%010d"' % ((rank * n_rec) % 10**10)), first
+        del d_ring
+        torch.cuda.empty_cache()
+        total_push = (args.stream_gib << 30) // world
+        hs = C.c_void_p()
+        r = L.sj_stream_create(local_rank, max(2, args.inflight), args.stream_chunk_mib << 20, _lib.FLAG_COPY_STRINGS, C.byref(hs))
+        assert r == 0, r
+        res = _lib.StreamResult()
+        taken = C.c_size_t(0)
+        st = {"chunks": 0, "msg": 0, "tape": 0, "strings": 0}
+
+        def take_one():
+            rr = L.sj_stream_next(hs, C.byref(res))
+            if rr == 0:
+                st["chunks"] += 1
+                st["msg"] += res.message_len
+                st["tape"] += res.tape_len
+                st["strings"] += res.strings_len
+                L.sj_stream_release(hs, C.byref(res))
+            return rr
+
+        def push(nbytes):
+            pos, left = push.pos, nbytes
+            while left > 0:
+                n1 = min(left, ring_len - pos, 64 << 20)
+                rr = L.sj_stream_write(hs, h_ring.data_ptr() + pos, n1, C.byref(taken))
+                assert rr == 0, rr
+                pos = (pos + taken.value) % ring_len
+                left -= taken.value
+                if taken.value == 0:
+                    assert take_one() == 0
+            push.pos = pos
+
+        push.pos = 0
+        push(min(total_push, 2 * (args.stream_chunk_mib << 20)))  # warm the slots' buffers up
+        barrier()
+        t0 = time.perf_counter()
+        push(total_push)
+        while True:
+            rr = L.sj_stream_close_input(hs)
+            if rr != _lib.STREAM_BUSY:
+                break
+            assert take_one() == 0
+        assert rr == 0, rr
+        while take_one() == 0:
+            pass
+        t_stream = reduce_max(time.perf_counter() - t0)
+        barrier()
+        L.sj_stream_destroy(hs)
+        pushed = total_push + min(total_push, 2 * (args.stream_chunk_mib << 20))
+        assert abs(st["msg"] - pushed) <= 2 * st["chunks"] + ring_len, (st, pushed)  # everything pushed came back parsed (minus trimmed newlines / the tail)
+        stream_line = {"value": round(total_push * world / t_stream / 1e9, 3), "unit": "GB/s", "bytes_per_gpu": total_push,
+                       "seconds": round(t_stream, 3), "chunks_per_gpu": st["chunks"], "chunk_mib": args.stream_chunk_mib,
+                       "slots": max(2, args.inflight), "ring_mib": ring_len >> 20, "records_in_ring": n_rec,
+                       "tape_words_per_gpu": st["tape"], "string_bytes_per_gpu": st["strings"],
+                       "what": "sj_stream_* (the library's ParseNDStream): host bytes pushed with sj_stream_write, results taken in order "
+                               "from pinned slot buffers with sj_stream_next; unique records from K0 gen_ndjson; host wall clock, max over ranks"}
+        del h_ring
+
     # ---- tape consumer on the device: parseMessage + countWhere("Make", "HOND"), the reference's
     # BenchmarkNdjsonColdCountStarWithWhere (parse_json_amd64_test.go:134): host input, only two counts come back ----
     n_records = batch.count(b"\n") + 1
@@ -527,6 +609,8 @@ def main():
         }
         if roof_tw:
             line["roofline_twitter"] = roof_tw
+        if stream_line:
+            line["stream"] = stream_line
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))

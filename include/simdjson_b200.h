@@ -188,6 +188,16 @@ int sj_stream_next(sj_stream* s, sj_stream_result* res);
 int sj_stream_release(sj_stream* s, const sj_stream_result* res);
 
 /*
+ * K0: the synthetic NDJSON stream of the benchmark, generated on the device: record g is line
+ * (g mod L) of `tmpl` (L records separated by '\n', each starting with {"Ticket":"<10 digits>" -- the reference's
+ * parking-citations fixture) with the ten digits replaced by g, zero padded.  Writes records first_record ..
+ * first_record + n_records - 1 joined by '\n' into d_out (device memory, 16-byte aligned); first_record must be a
+ * multiple of L.  *out_len = bytes written (exact even on SJ_ERR_CAPACITY).
+ */
+int sj_gen_ndjson_device(sj_ctx* ctx, const uint8_t* tmpl, size_t tmpl_len, uint64_t first_record, uint64_t n_records,
+                         uint8_t* d_out, size_t cap, size_t* out_len);
+
+/*
  * Stage 1 + flatten only (findStructuralIndices, stage1_find_marks_amd64.go:41):
  * writes the concatenated uint32 index deltas the reference would hand to stage 2
  * (flatten_bits_amd64.s:26-60: delta to the previous structural, first = position+1).

@@ -19,6 +19,7 @@
 #include "stage2.cuh"
 #include "stage2_stream.cuh"
 #include "consume.cuh"
+#include "gen.cuh"
 
 using namespace sj;
 
@@ -516,6 +517,7 @@ extern "C" int sj_test_flatten_bits(sj_ctx* c, const uint64_t* masks, size_t nma
 #include "sj_parse.inl"
 #include "sj_consume.inl"
 #include "sj_stream.inl"
+#include "sj_gen.inl"
 
 #ifdef SJ_PROFILE_PHASES
 // development aid (not part of the C ABI): read / clear the per-phase cycle counters

@@ -78,6 +78,27 @@ struct sj_stream {
 
 namespace {
 
+// the one copy of the stream's bytes (caller memory -> pinned slot buffer): a single thread moves ~10 GB/s, less than the
+// PCIe link takes, so large pieces are split over a few helper threads
+void copy_in(uint8_t* dst, const uint8_t* src, size_t n) {
+    const size_t PIECE = 8u << 20;
+    if (n < 2 * PIECE) {
+        memcpy(dst, src, n);
+        return;
+    }
+    unsigned helpers = std::thread::hardware_concurrency();
+    helpers = helpers < 2 ? 1 : (helpers > 6 ? 6 : helpers);
+    size_t per = (n / helpers + 63) & ~(size_t)63;
+    std::vector<std::thread> th;
+    size_t done = 0;
+    for (unsigned i = 0; i + 1 < helpers && done + per < n; i++) {
+        th.emplace_back([=] { memcpy(dst + done, src + done, per); });
+        done += per;
+    }
+    memcpy(dst + done, src + done, n - done);
+    for (auto& t : th) t.join();
+}
+
 bool all_space(const uint8_t* p, size_t n) {
     for (size_t i = 0; i < n; i++)
         if (!ascii_space(p[i])) return false;
@@ -93,20 +114,31 @@ void stream_worker(sj_stream* s, int k) {
         if (s->stop) return;
         sl.state = SLOT_RUNNING;
         lk.unlock();
-        // parseMessage with the results left in the slot's context, then D2H into the slot's pinned buffers
+        // parseMessage: trim, upload, stage 1 + the counting half of stage 2 (one read-back: the totals size the slot's
+        // pinned output buffers), then the emitting half with tape and strings copied straight into them
         Stage2Result r2;
         memset(&r2, 0, sizeof r2);
-        int rc = parse_into_ctx(sl.ctx, reinterpret_cast<const uint8_t*>(sl.in.p), sl.in_len, s->flags, &sl.msg_off,
-                                &sl.msg_len, &r2);
+        sj_ctx* c = sl.ctx;
+        const uint8_t* msg = reinterpret_cast<const uint8_t*>(sl.in.p);
+        size_t a = 0, b = 0;
+        if (sl.in_len) trim_space(msg, sl.in_len, &a, &b);
+        sl.msg_off = a;
+        sl.msg_len = b - a;
+        int rc = SJ_OK;
+        if (b == a)
+            rc = SJ_ERR_STAGE1;
+        else if (b - a > SJ_MAX_MESSAGE)
+            rc = SJ_ERR_TOO_LARGE;
+        if (rc == SJ_OK) rc = upload_message(c, msg + a, b - a);
+        Stage1Result r1;
+        if (rc == SJ_OK) rc = front_half(c, c->msg.as<uint8_t>(), b - a, s->flags, &r1, &r2);
         if (rc == SJ_OK) rc = sl.tape.reserve((size_t)r2.tape_len * 8 + 64);
         if (rc == SJ_OK) rc = sl.strings.reserve((size_t)r2.strings_len + 64);
         if (rc == SJ_OK) {
-            sj_ctx* c = sl.ctx;
-            cudaError_t e = cudaMemcpyAsync(sl.tape.p, c->tape.p, (size_t)r2.tape_len * 8, cudaMemcpyDeviceToHost, c->stream);
-            if (e == cudaSuccess && r2.strings_len)
-                e = cudaMemcpyAsync(sl.strings.p, c->strings.p, (size_t)r2.strings_len, cudaMemcpyDeviceToHost, c->stream);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-            if (e != cudaSuccess) rc = -(1000 + (int)e);
+            const HostOut host{reinterpret_cast<uint64_t*>(sl.tape.p), (size_t)r2.tape_len, reinterpret_cast<uint8_t*>(sl.strings.p),
+                               (size_t)r2.strings_len};
+            rc = stage2_emit_any(c, nullptr, 0, nullptr, 0, ParseBases{0, 0, 0, nullptr}, &r2, &host);
+            if (rc == SJ_OK) rc = stage2_verdict(r2);
             sl.tape_len = (size_t)r2.tape_len;
             sl.strings_len = (size_t)r2.strings_len;
         }
@@ -219,7 +251,7 @@ extern "C" int sj_stream_write(sj_stream* s, const uint8_t* data, size_t len, si
         }
         if (rc == SJ_OK) {
             const size_t n = len < room ? len : room;
-            memcpy(buf + sl.in_len, data, n);
+            copy_in(buf + sl.in_len, data, n);
             sl.in_len += n;
             data += n;
             len -= n;

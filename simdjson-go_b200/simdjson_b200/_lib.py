@@ -17,7 +17,7 @@ OK, ERR_STAGE1, ERR_STAGE2, ERR_NO_DEVICE, ERR_CAPACITY, ERR_TOO_LARGE, ERR_ARGU
 # every symbol include/simdjson_b200.h declares
 EXPORTS = [
     "sj_supported", "sj_device_count", "sj_error_string", "sj_ctx_create", "sj_ctx_destroy", "sj_ctx_set_stage2_impl", "sj_ctx_set_stream", "sj_bind_to_device_numa", "sj_host_alloc",
-    "sj_host_free", "sj_trim_space", "sj_bounds", "sj_parse", "sj_parse_device", "sj_parse_nd_sharded_count", "sj_parse_nd_sharded_emit", "sj_find_structural_indices", "sj_stage1_device",
+    "sj_host_free", "sj_trim_space", "sj_bounds", "sj_parse", "sj_parse_device", "sj_gen_ndjson_device", "sj_parse_nd_sharded_count", "sj_parse_nd_sharded_emit", "sj_find_structural_indices", "sj_stage1_device",
     "sj_stage1_launch", "sj_ctx_sync", "sj_event_record", "sj_event_elapsed_ms", "sj_kernel_launches",
     "sj_test_block_masks", "sj_test_geometry", "sj_test_finalize", "sj_test_flatten_bits", "sj_test_parse_strings",
     "sj_test_parse_numbers", "sj_count_where_device", "sj_parse_count_where", "sj_stream_create", "sj_stream_destroy",
@@ -81,6 +81,8 @@ def load():
     L.sj_parse_nd_sharded_count.argtypes = [vp, vp, sz, u32, C.POINTER(ShardTotals), vp]
     L.sj_parse_nd_sharded_emit.restype = i32
     L.sj_parse_nd_sharded_emit.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64, vp, vp, sz, vp, sz]
+    L.sj_gen_ndjson_device.restype = i32
+    L.sj_gen_ndjson_device.argtypes = [vp, vp, sz, C.c_uint64, C.c_uint64, vp, sz, szp]
     L.sj_bind_to_device_numa.restype = i32
     L.sj_bind_to_device_numa.argtypes = [i32]
     L.sj_ctx_set_stream.restype = i32
