@@ -84,3 +84,24 @@ def test_foreign_device_tape(ctx, oracle):
             assert (roots.value, matches.value) == oracle.count_where(tape, strs, msg[off:off + ln], key, value)
     launches = ctx.launches()
     assert launches > 0
+
+
+def test_gen_ndjson_kernel(ctx):
+    """K0 gen_ndjson: record g = template line g mod 1000 with Ticket := g, zero padded, joined by
+    newlines -- byte for byte what this Python restatement builds, for a window that starts far into the stream"""
+    import ctypes as C
+    import torch
+    pk = load_fixture("parking-citations").strip()
+    lines = pk.split(b"\n")
+    assert len(lines) == 1000
+    for first, n in ((0, 2500), (1_234_567_000, 3001), (9_999_999_000, 1000 + 17)):
+        want = b"\n".join(l[:11] + b"%010d" % ((first + i) % 10**10) + l[21:] for i, l in ((i, lines[(first + i) % 1000]) for i in range(n)))
+        d_out = torch.zeros(len(want) + 64, dtype=torch.uint8, device="cuda:0")
+        glen = C.c_size_t(0)
+        rc = ctx.L.sj_gen_ndjson_device(ctx.h, pk, len(pk), first, n, d_out.data_ptr(), d_out.numel(), C.byref(glen))
+        assert rc == 0 and glen.value == len(want), (rc, glen.value, len(want))
+        got = d_out[: glen.value].cpu().numpy().tobytes()
+        assert got == want
+    # and the generated stream parses
+    rc, roots, matches = ctx.parse_count_where(got, b"Make", b"HOND")
+    assert rc == 0 and roots == 1017
