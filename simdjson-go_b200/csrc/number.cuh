@@ -447,4 +447,64 @@ __device__ __forceinline__ uint64_t parse_number(const uint8_t* buf, uint64_t av
     return float_tag;
 }
 
+// The common shapes in one pass:  [-] digits [ . digits ]  followed by an end-of-value byte, at most 18 digits in all,
+// no leading zero other than a lone "0" in front of the point, no exponent.  Such a number cannot hit any of the
+// special rules of parse_number.go:65-135 (leading zeros, integer overflow into float, must-have-digit, the 20-character
+// limit) or of strconv (19-digit truncation), so the result is computed directly: integers as 'l', decimals through
+// Clinger's exact case or Eisel-Lemire.  Everything else -- and the rare Eisel-Lemire "cannot decide" -- returns
+// PN_SLOW and takes parse_number() above, which stays the definition of the behaviour.
+constexpr uint64_t PN_SLOW = ~0ull;
+__device__ __forceinline__ uint64_t parse_number_fast(const uint8_t* buf, uint64_t avail, uint64_t* val) {
+    if (avail < 26) return PN_SLOW;  // (the loop below never looks past the message)
+    uint32_t i = 0;
+    const bool neg = buf[0] == '-';
+    i = neg ? 1 : 0;
+    const uint32_t first = buf[i];
+    uint64_t mant = 0;
+    uint32_t nint = 0, nfrac = 0;
+    bool dot = false;
+    uint32_t c;
+    for (;;) {
+        c = buf[i];
+        const uint32_t d = c - '0';
+        if (d <= 9u) {
+            mant = mant * 10 + d;
+            if (dot)
+                nfrac++;
+            else
+                nint++;
+        } else if (c == '.' && !dot && nint != 0) {
+            dot = true;
+        } else {
+            break;
+        }
+        i++;
+        if (i >= 24) return PN_SLOW;
+    }
+    if (nint == 0 || (dot && nfrac == 0) || nint + nfrac > 18) return PN_SLOW;
+    if (first == '0' && nint != 1) return PN_SLOW;  // leading zeros: the full rules decide
+    if (!(c == ',' || c == '}' || c == ']' || c == ' ' || c == '\t' || c == '\r' || c == '\n' || c == ':')) return PN_SLOW;
+    if (!dot) {  // ParseInt succeeds (at most 18 digits): int64, "-0" included
+        *val = neg ? (0 - mant) : mant;
+        return (uint64_t)'l' << 56;
+    }
+    const uint64_t sign = neg ? 0x8000000000000000ull : 0;
+    if (mant == 0) {
+        *val = sign;
+        return (uint64_t)'d' << 56;
+    }
+    const int e = -(int)nfrac;
+    if (mant < (1ull << 53) && e >= -22) {
+        const double P10[23] = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
+                                1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+        const double dv = __ddiv_rn((double)(long long)mant, P10[-e]);
+        *val = (uint64_t)__double_as_longlong(dv) | sign;
+        return (uint64_t)'d' << 56;
+    }
+    uint64_t b;
+    if (!eisel_lemire64(mant, e, &b)) return PN_SLOW;
+    *val = b | sign;
+    return (uint64_t)'d' << 56;
+}
+
 }  // namespace sj

@@ -763,12 +763,17 @@ __global__ void test_strings_kernel(const uint8_t* buf, const uint64_t* offs, si
     }
 }
 
-__global__ void test_numbers_kernel(const uint8_t* buf, const uint64_t* offs, size_t n, uint64_t* tag, uint64_t* val) {
+__global__ void test_numbers_kernel(const uint8_t* buf, const uint64_t* offs, size_t n, uint64_t* tag, uint64_t* val, uint64_t total) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint64_t v = 0;
     tag[i] = parse_number(buf + offs[i], offs[i + 1] - offs[i], &v);
     val[i] = v;
+    // the one-pass fast path (K2h tries it first) must agree wherever it decides at all
+    uint64_t vf = 0;
+    // (it may look at up to 24 bytes: give it the rest of the batch -- a number ends at its delimiter inside its own item)
+    const uint64_t tf = parse_number_fast(buf + offs[i], total - offs[i], &vf);
+    if (tf != PN_SLOW && (tf != tag[i] || vf != v)) tag[i] = 0xBAD0BAD0BAD0BAD0ull;
 }
 
 extern "C" int sj_test_parse_strings(sj_ctx* c, const uint8_t* buf, const uint64_t* offs, size_t n,
@@ -823,7 +828,7 @@ extern "C" int sj_test_parse_numbers(sj_ctx* c, const uint8_t* buf, const uint64
     uint64_t* d_val = k.take<uint64_t>(n);
     SJ_CUDA_CHECK(cudaMemcpyAsync(d_buf, buf, total, cudaMemcpyHostToDevice, c->stream));
     SJ_CUDA_CHECK(cudaMemcpyAsync(d_offs, offs, (n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
-    test_numbers_kernel<<<(unsigned)((n + 63) / 64), 64, 0, c->stream>>>(d_buf, d_offs, n, d_tag, d_val);
+    test_numbers_kernel<<<(unsigned)((n + 63) / 64), 64, 0, c->stream>>>(d_buf, d_offs, n, d_tag, d_val, (uint64_t)total);
     c->launches++;
     SJ_CUDA_CHECK(cudaGetLastError());
     SJ_CUDA_CHECK(cudaMemcpyAsync(tag, d_tag, n * 8, cudaMemcpyDeviceToHost, c->stream));

@@ -206,7 +206,8 @@ __global__ void __launch_bounds__(S2_THREADS) s2s_numbers_kernel(const uint8_t* 
     if (k >= count) return;
     const NumEntry e = list[k];
     uint64_t val = 0;
-    const uint64_t tag = parse_number(msg + e.pos, len - e.pos, &val);  // parse_number.go:65
+    uint64_t tag = parse_number_fast(msg + e.pos, len - e.pos, &val);
+    if (tag == PN_SLOW) tag = parse_number(msg + e.pos, len - e.pos, &val);  // parse_number.go:65
     if (tag == 0) atomicOr(error, 1u);
     tape[e.slot] = tag;
     tape[(uint64_t)e.slot + 1] = val;

@@ -529,3 +529,31 @@ def test_parse_nd_sharded_is_one_parsed_json(oracle_native, copy, world):
     assert b"".join(strs) == str_o
     for c, *_ in ranks:
         c.close()
+
+
+def test_numbers_fast_path_shapes(ctx, oracle):
+    """the one-pass fast path of K2h ([-]digits[.digits], at most 18 digits, no exponent) and its borders: the hook runs it
+    beside the full routine on every item and poisons the tag on a disagreement; the full routine is checked against the oracle"""
+    rng = np.random.default_rng(77)
+    items = []
+    for _ in range(30000):
+        nd = int(rng.integers(1, 21))
+        s = "".join(str(d) for d in rng.integers(0, 10, nd))
+        if rng.integers(0, 4):
+            s = s.lstrip("0") or "0"
+        if rng.integers(0, 3):
+            k = int(rng.integers(0, len(s) + 1))
+            s = s[:k] + "." + s[k:]
+        if rng.integers(0, 2):
+            s = "-" + s
+        items.append(s.encode() + [b",", b"]", b"}", b" ", b"\n", b":", b"\t", b"x", b"e5,", b"-"][int(rng.integers(0, 10))])
+    for s in ("0", "-0", "0.0", "-0.0", "00.5", "-00.5", "0.5", "01", "-01", "1.", ".5", "-.5", "1.5.5", "1-", "-", "12x", "9007199254740992.0",
+              "9007199254740993.0", "900719925474099.25", "0.000000000000000001", "123456789012345678", "1234567890123456789",
+              "12345678901234567.8", "999999999999999999", "-999999999999999999", "0.1", "0.2", "0.3", "2.5", "1e5", "1E5", "1+5", "+1"):
+        for term in (b",", b"]", b" "):
+            items.append(s.encode() + term)
+    items += [b"1234567890.123456," + b"   " * 10] * 3  # (pads the tail so the last real items have 26 readable bytes)
+    res = ctx.parse_numbers(items)
+    for it, (tag, val) in zip(items, res):
+        otag, oval = oracle.parse_number(it)
+        assert (tag, val) == (otag, oval), (it, hex(tag), hex(val), hex(otag), hex(oval))
