@@ -23,29 +23,45 @@ import "C"
 
 import (
 	"errors"
-	"sync"
 	"unsafe"
 )
 
-// one sj_ctx (CUDA stream + device scratch) per concurrent parse, recycled like the
-// reference recycles *ParsedJson internals (simdjson_amd64.go:46-51)
-var b200Pool = sync.Pool{New: func() any {
+// one sj_ctx (CUDA stream + device scratch) per concurrent parse, recycled like the reference
+// recycles *ParsedJson internals (simdjson_amd64.go:46-51).  A bounded free list, not a sync.Pool:
+// a context owns a CUDA stream, events, pinned memory and grow-only device scratch, so a handle
+// the pool drops must be destroyed, never just forgotten.
+var b200Free = make(chan *C.sj_ctx, 16)
+
+func b200Get() *C.sj_ctx {
+	select {
+	case h := <-b200Free:
+		return h
+	default:
+	}
 	var h *C.sj_ctx
 	if rc := C.sj_ctx_create(-1, &h); rc != C.SJ_OK {
-		return (*C.sj_ctx)(nil)
+		return nil
 	}
 	return h
-}}
+}
+
+func b200Put(h *C.sj_ctx) {
+	select {
+	case b200Free <- h:
+	default:
+		C.sj_ctx_destroy(h) // more contexts in flight than the list keeps: release the device resources now
+	}
+}
 
 // SupportedCPU reports whether the B200 path can run (simdjson_amd64.go:37).
 func SupportedCPU() bool { return C.sj_supported() != 0 }
 
 func (pj *internalParsedJson) parseMessage(msg []byte, ndjson bool) error {
-	h, _ := b200Pool.Get().(*C.sj_ctx)
+	h := b200Get()
 	if h == nil {
 		return errors.New("Host CPU does not meet target specs") // simdjson_amd64.go:43
 	}
-	defer b200Pool.Put(h)
+	defer b200Put(h)
 
 	var flags C.uint32_t
 	if ndjson {
@@ -54,25 +70,40 @@ func (pj *internalParsedJson) parseMessage(msg []byte, ndjson bool) error {
 	if pj.copyStrings {
 		flags |= C.SJ_FLAG_COPY_STRINGS
 	}
-	var tapeCap, strCap C.size_t
-	C.sj_bounds(C.size_t(len(msg)), &tapeCap, &strCap)
-	if cap(pj.Tape) < int(tapeCap) {
-		pj.Tape = make([]uint64, 0, tapeCap)
+	// Output buffers: sj_bounds() is the safe bound (16 bytes of tape per input byte) -- far more than any real
+	// document needs, so start from what is there (or an estimate in the spirit of parse_json_amd64.go:30) and
+	// let SJ_ERR_CAPACITY, which reports the exact sizes before anything is written, drive one retry.
+	if cap(pj.Tape) == 0 {
+		pj.Tape = make([]uint64, 0, len(msg)/4+1024)
 	}
-	if pj.Strings == nil || cap(pj.Strings.B) < int(strCap) {
-		pj.Strings = &TStrings{make([]byte, 0, strCap)}
+	if pj.Strings == nil {
+		pj.Strings = &TStrings{make([]byte, 0, len(msg)+64)}
 	}
 	var tapeLen, strLen, off, n C.size_t
 	var p *C.uint8_t
 	if len(msg) > 0 {
 		p = (*C.uint8_t)(unsafe.Pointer(&msg[0]))
 	}
-	tape := pj.Tape[:cap(pj.Tape)]
-	strs := pj.Strings.B[:cap(pj.Strings.B)]
-	rc := C.sj_parse(h, p, C.size_t(len(msg)), flags,
-		(*C.uint64_t)(unsafe.Pointer(unsafe.SliceData(tape))), tapeCap, &tapeLen,
-		(*C.uint8_t)(unsafe.Pointer(unsafe.SliceData(strs))), strCap, &strLen,
-		&off, &n)
+	var tape []uint64
+	var strs []byte
+	var rc C.int
+	for attempt := 0; attempt < 2; attempt++ {
+		tape = pj.Tape[:cap(pj.Tape)]
+		strs = pj.Strings.B[:cap(pj.Strings.B)]
+		rc = C.sj_parse(h, p, C.size_t(len(msg)), flags,
+			(*C.uint64_t)(unsafe.Pointer(unsafe.SliceData(tape))), C.size_t(len(tape)), &tapeLen,
+			(*C.uint8_t)(unsafe.Pointer(unsafe.SliceData(strs))), C.size_t(len(strs)), &strLen,
+			&off, &n)
+		if rc != C.SJ_ERR_CAPACITY {
+			break
+		}
+		if int(tapeLen) > cap(pj.Tape) {
+			pj.Tape = make([]uint64, 0, int(tapeLen)+int(tapeLen)/8)
+		}
+		if int(strLen) > cap(pj.Strings.B) {
+			pj.Strings.B = make([]byte, 0, int(strLen)+int(strLen)/8+64)
+		}
+	}
 	pj.Message = msg[off : off+n] // bytes.TrimSpace window (parse_json_amd64.go:55)
 	switch rc {
 	case C.SJ_OK:
@@ -96,11 +127,11 @@ func (pj *internalParsedJson) parseMessage(msg []byte, ndjson bool) error {
 // counts cross PCIe, so the call is bound by the upload of msg, not by the download of a tape
 // 1.7x its size.  This is an addition next to the drop-in path, not a replacement of it.
 func ParseAndCountWhere(msg []byte, ndjson bool, key, value string) (records, matches uint64, err error) {
-	h, _ := b200Pool.Get().(*C.sj_ctx)
+	h := b200Get()
 	if h == nil {
 		return 0, 0, errors.New("Host CPU does not meet target specs")
 	}
-	defer b200Pool.Put(h)
+	defer b200Put(h)
 	flags := C.uint32_t(C.SJ_FLAG_COPY_STRINGS)
 	if ndjson {
 		flags |= C.SJ_FLAG_NDJSON
