@@ -68,14 +68,15 @@ struct HeadInfo {
     uint32_t head;
     uint32_t bad;
 };
+// `behind`: the byte at T - 1 - lane for lanes 0..10 (asked for at the start of the slab, so its latency is long gone)
 template <class W>
-SJ_HD HeadInfo head_info(W& wp, const GlobalReader& g, uint64_t T, bool in_string) {
+SJ_HD HeadInfo head_info(W& wp, const GlobalReader& g, uint64_t T, bool in_string, uint32_t behind) {
     HeadInfo h;
     h.drop = 0, h.nhead = 0, h.head = 0, h.bad = 0;
     const uint32_t lane = wp.lane();
     uint32_t mine = 0;
     const uint64_t back = (uint64_t)lane + 1;
-    if (lane < 11 && T >= back && in_string) mine = g(T - back) == '\\' ? 1u : 0u;
+    if (lane < 11 && T >= back && in_string) mine = behind == '\\' ? 1u : 0u;
     if (!wp.any(mine != 0)) return h;  // no backslash among the last eleven bytes (or not inside a string): nothing straddles
     uint32_t drop = 0, nhead = 0, head = 0, bad = 0;
     if (mine) {
@@ -168,6 +169,13 @@ SJ_HD void s2s_slab(W& wp, const S2sParams& p, uint32_t slab, const S2sWarpMem& 
         const uint32_t i1 = have1 ? p.idx[r - back] : 0u, i2 = have2 ? p.idx[r - back - 1] : 0u;
         pc1 = have1 ? g(i1) : 0u;
         pc2 = have2 ? g(i2) : 0u;
+    }
+    // the bytes in front of each step edge (lanes 0..10: byte edge - 1 - lane), for the escapes that straddle it
+    uint32_t behind[S2S_STEPS];
+#pragma unroll
+    for (uint32_t s = 0; s < S2S_STEPS; s++) {
+        const uint64_t T = slab_start + (uint64_t)s * S2S_STEP_BYTES;
+        behind[s] = (lane < 11 && T > lane) ? g(T - 1 - lane) : 0x20u;
     }
     if (S2S_IMAGE_STEPS == S2S_STEPS) fill_image(slab_start, S2S_SLAB_BYTES);
     MsgReader rd{p.msg, p.len, sm.src, slab_start, slab_end};
@@ -280,7 +288,7 @@ SJ_HD void s2s_slab(W& wp, const S2sParams& p, uint32_t slab, const S2sWarpMem& 
         // ---------------- D: escapes inside strings -> dropped bytes ----------------
         uint64_t D = 0;
         const uint64_t Ein = E & qm;
-        const HeadInfo hd = head_info(wp, g, step_start, par_step);
+        const HeadInfo hd = head_info(wp, g, step_start, par_step, behind[s]);
         err |= hd.bad;
         const bool any_esc = wp.any(Ein != 0);
         {

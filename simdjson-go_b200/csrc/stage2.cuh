@@ -1169,6 +1169,14 @@ __global__ void __launch_bounds__(S2_THREADS) s2_ansv_kernel(AnsvLevels L, int32
     if (k >= L.n[0]) return;
     const int32_t* D = L.lv[0];
     const int32_t t = D[k];
+    if (t <= 0) {
+        // nothing in front of a bracket at depth 0 can be shallower unless an earlier close went below the top level --
+        // which the grammar check rejects anyway (a close at the top level is in no legal transition), so the
+        // answer "none" is exact for every accepted document and harmless for the others.  (Every NDJSON record
+        // opens at depth 0: without this each of them walks the whole min hierarchy to find nothing.)
+        par[k] = -1;
+        return;
+    }
     int64_t found = -1;
     {
         int64_t lo = k & ~31u;
