@@ -223,13 +223,7 @@ SJ_HD uint64_t range64(uint32_t lo, uint32_t hi) { return lo >= hi ? 0ull : belo
 constexpr uint32_t S2S_STEP_BYTES = 2048;                            // one warp pass: 32 lanes x 64 bytes
 constexpr uint32_t S2S_STEPS = 3;
 constexpr uint32_t S2S_SLAB_BYTES = S2S_STEPS * S2S_STEP_BYTES;      // == S1_SLAB_BYTES (static_assert in stage2_stream.cuh)
-// steps of the slab kept as an image in shared memory at a time: 3 = the whole slab (loaded once), 1 = one step (three
-// loads, a third of the shared memory: more warps per SM)
-#ifndef SJ_S2S_IMAGE_STEPS
-#define SJ_S2S_IMAGE_STEPS 3
-#endif
-constexpr uint32_t S2S_IMAGE_STEPS = SJ_S2S_IMAGE_STEPS;
-constexpr uint32_t S2S_IMAGE_BYTES = S2S_IMAGE_STEPS * S2S_STEP_BYTES;
+constexpr uint32_t S2S_IMAGE_BYTES = 2 * S2S_STEP_BYTES;              // two image buffers: the step at hand and the next one in flight
 constexpr uint32_t S2S_SSTAGE_BYTES = S2S_STEP_BYTES + 32;           // compacted string bytes of one step (+ alignment shift)
 #ifndef SJ_S2S_TSTAGE_WORDS
 #define SJ_S2S_TSTAGE_WORDS 640
@@ -574,7 +568,7 @@ SJ_HD uint64_t s2s_str_base(const S2sParams& p) { return p.bases_dev ? p.bases_d
 
 // per-warp working memory (shared memory on the device)
 struct S2sWarpMem {
-    uint8_t* src;        // [S2S_SLAB_BYTES] the slab, 16-byte chunks XOR-swizzled inside each 64-byte block pair (never modified)
+    uint8_t* src;        // [S2S_IMAGE_BYTES] two step images, 16-byte chunks XOR-swizzled inside each 64-byte block pair
     uint8_t* sstage;     // [S2S_SSTAGE_BYTES] compacted string bytes of the current step
     uint64_t* tstage;    // [S2S_TSTAGE_WORDS] tape words of the current step
     const uint8_t* ctab;   // [256] char_type

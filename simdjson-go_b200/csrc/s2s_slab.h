@@ -17,14 +17,11 @@ namespace sj {
 struct MsgReader {
     const uint8_t* msg;
     uint64_t len;
-    const uint8_t* src;   // slab image (swizzled per step)
-    uint64_t slab_start;
-    uint64_t slab_end;    // end of the image that holds message bytes (min(slab_start + slab bytes, len))
+    const uint8_t* src;   // image of the current step (swizzled)
+    uint64_t slab_start;  // message range the image holds: [slab_start, slab_end)
+    uint64_t slab_end;
     SJ_HD uint32_t operator()(uint64_t pos) const {
-        if (pos >= slab_start && pos < slab_end) {
-            const uint32_t o = (uint32_t)(pos - slab_start);
-            return src[(o & ~(S2S_STEP_BYTES - 1)) + swz(o & (S2S_STEP_BYTES - 1))];
-        }
+        if (pos >= slab_start && pos < slab_end) return src[swz((uint32_t)(pos - slab_start))];
         return pos < len ? msg[pos] : 0u;
     }
 };
@@ -124,35 +121,46 @@ SJ_HD uint32_t backslash_run_before_p(W& wp, const GlobalReader& g, uint64_t end
     }
 }
 
-template <class W, bool EMIT>
-SJ_HD void s2s_slab(W& wp, const S2sParams& p, uint32_t slab, const S2sWarpMem& sm) {
-    const uint32_t lane = wp.lane();
-    const uint32_t lt = (1u << lane) - 1u;
-    const uint64_t slab_start = (uint64_t)slab * S2S_SLAB_BYTES;
-    const uint64_t len16 = (p.len + 15) & ~15ull;
-    const uint64_t slab_end = slab_start + S2S_SLAB_BYTES < p.len ? slab_start + S2S_SLAB_BYTES : p.len;
-    const GlobalReader g{p.msg, p.len};
-
-    // ---- the image of the slab (or of one step of it) in shared memory: 16-byte chunks from global memory, stored
-    // XOR-swizzled per step; bytes past the end of the message read as spaces (find_structural_bits_amd64.s:167) ----
-    auto fill_image = [&](uint64_t first, uint32_t nbytes) {
-        for (uint32_t c = lane; c < nbytes / 16; c += 32) {
+// Ask for the 2 KiB step that starts at message offset `first` into the image buffer `dst` (XOR-swizzled): whole
+// 16-byte chunks inside the message travel asynchronously (LDGSTS on the device), the chunk that holds the end of the
+// message and the chunks behind it are written directly, padded with spaces (find_structural_bits_amd64.s:167).
+// first == ~0: nothing to ask for (an empty group keeps the wait's bookkeeping uniform).
+template <class W>
+SJ_HD void s2s_issue_step(W& wp, const S2sParams& p, uint64_t first, uint8_t* dst) {
+    if (first != ~0ull) {
+        const uint32_t lane = wp.lane();
+        const uint64_t len16 = (p.len + 15) & ~15ull;
+        for (uint32_t c = lane; c < S2S_STEP_BYTES / 16; c += 32) {
             const uint64_t gofs = first + 16ull * c;
-            V16 q{0x20202020u, 0x20202020u, 0x20202020u, 0x20202020u};
-            if (gofs < len16) {
-                q = *reinterpret_cast<const V16*>(p.msg + gofs);
-                if (gofs + 16 > p.len) {  // the chunk that holds the end of the message
+            uint8_t* d = dst + swz(16u * c);
+            if (gofs + 16 <= p.len) {
+                wp.async_copy16(d, p.msg + gofs);
+            } else {
+                V16 q{0x20202020u, 0x20202020u, 0x20202020u, 0x20202020u};
+                if (gofs < len16) {
+                    q = *reinterpret_cast<const V16*>(p.msg + gofs);
                     uint32_t qq[4] = {q.x, q.y, q.z, q.w};
                     for (uint32_t k = 0; k < 16; k++)
                         if (gofs + k >= p.len) qq[k >> 2] = (qq[k >> 2] & ~(0xffu << (8 * (k & 3)))) | (0x20u << (8 * (k & 3)));
                     q = V16{qq[0], qq[1], qq[2], qq[3]};
                 }
+                *reinterpret_cast<V16*>(d) = q;
             }
-            const uint32_t o = 16u * c;
-            *reinterpret_cast<V16*>(sm.src + (o & ~(S2S_STEP_BYTES - 1)) + swz(o & (S2S_STEP_BYTES - 1))) = q;
         }
-        wp.sync();
-    };
+    }
+    wp.async_commit();
+}
+
+// One slab.  `cur`: which of the two image buffers holds (will hold) the slab's first step -- the caller asked for it
+// before the call (s2s_warp_loop) -- and, on return, the one that holds the first step of `next_slab`.
+template <class W, bool EMIT>
+SJ_HD void s2s_slab(W& wp, const S2sParams& p, uint32_t slab, const S2sWarpMem& sm, uint32_t& cur, uint32_t next_slab) {
+    const uint32_t lane = wp.lane();
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint64_t slab_start = (uint64_t)slab * S2S_SLAB_BYTES;
+    const uint64_t slab_end = slab_start + S2S_SLAB_BYTES < p.len ? slab_start + S2S_SLAB_BYTES : p.len;
+    const GlobalReader g{p.msg, p.len};
+
     // what the slab needs from global memory besides its own bytes is asked for first, so that these (dependent)
     // loads are in flight under the image fill
     uint32_t par = (p.slabpar[slab / p.slabs_per_tile] >> (slab % p.slabs_per_tile)) & 1u;  // in-string state in front of the slab (stage 1's chain 1)
@@ -177,7 +185,6 @@ SJ_HD void s2s_slab(W& wp, const S2sParams& p, uint32_t slab, const S2sWarpMem& 
         const uint64_t T = slab_start + (uint64_t)s * S2S_STEP_BYTES;
         behind[s] = (lane < 11 && T > lane) ? g(T - 1 - lane) : 0x20u;
     }
-    if (S2S_IMAGE_STEPS == S2S_STEPS) fill_image(slab_start, S2S_SLAB_BYTES);
     MsgReader rd{p.msg, p.len, sm.src, slab_start, slab_end};
 
     // ---- carries into the slab ----
@@ -238,13 +245,21 @@ SJ_HD void s2s_slab(W& wp, const S2sParams& p, uint32_t slab, const S2sWarpMem& 
         if (step_start >= p.len) break;  // warp-uniform
         const uint64_t step_end = step_start + S2S_STEP_BYTES;
         const uint64_t block_pos = step_start + 64ull * lane;
-        if (S2S_IMAGE_STEPS != S2S_STEPS) {  // one step at a time
-            wp.sync();  // (the previous step's readers are done)
-            fill_image(step_start, S2S_STEP_BYTES);
-            rd.slab_start = step_start;
-            rd.slab_end = step_end < p.len ? step_end : p.len;
+        // the image pipeline: ask for the NEXT step (of this slab or of the warp's next one) into the other buffer,
+        // then wait for this step's bytes -- they were asked for one step ago
+        {
+            uint64_t nxt = step_end;
+            if (s + 1 >= S2S_STEPS || nxt >= p.len) nxt = next_slab < p.nslabs ? (uint64_t)next_slab * S2S_SLAB_BYTES : ~0ull;
+            wp.sync();  // (the readers of the buffer about to be overwritten -- the step before this one -- are done)
+            s2s_issue_step(wp, p, nxt, sm.src + (cur ^ 1u) * S2S_STEP_BYTES);
+            wp.async_wait_prev();
+            wp.sync();
         }
-        const uint8_t* sbase = sm.src + (S2S_IMAGE_STEPS == S2S_STEPS ? s * S2S_STEP_BYTES : 0);
+        const uint8_t* sbase = sm.src + cur * S2S_STEP_BYTES;
+        cur ^= 1u;
+        rd.src = sbase;
+        rd.slab_start = step_start;
+        rd.slab_end = step_end < p.len ? step_end : p.len;
 
         // ---------------- A: load + classify ----------------
         uint32_t w[16];
@@ -288,7 +303,7 @@ SJ_HD void s2s_slab(W& wp, const S2sParams& p, uint32_t slab, const S2sWarpMem& 
         // ---------------- D: escapes inside strings -> dropped bytes ----------------
         uint64_t D = 0;
         const uint64_t Ein = E & qm;
-        const HeadInfo hd = head_info(wp, g, step_start, par_step, behind[s]);
+        const HeadInfo hd = head_info(wp, g, step_start, par_step, s == 0 ? behind[0] : s == 1 ? behind[1] : behind[2]);
         err |= hd.bad;
         const bool any_esc = wp.any(Ein != 0);
         {
@@ -661,6 +676,15 @@ SJ_HD void s2s_slab(W& wp, const S2sParams& p, uint32_t slab, const S2sWarpMem& 
         run.trail = (hasq ? TRAIL_HASQ : 0u) | (trail & ~TRAIL_HASQ);
         p.agg[slab] = run;
     }
+}
+
+// What one warp does: slabs first, first + stride, ... with the image of the next step always in flight.
+template <class W, bool EMIT>
+SJ_HD void s2s_warp_loop(W& wp, const S2sParams& p, uint32_t first, uint32_t stride, const S2sWarpMem& sm) {
+    if (first >= p.nslabs) return;  // warp-uniform
+    uint32_t cur = 0;
+    s2s_issue_step(wp, p, (uint64_t)first * S2S_SLAB_BYTES, sm.src);
+    for (uint32_t slab = first; slab < p.nslabs; slab += stride) s2s_slab<W, EMIT>(wp, p, slab, sm, cur, slab + stride);
 }
 
 }  // namespace sj

@@ -419,7 +419,9 @@ static int stream_count(sj_ctx* c, const uint8_t* d_msg, size_t len, const uint3
     Stage2Result* d_res = reinterpret_cast<Stage2Result*>(c->result.as<uint8_t>() + 64);
     p.error = &d_res->error;
     SJ_CUDA_CHECK(cudaMemsetAsync(d_res, 0, sizeof(Stage2Result), c->stream));
-    const unsigned grid = (nslabs + S2S_WARPS - 1) / S2S_WARPS;
+    // persistent warps: each walks slabs w, w + W, ... with the next step's image always in flight
+    unsigned grid = (nslabs + S2S_WARPS - 1) / S2S_WARPS;
+    if (grid > (unsigned)(c->sm_count * SJ_S2S_COUNT_MIN_BLOCKS)) grid = (unsigned)(c->sm_count * SJ_S2S_COUNT_MIN_BLOCKS);
     s2s_count_kernel<<<grid, S2S_THREADS, S2S_SMEM_COUNT, c->stream>>>(p);
     s2s_scan_groups_kernel<<<ngroups, 1024, 0, c->stream>>>(p.agg, nslabs, pre, grp_sum);
     s2s_scan_top_kernel<<<1, 1024, 0, c->stream>>>(grp_sum, ngroups, grp_pre, d_res, d_totals, (uint64_t)len);
@@ -446,7 +448,8 @@ static int stream_emit(sj_ctx* c, uint64_t* d_tape, size_t tape_cap, uint8_t* d_
     const Stage2Result tot = pd->tot;
     const uint8_t* d_msg = p.msg;
     const size_t len = p.len;
-    const unsigned grid = (p.nslabs + S2S_WARPS - 1) / S2S_WARPS;
+    unsigned grid = (p.nslabs + S2S_WARPS - 1) / S2S_WARPS;
+    if (grid > (unsigned)(c->sm_count * SJ_S2S_EMIT_MIN_BLOCKS)) grid = (unsigned)(c->sm_count * SJ_S2S_EMIT_MIN_BLOCKS);
     Stage2Result* d_res = reinterpret_cast<Stage2Result*>(c->result.as<uint8_t>() + 64);
     Stage2Result* h_res = reinterpret_cast<Stage2Result*>(reinterpret_cast<uint8_t*>(c->host_result) + 64);
     int rc;

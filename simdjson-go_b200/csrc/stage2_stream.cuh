@@ -55,6 +55,12 @@ struct DevWarp {
     __device__ __forceinline__ void sync() { __syncwarp(); }
     __device__ __forceinline__ void atomic_and(uint32_t* p, uint32_t v) { atomicAnd(p, v); }
     __device__ __forceinline__ void atomic_or(uint32_t* p, uint32_t v) { atomicOr(p, v); }
+    // LDGSTS: 16 bytes global -> shared without a register round trip; .ca keeps the line in L1 for the byte look-ups
+    __device__ __forceinline__ void async_copy16(void* dst, const void* src) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+    }
+    __device__ __forceinline__ void async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+    __device__ __forceinline__ void async_wait_prev() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
     __device__ __forceinline__ void atomic_or_shared(uint32_t* p, uint32_t v) {
         asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
     }
@@ -81,8 +87,6 @@ __global__ void __launch_bounds__(S2S_THREADS, SJ_S2S_COUNT_MIN_BLOCKS) s2s_coun
     s2s_fill_tables(tabs);
     __syncthreads();
     const uint32_t warp = threadIdx.x >> 5;
-    const uint32_t slab = blockIdx.x * S2S_WARPS + warp;
-    if (slab >= p.nslabs) return;  // warp-uniform
     S2sWarpMem sm;
     sm.src = s2s_smem + (size_t)warp * S2S_WARP_SMEM_COUNT;
     sm.sstage = nullptr;
@@ -91,7 +95,7 @@ __global__ void __launch_bounds__(S2S_THREADS, SJ_S2S_COUNT_MIN_BLOCKS) s2s_coun
     sm.oktab = tabs.oktab;
     sm.cmptab = tabs.cmptab;
     DevWarp wp;
-    s2s_slab<DevWarp, false>(wp, p, slab, sm);
+    s2s_warp_loop<DevWarp, false>(wp, p, blockIdx.x * S2S_WARPS + warp, gridDim.x * S2S_WARPS, sm);
 }
 
 __global__ void __launch_bounds__(S2S_THREADS, SJ_S2S_EMIT_MIN_BLOCKS) s2s_emit_kernel(const S2sParams p) {
@@ -100,8 +104,6 @@ __global__ void __launch_bounds__(S2S_THREADS, SJ_S2S_EMIT_MIN_BLOCKS) s2s_emit_
     s2s_fill_tables(tabs);
     __syncthreads();
     const uint32_t warp = threadIdx.x >> 5;
-    const uint32_t slab = blockIdx.x * S2S_WARPS + warp;
-    if (slab >= p.nslabs) return;  // warp-uniform
     S2sWarpMem sm;
     uint8_t* base = s2s_smem + (size_t)warp * S2S_WARP_SMEM_EMIT;
     sm.src = base;
@@ -111,7 +113,7 @@ __global__ void __launch_bounds__(S2S_THREADS, SJ_S2S_EMIT_MIN_BLOCKS) s2s_emit_
     sm.oktab = tabs.oktab;
     sm.cmptab = tabs.cmptab;
     DevWarp wp;
-    s2s_slab<DevWarp, true>(wp, p, slab, sm);
+    s2s_warp_loop<DevWarp, true>(wp, p, blockIdx.x * S2S_WARPS + warp, gridDim.x * S2S_WARPS, sm);
 }
 
 // ---------------------------------------------------------------------------------

@@ -106,6 +106,9 @@ struct FiberWarp {
     void atomic_and(uint32_t* p, uint32_t v) { *p &= v; }
     void atomic_or(uint32_t* p, uint32_t v) { *p |= v; }
     void atomic_or_shared(uint32_t* p, uint32_t v) { *p |= v; }
+    void async_copy16(void* dst, const void* src) { memcpy(dst, src, 16); }  // (immediately: the emulation has no latency to hide)
+    void async_commit() {}
+    void async_wait_prev() {}
 };
 
 struct Tables {
@@ -146,7 +149,7 @@ extern "C" int s2s_emu_parse(const uint8_t* msg, size_t len, int ndjson, const u
         }
     }
     std::vector<SlabAgg> agg(nslabs), pre(nslabs), grp_pre((nslabs + 1023) / 1024 + 1);
-    std::vector<uint8_t> src(S2S_SLAB_BYTES + 64), sstage(S2S_SSTAGE_BYTES + 64);
+    std::vector<uint8_t> src(S2S_IMAGE_BYTES + 64), sstage(S2S_SSTAGE_BYTES + 64);
     std::vector<uint64_t> tstage(S2S_TSTAGE_WORDS + 8);
     uint32_t error = 0;
     S2sParams p;
@@ -173,7 +176,8 @@ extern "C" int s2s_emu_parse(const uint8_t* msg, size_t len, int ndjson, const u
     sm.cmptab = T.cmptab;
     FiberWarp W;
     // ---- K2p ----
-    for (uint32_t s = 0; s < nslabs; s++) W.run([&](FiberWarp& w) { s2s_slab<FiberWarp, false>(w, p, s, sm); });
+    // (three "warps" of a stride-3 grid, so that the hand-over of the image pipeline from slab to slab is exercised)
+    for (uint32_t f = 0; f < 3; f++) W.run([&](FiberWarp& w) { s2s_warp_loop<FiberWarp, false>(w, p, f, 3, sm); });
     // ---- K2q: exclusive scan in groups of 1024 + exclusive scan of the group totals ----
     SlabAgg grand = agg_zero();
     for (uint32_t g0 = 0, gi = 0; g0 < nslabs; g0 += 1024, gi++) {
@@ -206,7 +210,7 @@ extern "C" int s2s_emu_parse(const uint8_t* msg, size_t len, int ndjson, const u
     p.rootpos = rootpos.data();
     p.numlist = numlist.data();
     // ---- K2r ----
-    for (uint32_t s = 0; s < nslabs; s++) W.run([&](FiberWarp& w) { s2s_slab<FiberWarp, true>(w, p, s, sm); });
+    for (uint32_t f = 0; f < 3; f++) W.run([&](FiberWarp& w) { s2s_warp_loop<FiberWarp, true>(w, p, f, 3, sm); });
     if (collectives) *collectives = W.collectives;
     for (uint32_t i = 0; i < grand.num; i++) {
         num_pos[i] = numlist[i].pos;
