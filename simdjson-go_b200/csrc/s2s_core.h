@@ -431,15 +431,19 @@ SJ_HD uint32_t backslashes_before(const R& rd, uint64_t x) {
     while (x > k && rd(x - 1 - k) == '\\') k++;
     return k;
 }
-// is there a "\uD8xx".."\uDBxx" escape STARTING at y (a backslash at an even offset of its run)?  Cheapest tests first:
-// almost every "\u" escape is preceded by something that is not a high surrogate, and the third byte says so
-template <class R>
-SJ_HD bool high_escape_at(const R& rd, uint64_t y) {
-    const uint32_t c0 = rd(y), c1 = rd(y + 1), c2 = rd(y + 2);
+// is there a "\uD8xx".."\uDBxx" escape STARTING at y (a backslash at an even offset of its run)?  Cheapest test first:
+// almost every "\u" escape is preceded by something that is not a high surrogate, and its third byte says so.  `near`
+// may be the shared-memory image, which earlier escapes have patched in place: they put their output at the END of
+// their own bytes (esc_out_pos), so the first three bytes of a 6-byte escape -- and all of the first half of a pair --
+// still read as in the message; everything beyond the quick test is read from the message itself (`far`).
+template <class N, class F>
+SJ_HD bool high_escape_at(const N& near, const F& far, uint64_t y) {
+    const uint32_t c0 = near(y), c1 = near(y + 1), c2 = near(y + 2);
     if (c0 != '\\' || c1 != 'u' || (c2 | 0x20u) != 'd') return false;
-    const uint32_t v = hex4_at(rd, y + 2);
+    if (far(y) != '\\' || far(y + 1) != 'u') return false;
+    const uint32_t v = hex4_at(far, y + 2);
     if (v == 0xffffffffu || (v & 0xFC00u) != 0xD800u) return false;
-    return (backslashes_before(rd, y) & 1u) == 0;
+    return (backslashes_before(far, y) & 1u) == 0;
 }
 
 SJ_HD uint32_t utf8_pack(uint32_t cp, uint32_t n) {
@@ -454,10 +458,10 @@ SJ_HD uint32_t utf8_pack(uint32_t cp, uint32_t n) {
 // half is an escape start of its own, recognised by walking the chain of high surrogates in front of it: it is a
 // second half iff an odd number of them precede it back to back (the reference does not range-check the low half,
 // so "\ud800𐀀" is pair + lone low surrogate: parse_string_amd64.s:200-229).
-// rd: the bytes at and behind x (the escape's own; may come from the shared-memory image), back: the bytes in FRONT of x
-// (always the original message: the image is patched in place as escapes are decoded)
+// rd: the escape's own bytes and the quick look at what precedes it (may be the shared-memory image, patched in place
+// by the escapes in front of x -- see high_escape_at); far: the original message
 template <class R, class B>
-SJ_HD EscInfo esc_decode(const R& rd, const B& back, uint64_t x) {
+SJ_HD EscInfo esc_decode(const R& rd, const B& far, uint64_t x) {
     EscInfo r;
     r.c = 2, r.n = 1, r.bytes = 0, r.valid = true, r.second = false;
     const uint32_t e = rd(x + 1);
@@ -470,7 +474,7 @@ SJ_HD EscInfo esc_decode(const R& rd, const B& back, uint64_t x) {
     {
         uint32_t k = 0;
         uint64_t y = x;
-        while (y >= 6 && high_escape_at(back, y - 6)) {
+        while (y >= 6 && high_escape_at(rd, far, y - 6)) {
             k++;
             y -= 6;
         }
@@ -517,13 +521,11 @@ SJ_HD EscInfo esc_decode(const R& rd, const B& back, uint64_t x) {
     return r;
 }
 
-// Where the produced bytes of the escape at x live among its c source bytes (the rest is dropped from Strings.B):
-// at the escape's first n positions -- unless the escape straddles the end of its 2 KiB step and fewer than n of
-// its bytes are in front of that edge, then at the first n positions behind the edge, so that no escape ever has
-// output on both sides of a step (each step compacts and patches its own bytes only).
-SJ_HD uint64_t esc_out_pos(uint64_t x, uint32_t c, uint32_t n, uint64_t step_end) {
-    return (x + c > step_end && (uint64_t)n > step_end - x) ? step_end : x;
-}
+// Where the produced bytes of the escape at x live among its c source bytes (the rest is dropped from Strings.B): at
+// the escape's LAST n positions -- never over the first three bytes of a 6-byte escape nor over any byte of the first
+// half or the "\u" of the second half of a pair, which later escapes (and the second half itself) still look at.  When
+// the escape straddles the end of its 2 KiB step, each side patches the positions that fall into its own image.
+SJ_HD uint64_t esc_out_pos(uint64_t x, uint32_t c, uint32_t n) { return x + c - n; }
 
 // ---------------------------------------------------------------------------------
 // parameters / outputs

@@ -62,6 +62,7 @@ SJ_HD void mark_range(uint64_t& m, uint32_t& spill, uint32_t lo, uint32_t hi) {
 struct HeadInfo {
     uint32_t drop;
     uint32_t nhead;
+    uint32_t hpos;   // offset of the head bytes behind the edge
     uint32_t head;
     uint32_t bad;
 };
@@ -69,13 +70,13 @@ struct HeadInfo {
 template <class W>
 SJ_HD HeadInfo head_info(W& wp, const GlobalReader& g, uint64_t T, bool in_string, uint32_t behind) {
     HeadInfo h;
-    h.drop = 0, h.nhead = 0, h.head = 0, h.bad = 0;
+    h.drop = 0, h.nhead = 0, h.hpos = 0, h.head = 0, h.bad = 0;
     const uint32_t lane = wp.lane();
     uint32_t mine = 0;
     const uint64_t back = (uint64_t)lane + 1;
     if (lane < 11 && T >= back && in_string) mine = behind == '\\' ? 1u : 0u;
     if (!wp.any(mine != 0)) return h;  // no backslash among the last eleven bytes (or not inside a string): nothing straddles
-    uint32_t drop = 0, nhead = 0, head = 0, bad = 0;
+    uint32_t drop = 0, nhead = 0, hpos = 0, head = 0, bad = 0;
     if (mine) {
         const uint64_t x = T - back;
         if ((backslashes_before(g, x) & 1u) == 0) {  // an escape start
@@ -85,12 +86,14 @@ SJ_HD HeadInfo head_info(W& wp, const GlobalReader& g, uint64_t T, bool in_strin
                     bad = 1;
                 } else if (x + e.c > T) {
                     const uint32_t over = (uint32_t)(x + e.c - T);  // bytes of the escape at T..
-                    if (esc_out_pos(x, e.c, e.n, T) == T) {
-                        nhead = e.n;
-                        head = e.bytes;
-                        drop = (uint32_t)range64(e.n, over);
-                    } else {
-                        drop = (uint32_t)range64(0, over);
+                    const uint64_t op = esc_out_pos(x, e.c, e.n);
+                    drop = (uint32_t)range64(0, over);
+                    const uint32_t k0 = op < T ? (uint32_t)(T - op) : 0u;  // output bytes in front of the edge (patched there)
+                    if (k0 < e.n) {
+                        nhead = e.n - k0;
+                        hpos = op < T ? 0u : (uint32_t)(op - T);
+                        head = e.bytes >> (8 * k0);
+                        drop &= ~(uint32_t)range64(hpos, hpos + nhead);
                     }
                 }
             }
@@ -101,6 +104,7 @@ SJ_HD HeadInfo head_info(W& wp, const GlobalReader& g, uint64_t T, bool in_strin
     const uint32_t pick = have ? (uint32_t)(pi::ctz64(have)) : 0;  // lanes count backwards from the edge: the nearest start
     h.drop = have ? wp.shfl(drop, pick) : 0;
     h.nhead = have ? wp.shfl(nhead, pick) : 0;
+    h.hpos = have ? wp.shfl(hpos, pick) : 0;
     h.head = have ? wp.shfl(head, pick) : 0;
     h.bad = wp.any(bad != 0) ? 1u : 0u;
     return h;
@@ -322,15 +326,16 @@ SJ_HD void s2s_slab(W& wp, const S2sParams& p, uint32_t slab, const S2sWarpMem& 
                     }
                     // all c source bytes are dropped except the n that hold the output (esc_out_pos)
                     mark_range(D, spill, b, b + ei.c);
-                    const uint32_t ob = (uint32_t)(esc_out_pos(x, ei.c, ei.n, step_end) - block_pos);
-                    if (block_pos + ob < step_end) {  // output in this step: un-drop its n positions
+                    const uint32_t ob = (uint32_t)(esc_out_pos(x, ei.c, ei.n) - block_pos);
+                    {   // un-drop the n output positions (what lies behind the step's end is the next step's business)
                         D &= ~range64(ob, ob + ei.n);
                         if (ob + ei.n > 64) spill &= ~(uint32_t)range64(ob > 64 ? ob - 64 : 0, ob + ei.n - 64);
                         if (EMIT) {
-                            // the UTF-8 bytes go straight into the image, over the escape's own first bytes: nobody reads
-                            // those again (escapes in FRONT of a position are looked at in the original message only)
+                            // the UTF-8 bytes go straight into the image, over the escape's own LAST bytes: what a later
+                            // escape's quick look-behind reads of this one (its first three bytes) stays as it was
                             uint8_t* img = const_cast<uint8_t*>(sbase);
-                            for (uint32_t i = 0; i < ei.n; i++) img[swz(64 * lane + ob + i)] = (uint8_t)(ei.bytes >> (8 * i));
+                            for (uint32_t i = 0; i < ei.n; i++)
+                                if (64 * lane + ob + i < S2S_STEP_BYTES) img[swz(64 * lane + ob + i)] = (uint8_t)(ei.bytes >> (8 * i));
                         }
                     }
                 }
@@ -345,7 +350,7 @@ SJ_HD void s2s_slab(W& wp, const S2sParams& p, uint32_t slab, const S2sWarpMem& 
         if (EMIT && (any_esc || hd.nhead)) {  // warp-uniform: the image was patched, the compaction wants the patched words
             if (hd.nhead && lane == 0) {
                 uint8_t* img = const_cast<uint8_t*>(sbase);
-                for (uint32_t i = 0; i < hd.nhead; i++) img[swz(i)] = (uint8_t)(hd.head >> (8 * i));
+                for (uint32_t i = 0; i < hd.nhead; i++) img[swz(hd.hpos + i)] = (uint8_t)(hd.head >> (8 * i));
             }
             wp.sync();
             const uint32_t r = (lane >> 1) & 3;

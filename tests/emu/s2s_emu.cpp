@@ -34,14 +34,25 @@ struct FiberWarp {
     long collectives = 0;
     std::function<void(FiberWarp&)> body;
 
+    // the order in which the lanes run between two collectives: ascending, or (-DS2S_EMU_REVERSE) descending -- code that
+    // is correct on a GPU must not care, so the suite is run both ways
+#ifdef S2S_EMU_REVERSE
+    static int first_lane() { return N - 1; }
+    static int next_lane(int me) { return (me + N - 1) % N; }
+    static bool is_last(int me) { return me == 0; }
+#else
+    static int first_lane() { return 0; }
+    static int next_lane(int me) { return (me + 1) % N; }
+    static bool is_last(int me) { return me == N - 1; }
+#endif
     static void entry() {
         FiberWarp* w = g_warp;
         w->body(*w);
         const int me = w->cur;
         w->done[me] = true;
-        if (me + 1 < N) {
-            w->cur = me + 1;
-            swapcontext(&w->ctx[me], &w->ctx[me + 1]);
+        if (!is_last(me)) {
+            w->cur = next_lane(me);
+            swapcontext(&w->ctx[me], &w->ctx[w->cur]);
         } else {
             swapcontext(&w->ctx[me], &w->main_ctx);
         }
@@ -59,8 +70,8 @@ struct FiberWarp {
             done[i] = false;
             phase[i] = 0;
         }
-        cur = 0;
-        swapcontext(&main_ctx, &ctx[0]);
+        cur = first_lane();
+        swapcontext(&main_ctx, &ctx[cur]);
         for (int i = 0; i < N; i++)
             if (!done[i]) {
                 fprintf(stderr, "s2s_emu: lane %d did not finish (non-uniform collectives)\n", i);
@@ -72,7 +83,7 @@ struct FiberWarp {
         const int me = cur, ph = phase[me];
         slot[ph][me] = v;
         phase[me] ^= 1;
-        const int nx = (me + 1) % N;
+        const int nx = next_lane(me);
         if (done[nx]) {
             fprintf(stderr, "s2s_emu: lane %d waits in a collective that lane %d never reached\n", me, nx);
             abort();

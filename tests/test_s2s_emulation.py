@@ -135,3 +135,19 @@ def test_fuzz_corpus_sample(oracle_native, which, limit):
             same_as_oracle(oracle_native, data, True)
         n += 1
     assert n > 300
+
+
+def test_lane_order_does_not_matter():
+    """the fibers of the emulated warp run in ascending lane order between two collectives; correct GPU code cannot depend on
+    that (escapes are patched into the shared image in place while other lanes still read it), so the edge and escape
+    cases run once more with the lanes in DESCENDING order (-DS2S_EMU_REVERSE build of the emulator)"""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("S2S_EMU_FLAGS"):
+        pytest.skip("already a variant build")
+    env = dict(os.environ, S2S_EMU_FLAGS="-DS2S_EMU_REVERSE")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "pytest", "tests/test_s2s_emulation.py", "-x", "-q", "-k",
+                          "escapes or strings_across or twitterescaped or ndjson or golden"], cwd=root, env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:]
