@@ -182,13 +182,10 @@ SJ_HD void s2s_slab(W& wp, const S2sParams& p, uint32_t slab, const S2sWarpMem& 
         pc1 = have1 ? g(i1) : 0u;
         pc2 = have2 ? g(i2) : 0u;
     }
-    // the bytes in front of each step edge (lanes 0..10: byte edge - 1 - lane), for the escapes that straddle it
-    uint32_t behind[S2S_STEPS];
-#pragma unroll
-    for (uint32_t s = 0; s < S2S_STEPS; s++) {
-        const uint64_t T = slab_start + (uint64_t)s * S2S_STEP_BYTES;
-        behind[s] = (lane < 11 && T > lane) ? g(T - 1 - lane) : 0x20u;
-    }
+    // the bytes in front of the slab (lanes 0..10: byte slab_start - 1 - lane), for an escape that straddles its start
+    const uint32_t behind0 = (lane < 11 && slab_start > lane) ? g(slab_start - 1 - lane) : 0x20u;
+    HeadInfo hd_next;
+    hd_next.drop = 0, hd_next.nhead = 0, hd_next.hpos = 0, hd_next.head = 0, hd_next.bad = 0;
     MsgReader rd{p.msg, p.len, sm.src, slab_start, slab_end};
 
     // ---- carries into the slab ----
@@ -307,11 +304,17 @@ SJ_HD void s2s_slab(W& wp, const S2sParams& p, uint32_t slab, const S2sWarpMem& 
         // ---------------- D: escapes inside strings -> dropped bytes ----------------
         uint64_t D = 0;
         const uint64_t Ein = E & qm;
-        const HeadInfo hd = head_info(wp, g, step_start, par_step, s == 0 ? behind[0] : s == 1 ? behind[1] : behind[2]);
+        // what an escape that starts in front of this step leaves at its head: inside the slab the previous step saw it
+        // and hands it over (hd_next); at the start of a slab -- another warp owns what precedes -- it is worked out
+        // from the message (head_info)
+        HeadInfo hd = hd_next;
+        if (s == 0) hd = head_info(wp, g, step_start, par_step, behind0);
         err |= hd.bad;
+        hd_next.drop = 0, hd_next.nhead = 0, hd_next.hpos = 0, hd_next.head = 0, hd_next.bad = 0;
         const bool any_esc = wp.any(Ein != 0);
         {
             uint32_t spill = 0;
+            uint32_t st_drop = 0, st_nhead = 0, st_hpos = 0, st_head = 0;  // this lane's escape that runs past the end of the step
             if (any_esc) {
                 uint64_t e = Ein;
                 while (e) {
@@ -327,6 +330,18 @@ SJ_HD void s2s_slab(W& wp, const S2sParams& p, uint32_t slab, const S2sWarpMem& 
                     // all c source bytes are dropped except the n that hold the output (esc_out_pos)
                     mark_range(D, spill, b, b + ei.c);
                     const uint32_t ob = (uint32_t)(esc_out_pos(x, ei.c, ei.n) - block_pos);
+                    if (x + ei.c > step_end) {  // runs past the end of the step: the same bookkeeping head_info does
+                        const uint32_t over = (uint32_t)(x + ei.c - step_end);
+                        const uint64_t op = block_pos + ob;
+                        const uint32_t k0 = op < step_end ? (uint32_t)(step_end - op) : 0u;
+                        st_drop = (uint32_t)range64(0, over);
+                        if (k0 < ei.n) {
+                            st_nhead = ei.n - k0;
+                            st_hpos = op < step_end ? 0u : (uint32_t)(op - step_end);
+                            st_head = ei.bytes >> (8 * k0);
+                            st_drop &= ~(uint32_t)range64(st_hpos, st_hpos + st_nhead);
+                        }
+                    }
                     {   // un-drop the n output positions (what lies behind the step's end is the next step's business)
                         D &= ~range64(ob, ob + ei.n);
                         if (ob + ei.n > 64) spill &= ~(uint32_t)range64(ob > 64 ? ob - 64 : 0, ob + ei.n - 64);
@@ -344,6 +359,16 @@ SJ_HD void s2s_slab(W& wp, const S2sParams& p, uint32_t slab, const S2sWarpMem& 
                 uint32_t spin = wp.shfl_up(spill, 1);
                 if (lane == 0) spin = hd.drop;
                 D |= (uint64_t)spin;
+            }
+            if (any_esc) {  // (at most one escape straddles the end of the step in a valid document)
+                const uint32_t have = wp.ballot(st_drop != 0 || st_nhead != 0);
+                if (have) {
+                    const uint32_t pick = 31 - pi::clz32(have);
+                    hd_next.drop = wp.shfl(st_drop, pick);
+                    hd_next.nhead = wp.shfl(st_nhead, pick);
+                    hd_next.hpos = wp.shfl(st_hpos, pick);
+                    hd_next.head = wp.shfl(st_head, pick);
+                }
             }
         }
         const uint64_t K = qm & ~qb & ~D;  // bytes of Strings.B, at their source positions
