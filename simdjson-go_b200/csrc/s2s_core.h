@@ -576,7 +576,16 @@ struct S2sWarpMem {
     const uint8_t* ctab;   // [256] char_type
     const uint8_t* oktab;  // [256] transition_mask(p, c) at [p * 16 + c]
     const uint32_t* cmptab;  // [16] compress_sel(m) | popcount(m) << 16
+    const uint8_t* hextab;   // [256] digit_to_val for hex digits, 0x80 for anything that makes a \uXXXX escape invalid
 };
+// digit_to_val_p with the raw quote and every non-digit folded into one "invalid" code (see hex4_at)
+SJ_HDC uint32_t hex_code(uint32_t c) {
+    return c == '"' ? 0x80u
+           : c < 0x30 ? 0u
+           : c <= '9' ? c - '0'
+           : ((c | 0x20u) >= 'a' && (c | 0x20u) <= 'f' && c >= 'A' && c < 0x80) ? (c | 0x20u) - 'a' + 10u
+                                                                                 : 0x80u;
+}
 
 // byte offset of message byte `o` of a step inside the swizzled step image: the four 16-byte chunks of block b are
 // stored at chunk slots (j ^ ((b >> 1) & 3)) -- the pattern of a 64-byte TMA swizzle -- so that lane b reading its

@@ -56,6 +56,36 @@ SJ_HD void mark_range(uint64_t& m, uint32_t& spill, uint32_t lo, uint32_t hi) {
     }
 }
 
+// esc_decode for the common case, straight from the step image: the escape's six bytes and the three bytes six in
+// front of it each lie inside one 16-byte chunk of the image (so one swizzled address + immediate offsets reaches
+// them), the escape is not a high surrogate and what precedes it does not look like one.  Returns false when it does
+// not apply -- esc_decode (s2s_core.h) is the definition and takes those.
+SJ_HD bool esc_decode_fast(const uint8_t* img, uint32_t o, uint32_t step_len, const uint8_t* hextab, EscInfo& r) {
+    if ((o & 15u) > 10u || o + 6 > step_len || o < 6 || ((o - 6) & 15u) > 13u) return false;
+    const uint8_t* b = img + swz(o);
+    const uint32_t e = b[1];
+    const uint8_t* y = img + swz(o - 6);
+    if (y[0] == '\\' && y[1] == 'u' && (y[2] | 0x20u) == 'd') return false;  // may be the low half of a pair: the full rules decide
+    r.second = false;
+    r.valid = true;
+    if (e != 'u') {
+        const uint32_t m = escape_map_p(e);
+        r.c = 2, r.n = 1, r.bytes = m, r.valid = m != 0;
+        return true;
+    }
+    const uint32_t h0 = hextab[b[2]], h1 = hextab[b[3]], h2 = hextab[b[4]], h3 = hextab[b[5]];
+    r.c = 6, r.n = 1, r.bytes = 0;
+    if ((h0 | h1 | h2 | h3) & 0x80u) {
+        r.valid = false;
+        return true;
+    }
+    const uint32_t cp = (h0 << 12) | (h1 << 8) | (h2 << 4) | h3;
+    if ((cp & 0xFC00u) == 0xD800u) return false;  // high surrogate: pair logic
+    r.n = cp < 0x80u ? 1u : cp < 0x800u ? 2u : 3u;
+    r.bytes = utf8_pack(cp, r.n);
+    return true;
+}
+
 // What an escape that starts IN FRONT of position T (a step start) leaves behind it: `drop` = the bytes at T.. that
 // belong to it and carry no output, `nhead` / `head` = its UTF-8 bytes when they live behind the edge (esc_out_pos).
 // Lanes 0..10 each test one of the eleven positions in front of T (a pair is 12 bytes long); original bytes only.
@@ -321,7 +351,17 @@ SJ_HD void s2s_slab(W& wp, const S2sParams& p, uint32_t slab, const S2sWarpMem& 
                     const uint32_t b = pi::ctz64(e);
                     e &= e - 1;
                     const uint64_t x = block_pos + b;
-                    const EscInfo ei = esc_decode(rd, g, x);
+                    EscInfo ei;
+                    if (!esc_decode_fast(sbase, 64 * lane + b, (uint32_t)(rd.slab_end - rd.slab_start), sm.hextab, ei)) ei = esc_decode(rd, g, x);
+#ifdef S2S_EMU_CHECK
+                    {   // (emulation builds: the fast path agrees with the definition wherever it applies)
+                        EscInfo chk;
+                        if (esc_decode_fast(sbase, 64 * lane + b, (uint32_t)(rd.slab_end - rd.slab_start), sm.hextab, chk)) {
+                            const EscInfo ref = esc_decode(rd, g, x);
+                            if (chk.valid != ref.valid || chk.second != ref.second || (ref.valid && !ref.second && (chk.c != ref.c || chk.n != ref.n || chk.bytes != ref.bytes))) err = 1;
+                        }
+                    }
+#endif
                     if (ei.second) continue;
                     if (!ei.valid) {
                         err = 1;
