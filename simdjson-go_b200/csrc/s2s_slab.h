@@ -56,6 +56,12 @@ SJ_HD void mark_range(uint64_t& m, uint32_t& spill, uint32_t lo, uint32_t hi) {
     }
 }
 
+// (measured on a B200: SLOWER than esc_decode -- twitterescaped 65.7 -> 56.7 GB/s: the kernels are bound by dependent
+// latencies, not by instruction count, and the table look-ups chain two shared-memory loads per digit.  Kept behind
+// SJ_S2S_ESC_FAST = 0 as a measured dead end.)
+#ifndef SJ_S2S_ESC_FAST
+#define SJ_S2S_ESC_FAST 0
+#endif
 // esc_decode for the common case, straight from the step image: the escape's six bytes and the three bytes six in
 // front of it each lie inside one 16-byte chunk of the image (so one swizzled address + immediate offsets reaches
 // them), the escape is not a high surrogate and what precedes it does not look like one.  Returns false when it does
@@ -352,7 +358,11 @@ SJ_HD void s2s_slab(W& wp, const S2sParams& p, uint32_t slab, const S2sWarpMem& 
                     e &= e - 1;
                     const uint64_t x = block_pos + b;
                     EscInfo ei;
+#if SJ_S2S_ESC_FAST
                     if (!esc_decode_fast(sbase, 64 * lane + b, (uint32_t)(rd.slab_end - rd.slab_start), sm.hextab, ei)) ei = esc_decode(rd, g, x);
+#else
+                    ei = esc_decode(rd, g, x);
+#endif
 #ifdef S2S_EMU_CHECK
                     {   // (emulation builds: the fast path agrees with the definition wherever it applies)
                         EscInfo chk;
