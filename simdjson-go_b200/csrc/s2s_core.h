@@ -576,8 +576,11 @@ struct S2sWarpMem {
     const uint8_t* ctab;   // [256] char_type
     const uint8_t* oktab;  // [256] transition_mask(p, c) at [p * 16 + c]
     const uint32_t* cmptab;  // [16] compress_sel(m) | popcount(m) << 16
-    const uint8_t* hextab;   // [256] digit_to_val for hex digits, 0x80 for anything that makes a \uXXXX escape invalid
+    const uint8_t* hextab;   // [256] hex_code
+    uint8_t* esc;            // [S2S_ESC_SCRATCH] escape positions + decode results of a step (K2r: the tape staging area, idle then)
 };
+constexpr uint32_t S2S_ESC_CAP = 256;                        // escapes of a step decoded by the balanced scheme
+constexpr uint32_t S2S_ESC_SCRATCH = S2S_ESC_CAP * (2 + 8);  // u16 position + u64 result each
 // digit_to_val_p with the raw quote and every non-digit folded into one "invalid" code (see hex4_at)
 SJ_HDC uint32_t hex_code(uint32_t c) {
     return c == '"' ? 0x80u

@@ -352,26 +352,47 @@ SJ_HD void s2s_slab(W& wp, const S2sParams& p, uint32_t slab, const S2sWarpMem& 
             uint32_t spill = 0;
             uint32_t st_drop = 0, st_nhead = 0, st_hpos = 0, st_head = 0;  // this lane's escape that runs past the end of the step
             if (any_esc) {
+                // Escape-heavy text is lumpy (a run of "\\uXXXX\\uXXXX..." puts ten escapes into one block and none into its
+                // neighbours), and a decode is a long dependent chain: with every lane decoding its own escapes the warp
+                // waits for the fullest block.  So the step's escapes are first listed in shared memory and decoded
+                // round-robin by all lanes; each lane then only reads the results of its own.  (More than S2S_ESC_CAP of
+                // them in one step: every lane decodes its own.)
+                const uint32_t e_cnt = pi::popc64(Ein);
+                uint32_t e_inc = e_cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t t = wp.shfl_up(e_inc, d);
+                    if ((int)lane >= d) e_inc += t;
+                }
+                const uint32_t e_tot = wp.shfl(e_inc, 31), e_ex = e_inc - e_cnt;
+                const bool shared_decode = e_tot <= S2S_ESC_CAP;  // warp-uniform
+                uint16_t* epos = reinterpret_cast<uint16_t*>(sm.esc + 8 * S2S_ESC_CAP);
+                uint64_t* eres = reinterpret_cast<uint64_t*>(sm.esc);
+                if (shared_decode) {
+                    uint32_t k = e_ex;
+                    for (uint64_t e = Ein; e; e &= e - 1) epos[k++] = (uint16_t)(64 * lane + pi::ctz64(e));
+                    wp.sync();
+                    for (uint32_t i = lane; i < e_tot; i += 32) {
+                        const EscInfo ei = esc_decode(rd, g, step_start + epos[i]);
+                        eres[i] = (uint64_t)ei.bytes | ((uint64_t)ei.c << 32) | ((uint64_t)ei.n << 36) | ((uint64_t)(ei.valid ? 1 : 0) << 39) |
+                                  ((uint64_t)(ei.second ? 1 : 0) << 40);
+                    }
+                    wp.sync();
+                }
+                uint32_t k = e_ex;
                 uint64_t e = Ein;
                 while (e) {
                     const uint32_t b = pi::ctz64(e);
                     e &= e - 1;
                     const uint64_t x = block_pos + b;
                     EscInfo ei;
-#if SJ_S2S_ESC_FAST
-                    if (!esc_decode_fast(sbase, 64 * lane + b, (uint32_t)(rd.slab_end - rd.slab_start), sm.hextab, ei)) ei = esc_decode(rd, g, x);
-#else
-                    ei = esc_decode(rd, g, x);
-#endif
-#ifdef S2S_EMU_CHECK
-                    {   // (emulation builds: the fast path agrees with the definition wherever it applies)
-                        EscInfo chk;
-                        if (esc_decode_fast(sbase, 64 * lane + b, (uint32_t)(rd.slab_end - rd.slab_start), sm.hextab, chk)) {
-                            const EscInfo ref = esc_decode(rd, g, x);
-                            if (chk.valid != ref.valid || chk.second != ref.second || (ref.valid && !ref.second && (chk.c != ref.c || chk.n != ref.n || chk.bytes != ref.bytes))) err = 1;
-                        }
+                    if (shared_decode) {
+                        const uint64_t r = eres[k++];
+                        ei.bytes = (uint32_t)r, ei.c = (uint32_t)(r >> 32) & 15u, ei.n = (uint32_t)(r >> 36) & 7u;
+                        ei.valid = ((r >> 39) & 1) != 0, ei.second = ((r >> 40) & 1) != 0;
+                    } else {
+                        ei = esc_decode(rd, g, x);
                     }
-#endif
                     if (ei.second) continue;
                     if (!ei.valid) {
                         err = 1;
@@ -395,13 +416,30 @@ SJ_HD void s2s_slab(W& wp, const S2sParams& p, uint32_t slab, const S2sWarpMem& 
                     {   // un-drop the n output positions (what lies behind the step's end is the next step's business)
                         D &= ~range64(ob, ob + ei.n);
                         if (ob + ei.n > 64) spill &= ~(uint32_t)range64(ob > 64 ? ob - 64 : 0, ob + ei.n - 64);
-                        if (EMIT) {
-                            // the UTF-8 bytes go straight into the image, over the escape's own LAST bytes: what a later
-                            // escape's quick look-behind reads of this one (its first three bytes) stays as it was
-                            uint8_t* img = const_cast<uint8_t*>(sbase);
-                            for (uint32_t i = 0; i < ei.n; i++)
-                                if (64 * lane + ob + i < S2S_STEP_BYTES) img[swz(64 * lane + ob + i)] = (uint8_t)(ei.bytes >> (8 * i));
+                    }
+                }
+                // In the shared scheme ALL decodes (which read the image) are done before ANY patch is written, so
+                // they see the message as it is; in the per-lane scheme decodes and patches of different lanes interleave
+                // (see high_escape_at for why that is fine).
+                if (EMIT) {
+                    if (shared_decode) wp.sync();
+                    uint8_t* img = const_cast<uint8_t*>(sbase);
+                    uint32_t k2 = e_ex;
+                    for (uint64_t e2 = Ein; e2; e2 &= e2 - 1) {
+                        const uint32_t b = pi::ctz64(e2);
+                        EscInfo ei;
+                        if (shared_decode) {
+                            const uint64_t r = eres[k2++];
+                            ei.bytes = (uint32_t)r, ei.c = (uint32_t)(r >> 32) & 15u, ei.n = (uint32_t)(r >> 36) & 7u;
+                            ei.valid = ((r >> 39) & 1) != 0, ei.second = ((r >> 40) & 1) != 0;
+                        } else {
+                            ei = esc_decode(rd, g, block_pos + b);
                         }
+                        if (ei.second || !ei.valid) continue;
+                        // the UTF-8 bytes go straight into the image, over the escape's own LAST bytes
+                        const uint32_t ob = (uint32_t)(esc_out_pos(block_pos + b, ei.c, ei.n) - block_pos);
+                        for (uint32_t i = 0; i < ei.n; i++)
+                            if (64 * lane + ob + i < S2S_STEP_BYTES) img[swz(64 * lane + ob + i)] = (uint8_t)(ei.bytes >> (8 * i));
                     }
                 }
             }

@@ -34,7 +34,8 @@ static_assert(S1_WARPS <= 32, "one bit per slab of a tile");
 constexpr int S2S_WARPS = SJ_S2S_WARPS;  // slabs per CTA
 constexpr int S2S_THREADS = S2S_WARPS * 32;
 constexpr uint32_t S2S_SSTAGE_PAD = (S2S_SSTAGE_BYTES + 15u) & ~15u;
-constexpr uint32_t S2S_WARP_SMEM_COUNT = S2S_IMAGE_BYTES;
+constexpr uint32_t S2S_WARP_SMEM_COUNT = S2S_IMAGE_BYTES + S2S_ESC_SCRATCH;
+static_assert(S2S_TSTAGE_WORDS * 8 >= S2S_ESC_SCRATCH, "K2r decodes escapes in the (then idle) tape staging area");
 constexpr uint32_t S2S_WARP_SMEM_EMIT = S2S_IMAGE_BYTES + S2S_SSTAGE_PAD + S2S_TSTAGE_WORDS * 8;
 constexpr size_t S2S_SMEM_COUNT = (size_t)S2S_WARPS * S2S_WARP_SMEM_COUNT;
 constexpr size_t S2S_SMEM_EMIT = (size_t)S2S_WARPS * S2S_WARP_SMEM_EMIT;
@@ -93,6 +94,7 @@ __global__ void __launch_bounds__(S2S_THREADS, SJ_S2S_COUNT_MIN_BLOCKS) s2s_coun
     sm.src = s2s_smem + (size_t)warp * S2S_WARP_SMEM_COUNT;
     sm.sstage = nullptr;
     sm.tstage = nullptr;
+    sm.esc = sm.src + S2S_IMAGE_BYTES;
     sm.ctab = tabs.ctab;
     sm.oktab = tabs.oktab;
     sm.cmptab = tabs.cmptab;
@@ -112,6 +114,7 @@ __global__ void __launch_bounds__(S2S_THREADS, SJ_S2S_EMIT_MIN_BLOCKS) s2s_emit_
     sm.src = base;
     sm.sstage = base + S2S_IMAGE_BYTES;
     sm.tstage = reinterpret_cast<uint64_t*>(base + S2S_IMAGE_BYTES + S2S_SSTAGE_PAD);
+    sm.esc = reinterpret_cast<uint8_t*>(sm.tstage);
     sm.ctab = tabs.ctab;
     sm.oktab = tabs.oktab;
     sm.cmptab = tabs.cmptab;

@@ -184,6 +184,7 @@ extern "C" int s2s_emu_parse(const uint8_t* msg, size_t len, int ndjson, const u
     sm.src = (uint8_t*)(((uintptr_t)src.data() + 15) & ~(uintptr_t)15);
     sm.sstage = (uint8_t*)(((uintptr_t)sstage.data() + 15) & ~(uintptr_t)15);
     sm.tstage = tstage.data();
+    sm.esc = reinterpret_cast<uint8_t*>(tstage.data());  // (as in K2r; K2p has nothing else in there)
     sm.ctab = T.ctab;
     sm.oktab = T.oktab;
     sm.cmptab = T.cmptab;
