@@ -372,10 +372,19 @@ SJ_HD void s2s_slab(W& wp, const S2sParams& p, uint32_t slab, const S2sWarpMem& 
                     uint32_t k = e_ex;
                     for (uint64_t e = Ein; e; e &= e - 1) epos[k++] = (uint16_t)(64 * lane + pi::ctz64(e));
                     wp.sync();
+                    uint8_t* img = const_cast<uint8_t*>(sbase);
                     for (uint32_t i = lane; i < e_tot; i += 32) {
-                        const EscInfo ei = esc_decode(rd, g, step_start + epos[i]);
+                        const uint32_t o = epos[i];
+                        const EscInfo ei = esc_decode(rd, g, step_start + o);
                         eres[i] = (uint64_t)ei.bytes | ((uint64_t)ei.c << 32) | ((uint64_t)ei.n << 36) | ((uint64_t)(ei.valid ? 1 : 0) << 39) |
                                   ((uint64_t)(ei.second ? 1 : 0) << 40);
+                        if (EMIT && ei.valid && !ei.second) {
+                            // the UTF-8 bytes go straight into the image, over the escape's own LAST bytes (whoever decoded it
+                            // writes them: other lanes may still be decoding -- see high_escape_at for why that is fine)
+                            const uint32_t op = o + ei.c - ei.n;
+                            for (uint32_t j = 0; j < ei.n; j++)
+                                if (op + j < S2S_STEP_BYTES) img[swz(op + j)] = (uint8_t)(ei.bytes >> (8 * j));
+                        }
                     }
                     wp.sync();
                 }
@@ -398,12 +407,16 @@ SJ_HD void s2s_slab(W& wp, const S2sParams& p, uint32_t slab, const S2sWarpMem& 
                         err = 1;
                         continue;
                     }
-                    // all c source bytes are dropped except the n that hold the output (esc_out_pos)
-                    mark_range(D, spill, b, b + ei.c);
-                    const uint32_t ob = (uint32_t)(esc_out_pos(x, ei.c, ei.n) - block_pos);
+                    // all c source bytes are dropped except the last n, which hold the output (esc_out_pos): a short mask
+                    // shifted to the escape's position, the part beyond bit 63 spills into the next lane
+                    {
+                        const uint64_t m = (uint64_t)(((1u << ei.c) - 1u) & ~(((1u << ei.n) - 1u) << (ei.c - ei.n)));
+                        D |= m << b;
+                        if (b > 52) spill |= (uint32_t)(m >> (64 - b));
+                    }
                     if (x + ei.c > step_end) {  // runs past the end of the step: the same bookkeeping head_info does
                         const uint32_t over = (uint32_t)(x + ei.c - step_end);
-                        const uint64_t op = block_pos + ob;
+                        const uint64_t op = x + ei.c - ei.n;
                         const uint32_t k0 = op < step_end ? (uint32_t)(step_end - op) : 0u;
                         st_drop = (uint32_t)range64(0, over);
                         if (k0 < ei.n) {
@@ -413,31 +426,9 @@ SJ_HD void s2s_slab(W& wp, const S2sParams& p, uint32_t slab, const S2sWarpMem& 
                             st_drop &= ~(uint32_t)range64(st_hpos, st_hpos + st_nhead);
                         }
                     }
-                    {   // un-drop the n output positions (what lies behind the step's end is the next step's business)
-                        D &= ~range64(ob, ob + ei.n);
-                        if (ob + ei.n > 64) spill &= ~(uint32_t)range64(ob > 64 ? ob - 64 : 0, ob + ei.n - 64);
-                    }
-                }
-                // In the shared scheme ALL decodes (which read the image) are done before ANY patch is written, so
-                // they see the message as it is; in the per-lane scheme decodes and patches of different lanes interleave
-                // (see high_escape_at for why that is fine).
-                if (EMIT) {
-                    if (shared_decode) wp.sync();
-                    uint8_t* img = const_cast<uint8_t*>(sbase);
-                    uint32_t k2 = e_ex;
-                    for (uint64_t e2 = Ein; e2; e2 &= e2 - 1) {
-                        const uint32_t b = pi::ctz64(e2);
-                        EscInfo ei;
-                        if (shared_decode) {
-                            const uint64_t r = eres[k2++];
-                            ei.bytes = (uint32_t)r, ei.c = (uint32_t)(r >> 32) & 15u, ei.n = (uint32_t)(r >> 36) & 7u;
-                            ei.valid = ((r >> 39) & 1) != 0, ei.second = ((r >> 40) & 1) != 0;
-                        } else {
-                            ei = esc_decode(rd, g, block_pos + b);
-                        }
-                        if (ei.second || !ei.valid) continue;
-                        // the UTF-8 bytes go straight into the image, over the escape's own LAST bytes
-                        const uint32_t ob = (uint32_t)(esc_out_pos(block_pos + b, ei.c, ei.n) - block_pos);
+                    if (EMIT && !shared_decode) {
+                        uint8_t* img = const_cast<uint8_t*>(sbase);
+                        const uint32_t ob = b + ei.c - ei.n;
                         for (uint32_t i = 0; i < ei.n; i++)
                             if (64 * lane + ob + i < S2S_STEP_BYTES) img[swz(64 * lane + ob + i)] = (uint8_t)(ei.bytes >> (8 * i));
                     }
