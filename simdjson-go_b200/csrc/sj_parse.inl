@@ -531,19 +531,12 @@ static int stream_emit(sj_ctx* c, uint64_t* d_tape, size_t tape_cap, uint8_t* d_
         s2_ansv_kernel<<<(unsigned)((nb + S2_THREADS - 1) / S2_THREADS), S2_THREADS, 0, c->stream>>>(L, par);
         c->launches++;
     }
-    s2s_link_kernel<<<(unsigned)((nb + 1 + S2_THREADS - 1) / S2_THREADS), S2_THREADS, 0, c->stream>>>(p, par, (uint32_t)nb);
     {
-        Stage2Params rp;
-        memset(&rp, 0, sizeof rp);
-        rp.rootpos = p.rootpos;
-        rp.tape = d_tape;
-        rp.tape_cap = tape_cap;
-        rp.tape_base = bases.tape;
-        rp.bases_dev = bases.dev;
         const uint64_t nrec = tot.n_records;
-        s2_roots_kernel<<<(unsigned)((nrec + 1 + 255) / 256), 256, 0, c->stream>>>(rp, nrec, tot.tape_len);
+        const uint64_t threads = (nb + 1 > nrec + 1 ? nb + 1 : nrec + 1);
+        s2s_link_kernel<<<(unsigned)((threads + S2_THREADS - 1) / S2_THREADS), S2_THREADS, 0, c->stream>>>(p, par, (uint32_t)nb, nrec, tot.tape_len);
     }
-    c->launches += 2;
+    c->launches += 1;  // (links and roots share a launch)
     SJ_CUDA_CHECK(cudaGetLastError());
     if (host) {  // (on a stage-2 failure the copied words are meaningless; the verdict below says so)
         SJ_CUDA_CHECK(cudaMemcpyAsync(host->tape, d_tape, tot.tape_len * 8, cudaMemcpyDeviceToHost, c->stream));

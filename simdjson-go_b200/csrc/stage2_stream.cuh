@@ -229,10 +229,22 @@ __global__ void __launch_bounds__(S2_THREADS) s2s_numbers_kernel(const uint8_t* 
 // it closes (par = nearest previous bracket with a smaller depth in front of it, K2d).  Closing brackets cross-link
 // the tape words of their pair (stage2...go:327-334).
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(S2_THREADS) s2s_link_kernel(const S2sParams p, const int32_t* par, uint32_t nb) {
+// The same launch writes the root words (K2f, stage2...go:170,207-218,428-441): record r opens at rootpos[r], its close
+// sits right in front of the next record's open (or is the last word of the tape).
+__global__ void __launch_bounds__(S2_THREADS) s2s_link_kernel(const S2sParams p, const int32_t* par, uint32_t nb, uint64_t n_records,
+                                                              uint64_t tape_len) {
     const uint32_t k = blockIdx.x * S2_THREADS + threadIdx.x;
-    if (k > nb) return;
     const uint64_t tape_base = s2s_tape_base(p);
+    if (k <= n_records) {
+        const uint64_t R = (uint64_t)'r' << 56;
+        const uint64_t open = k == 0 ? 0 : p.rootpos[k];
+        const uint64_t next_open = k == n_records ? tape_len : p.rootpos[k + 1];
+        if (next_open <= tape_len && next_open != 0) {
+            p.tape[open] = R | (tape_base + next_open);
+            p.tape[next_open - 1] = R | (tape_base + open);
+        }
+    }
+    if (k > nb) return;
     uint32_t ctx = CTX_ROOT;
     if (k > 0) {
         const uint32_t kd = p.brk_kind[k - 1];
