@@ -434,8 +434,9 @@ static int stream_count(sj_ctx* c, const uint8_t* d_msg, size_t len, const uint3
     pd->tot = *h_res;
     pd->sp = p;
     pd->stream = true;
-    pd->valid = true;
     *out = pd->tot;
+    if (pd->tot.error) return SJ_ERR_STAGE2;  // an invalid escape, found by the counting pass: the emitting pass is not run on it
+    pd->valid = true;
     return SJ_OK;
 }
 
@@ -590,15 +591,15 @@ static int front_half(sj_ctx* c, const uint8_t* d_msg, size_t len, uint32_t flag
         rc = launch_stage1(c, d_msg, len, ndjson, false, c->idx.as<uint32_t>(), dcap, nullptr, true);
         if (rc) return rc;
         rc = stream_count(c, d_msg, len, c->idx.as<uint32_t>(), 0, flags, r2, d_totals);  // (its read-back brings the stage-1 block too)
-        if (rc) return rc;
+        if (rc && rc != SJ_ERR_STAGE2) return rc;
         memcpy(r1, c->host_result, sizeof(Stage1Result));
         if (!r1->overflow) {
             const uint8_t last_char = r1->n_idx && r1->last_pos < len ? (uint8_t)r1->last_char : 0;
-            if (!stage1_ok(*r1, last_char)) {
+            if (!stage1_ok(*r1, last_char)) {  // a stage-1 error wins over a stage-2 one (parse_json_amd64.go:123-126)
                 pending_of(c)->valid = false;
                 return SJ_ERR_STAGE1;
             }
-            return SJ_OK;
+            return rc;
         }
         dcap = (size_t)r1->n_idx + 64;  // the index buffer was too small (more than one structural in four bytes): once more
     }
