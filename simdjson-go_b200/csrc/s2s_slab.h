@@ -26,6 +26,20 @@ struct MsgReader {
     }
 };
 
+// the same with 32-bit arithmetic on the hot path (messages are shorter than 2 GiB, so the low words decide)
+struct ImageReader {
+    const uint8_t* src;
+    uint32_t start_lo;  // low word of the message offset the image starts at
+    uint32_t win;       // message bytes the image holds
+    const uint8_t* msg;
+    uint64_t len;
+    SJ_HD uint32_t operator()(uint64_t pos) const {
+        const uint32_t d = (uint32_t)pos - start_lo;
+        if (d < win) return src[swz(d)];
+        return pos < len ? msg[pos] : 0u;
+    }
+};
+
 struct GlobalReader {
     const uint8_t* msg;
     uint64_t len;
@@ -375,7 +389,8 @@ SJ_HD void s2s_slab(W& wp, const S2sParams& p, uint32_t slab, const S2sWarpMem& 
                     uint8_t* img = const_cast<uint8_t*>(sbase);
                     for (uint32_t i = lane; i < e_tot; i += 32) {
                         const uint32_t o = epos[i];
-                        const EscInfo ei = esc_decode(rd, g, step_start + o);
+                        const EscInfo ei = esc_decode(ImageReader{sbase, (uint32_t)step_start, (uint32_t)(rd.slab_end - rd.slab_start), p.msg, p.len}, g,
+                                                      step_start + o);
                         eres[i] = (uint64_t)ei.bytes | ((uint64_t)ei.c << 32) | ((uint64_t)ei.n << 36) | ((uint64_t)(ei.valid ? 1 : 0) << 39) |
                                   ((uint64_t)(ei.second ? 1 : 0) << 40);
                         if (EMIT && ei.valid && !ei.second) {
