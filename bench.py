@@ -594,7 +594,7 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "stage1_flatten_kernel<ndjson>", "achieved": round(achieved, 2), "peak": peak,
                          "unit": "GB/s", "frac": round(achieved / peak, 4), "peak_kind": peak_kind, "traffic": k1_traffic(n),
-                         "traffic_kind": "static: dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full capture of this command (profiles/k1_traffic.json), not measured in this run",
+                         "traffic_kind": "static: dram__bytes_read.sum + dram__bytes_write.sum of one K1 launch on this batch from the committed ncu --set full capture (profiles/k1_traffic.json, round 2), not measured in this run",
                          "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": round(t_s1 * 1e3, 4),
                          "input_read_gbs": round(n / t_s1 / 1e9, 2)},
             "roofline_parse": {"bound": "hbm", "what": "whole device-resident step (K1 + K2p/q/r + numbers, scope matching, links, roots), algorithmic bytes 2*N_in + 8*N_idx + 8*N_tape + N_strings (SURVEY.md 8d)",
