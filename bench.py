@@ -225,6 +225,7 @@ def main():
     ap.add_argument("--stream-gib", type=int, default=64, help="GiB pushed through sj_stream_* per GPU-SET (split over the ranks); 0: skip")
     ap.add_argument("--stream-ring-mib", type=int, default=1024, help="size of the pinned ring of generated records each rank cycles over")
     ap.add_argument("--stream-chunk-mib", type=int, default=256, help="chunk size of the library's stream pipeline")
+    ap.add_argument("--nccl-exchange", action="store_true", help="N > 1: exchange the shard totals through NCCL even where the peer-memory kernel is available (A/B)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs under ncu)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -275,20 +276,37 @@ def main():
     # N > 1: every rank's batch is one shard of ONE NDJSON stream (shards joined by a newline) and the N tapes are the
     # slices of ONE ParsedJson (simdjson_amd64.go:82-93): counting half -> all-gather of the shard totals + exclusive
     # prefix, enqueued on the same stream (no host round trip) -> emitting half with the bases read from device memory
+    exchange = "none"
     if world > 1:
         from simdjson_b200.parallel import ShardedParse
-        L.sj_ctx_set_stream(ctx.h, torch.cuda.current_stream().cuda_stream)
-        sp = ShardedParse(ctx)
-        my_tot = torch.zeros(4, dtype=torch.int64, device=dev)
-        all_tot = torch.zeros(world * 4, dtype=torch.int64, device=dev)
-        bases = torch.zeros(3, dtype=torch.int64, device=dev)
-        sep = torch.tensor([rank, 0, 0], dtype=torch.int64, device=dev)  # one '\n' between consecutive shards of the message
+        sp = ShardedParse(ctx, device=dev)
+        # the exchange as the library's own kernel over peer memory (exchange.cuh): totals pushed into every peer's buffer
+        # over NVLink at the end of the counting half, bases left in device memory for the emitting half.  If this box
+        # cannot share device memory between processes (CUDA IPC), the same exchange goes through NCCL instead.
+        rc_x = sp.connect_exchange(rank, world, gap_bytes=1) if not args.nccl_exchange else -1
+        if rc_x == 0:
+            exchange = "peer"
+            L.sj_exchange_set_timeout_ms(ctx.h, 20000)
+        else:
+            exchange = "nccl"
+            L.sj_ctx_set_stream(ctx.h, torch.cuda.current_stream().cuda_stream)
+            my_tot = torch.zeros(4, dtype=torch.int64, device=dev)
+            all_tot = torch.zeros(world * 4, dtype=torch.int64, device=dev)
+            bases = torch.zeros(3, dtype=torch.int64, device=dev)
+            sep = torch.tensor([rank, 0, 0], dtype=torch.int64, device=dev)  # one '\n' between consecutive shards of the message
 
     def step_device():
         if world == 1:
             r = L.sj_parse_device(ctx.h, d_msg.data_ptr(), n, flags, d_tape.data_ptr(), d_tape.numel(), C.byref(tl),
                                   d_strings.data_ptr(), d_strings.numel(), C.byref(sl))
             assert r == 0, r
+            return
+        if exchange == "peer":
+            r, tot = sp.count(d_msg.data_ptr(), n, True)
+            assert r == 0, r
+            r = sp.emit(0, 0, 0, d_tape.data_ptr(), d_tape.numel(), d_strings.data_ptr(), d_strings.numel(), sp.bases_ptr)
+            assert r == 0, r
+            tl.value, sl.value = tot[1], tot[2]
             return
         r, tot = sp.count(d_msg.data_ptr(), n, True, my_tot.data_ptr())
         assert r == 0, r
@@ -331,10 +349,11 @@ def main():
     assert tl.value == tape_words and sl.value == string_bytes
     if world > 1:
         # the slice is rebased: its first word is this shard's first root, chained to the next one in WHOLE-tape indices
-        b_host = [int(x) for x in bases.tolist()]
+        b_host = sp.exchange_result()[1][:3] if exchange == "peer" else [int(x) for x in bases.tolist()]
         first = int(d_tape[0].item()) & ((1 << 56) - 1)
         assert b_host[1] == rank * tape_words and first == b_host[1] + (int(tape_h[0]) & ((1 << 56) - 1)), (b_host, first)
-        L.sj_ctx_set_stream(ctx.h, None)
+        if exchange == "nccl":
+            L.sj_ctx_set_stream(ctx.h, None)
 
     # ---- roofline: stage1_flatten alone on the same batch ----
     info = sj.Stage1Info()
@@ -583,7 +602,9 @@ def main():
             "config": {"workload": WORKLOAD,
                        "batch_bytes_per_gpu": n, "records_per_batch": batch.count(b"\n") + 1, "tape_words": tape_words,
                        "string_bytes": string_bytes, "inputs_larger_than_l2": True, "parallelism": "ndjson-shard x%d" % world,
-                       "collective": "all_gather of 4 x int64 per rank per step (shard totals -> bases of ONE ParsedJson), enqueued on the parse's stream between sj_parse_nd_sharded_count and _emit" if world > 1 else "none",
+                       "collective": {"none": "none",
+                                      "peer": "the library's own exchange kernel (exchange.cuh): each rank's counting half ends with one warp that stores the shard totals (4 x u64) into every peer's buffer over NVLink (CUDA IPC peer memory), polls its local buffer for the peers' and leaves the bases of ONE ParsedJson in device memory for the emitting half; no NCCL on the data path",
+                                      "nccl": "all_gather of 4 x int64 per rank per step (shard totals -> bases of ONE ParsedJson), enqueued on the parse's stream between sj_parse_nd_sharded_count and _emit"}[exchange],
                        "numa_node_bound": int(numa_node)},
             "e2e": {"value": round(total_bytes / t_e2e / 1e9, 3), "unit": "GB/s", "h2d_bytes_per_step": n,
                     "d2h_bytes_per_step": tape_words * 8 + string_bytes, "ms_per_step": round(t_e2e / args.steps * 1e3, 3),

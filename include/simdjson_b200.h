@@ -42,6 +42,8 @@ extern "C" {
 #define SJ_STREAM_END 7   /* sj_stream_next: input closed and every result delivered (io.EOF, simdjson_amd64.go:189) */
 #define SJ_STREAM_EMPTY 8 /* sj_stream_next: nothing handed to a worker yet -- write more (or close the input) */
 #define SJ_STREAM_BUSY 9  /* sj_stream_close_input: every slot is in use -- take a result first, then call again */
+#define SJ_ERR_EXCHANGE 10 /* sj_parse_nd_sharded_count: a peer's totals did not arrive within the exchange's time limit */
+#define SJ_ERR_PEER 11     /* sj_parse_nd_sharded_count: a peer's shard failed before its totals existed (the whole ParseND fails) */
 /* negative values: -(1000 + cudaError_t) */
 
 #define SJ_MAX_MESSAGE 0x7fffff00ull /* positions are uint32, string lengths keep one flag bit */
@@ -131,6 +133,37 @@ int sj_parse_nd_sharded_count(sj_ctx* ctx, const uint8_t* d_msg, size_t len, uin
                               uint64_t* d_totals);
 int sj_parse_nd_sharded_emit(sj_ctx* ctx, uint64_t msg_base, uint64_t tape_base, uint64_t strings_base, const uint64_t* d_bases,
                              uint64_t* d_tape, size_t tape_cap, uint8_t* d_strings, size_t strings_cap);
+/*
+ * The exchange of step 2 as a kernel over peer memory (exchange.cuh) instead of a collective in the caller: the counting
+ * half then ENDS with a one-warp kernel that stores this shard's totals into every peer's exchange buffer over NVLink,
+ * waits (polling local memory) for the peers' totals and leaves the bases in device memory -- all in front of the
+ * counting half's own synchronisation, so the emitting half can be enqueued at once with d_bases = sj_exchange_bases().
+ *   sj_exchange_create        allocates this rank's buffer; *handle_out (SJ_EXCHANGE_HANDLE_BYTES, optional) is its CUDA IPC
+ *                             handle.  gap_bytes = message bytes between this shard's window and the next shard's (1: the
+ *                             newline the shards were cut at; sj_exchange_set_gap changes it for the following calls),
+ *                             counted into the msg_base of the ranks behind.  world <= 32.
+ *   sj_exchange_connect       handles = world x SJ_EXCHANGE_HANDLE_BYTES, rank r's at offset r (all-gathered by the caller,
+ *                             once); opens the peers' buffers (cudaIpcOpenMemHandle).
+ *   sj_exchange_connect_ptrs  the same with the peers' buffers already mapped (ranks of one process: sj_exchange_local of
+ *                             each context; or symmetric memory the caller owns).
+ *   sj_exchange_bases         device pointer to { msg_base, tape_base, strings_base, records_base, whole message bytes,
+ *                             whole tape words, whole string bytes, whole records, status, epoch }.
+ *   sj_exchange_result        the same ten integers on the host, as of the last sj_parse_nd_sharded_count.
+ * Once connected, EVERY sj_parse_nd_sharded_count of the context is a collective call: all ranks make it the same number
+ * of times.  A rank whose counting half fails still publishes (a failure marker): its peers' calls return SJ_ERR_PEER.  A
+ * peer that never calls makes the others return SJ_ERR_EXCHANGE after the time limit (two seconds by default); no kernel waits forever.
+ * Verdicts that only the emitting half finds (stage-2 grammar) stay per rank: the caller combines them.
+ */
+#define SJ_EXCHANGE_HANDLE_BYTES 64
+int sj_exchange_create(sj_ctx* ctx, int rank, int world, uint64_t gap_bytes, void* handle_out);
+int sj_exchange_set_gap(sj_ctx* ctx, uint64_t gap_bytes);
+int sj_exchange_set_timeout_ms(sj_ctx* ctx, uint32_t ms); /* how long a call waits for its peers (default 2000) */
+int sj_exchange_connect(sj_ctx* ctx, const void* handles);
+int sj_exchange_connect_ptrs(sj_ctx* ctx, void* const* peer_buffers);
+void* sj_exchange_local(sj_ctx* ctx);
+const uint64_t* sj_exchange_bases(sj_ctx* ctx);
+int sj_exchange_result(sj_ctx* ctx, uint64_t* out10);
+
 /* Run this context's work on the caller's CUDA stream (a cudaStream_t passed as void*; NULL: back to the context's own
  * stream).  For callers that order the parse against their own kernels / collectives without host synchronisation. */
 int sj_ctx_set_stream(sj_ctx* ctx, void* cuda_stream);

@@ -65,5 +65,6 @@ struct sj_ctx {
     uint64_t last_tape_len = 0;
     const uint8_t* last_strings = nullptr;
     const uint8_t* last_msg = nullptr;
+    void* xchg = nullptr;  // SjExchange (sj_exchange.inl): the sharded ParseND's exchange over peer memory, if set up
     DevBuf test_in, test_out, test_aux;
 };

@@ -221,7 +221,10 @@ SJ_HD uint64_t range64(uint32_t lo, uint32_t hi) { return lo >= hi ? 0ull : belo
 // geometry (the slab is the stage-1 kernel's slab: K1 hands over the in-string state in front of each one)
 // ---------------------------------------------------------------------------------
 constexpr uint32_t S2S_STEP_BYTES = 2048;                            // one warp pass: 32 lanes x 64 bytes
-constexpr uint32_t S2S_STEPS = 3;
+#ifndef SJ_S1_STEPS
+#define SJ_S1_STEPS 3
+#endif
+constexpr uint32_t S2S_STEPS = SJ_S1_STEPS;  // 2 KiB steps per slab, the same in stage 1 (its in-string bits are per slab)
 constexpr uint32_t S2S_SLAB_BYTES = S2S_STEPS * S2S_STEP_BYTES;      // == S1_SLAB_BYTES (static_assert in stage2_stream.cuh)
 constexpr uint32_t S2S_IMAGE_BYTES = 2 * S2S_STEP_BYTES;              // two image buffers: the step at hand and the next one in flight
 constexpr uint32_t S2S_SSTAGE_BYTES = S2S_STEP_BYTES + 32;           // compacted string bytes of one step (+ alignment shift)

@@ -4,6 +4,7 @@
 // stage-1 driver epilogue (stage1_find_marks_amd64.go:115-148); all byte work runs in the
 // sm_100a kernels of stage1.cuh / stage2.cuh.  There is NO CPU fallback: without a CUDA
 // device every entry point returns SJ_ERR_NO_DEVICE.
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -20,6 +21,7 @@
 #include "stage2_stream.cuh"
 #include "consume.cuh"
 #include "gen.cuh"
+#include "exchange.cuh"
 
 using namespace sj;
 
@@ -128,11 +130,14 @@ extern "C" const char* sj_error_string(int rc) {
     case SJ_STREAM_END: return "end of stream";
     case SJ_STREAM_EMPTY: return "no chunk in flight";
     case SJ_STREAM_BUSY: return "every stream slot is in use";
+    case SJ_ERR_EXCHANGE: return "sharded ParseND: a peer's totals did not arrive in time";
+    case SJ_ERR_PEER: return "sharded ParseND: a peer's shard failed";
     default: return rc < 0 ? cudaGetErrorString((cudaError_t)(-rc - 1000)) : "unknown error";
     }
 }
 
 extern "C" void sj_ctx_destroy(sj_ctx* c);
+static void exchange_release(sj_ctx* c);  // sj_exchange.inl
 
 extern "C" int sj_ctx_create(int device, sj_ctx** out) {
     if (!out) return SJ_ERR_ARGUMENT;
@@ -194,6 +199,7 @@ extern "C" void sj_ctx_destroy(sj_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    exchange_release(c);
     DevBuf* bufs[] = {&c->msg,  &c->idx, &c->desc, &c->result, &c->s2a,     &c->s2b,     &c->s2c,      &c->s2d,
                       &c->s2e,  &c->s2f, &c->s2g,  &c->tape,   &c->strings, &c->test_in, &c->test_out, &c->test_aux,
                       &c->tc_small, &c->tc_roots};
@@ -514,6 +520,7 @@ extern "C" int sj_test_flatten_bits(sj_ctx* c, const uint64_t* masks, size_t nma
     return SJ_OK;
 }
 
+#include "sj_exchange.inl"
 #include "sj_parse.inl"
 #include "sj_consume.inl"
 #include "sj_stream.inl"

@@ -211,6 +211,8 @@ static int legacy_count(sj_ctx* c, const uint8_t* d_msg, size_t len, const uint3
     s2_scan_top_kernel<<<1, 1024, 0, c->stream>>>(p.grp_sum, ngroups, p.grp_pre, d_res, d_totals, (uint64_t)len);
     c->launches += 3;
     SJ_CUDA_CHECK(cudaGetLastError());
+    rc = exchange_enqueue(c, d_totals, false, nullptr, nullptr);  // sharded ParseND with the exchange set up: push / wait / prefix, still in front of the read-back
+    if (rc) return rc;
     Stage2Result* h_res = reinterpret_cast<Stage2Result*>(reinterpret_cast<uint8_t*>(c->host_result) + 64);
     SJ_CUDA_CHECK(cudaMemcpyAsync(h_res, d_res, sizeof(Stage2Result), cudaMemcpyDeviceToHost, c->stream));
     SJ_CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -427,6 +429,10 @@ static int stream_count(sj_ctx* c, const uint8_t* d_msg, size_t len, const uint3
     s2s_scan_top_kernel<<<1, 1024, 0, c->stream>>>(grp_sum, ngroups, grp_pre, d_res, d_totals, (uint64_t)len);
     c->launches += 3;
     SJ_CUDA_CHECK(cudaGetLastError());
+    // sharded ParseND with the exchange set up: push / wait / prefix, still in front of the read-back.  The kernel reads stage
+    // 1's verdict on the device: overflow of the index buffer = skip (this counting half is repeated and the repeat publishes)
+    rc = exchange_enqueue(c, d_totals, false, c->result.as<Stage1Result>(), &d_res->error);
+    if (rc) return rc;
     // one read-back for both stages: the stage-1 result block sits in front of the stage-2 totals, and K1 ran on the same stream
     Stage2Result* h_res = reinterpret_cast<Stage2Result*>(reinterpret_cast<uint8_t*>(c->host_result) + 64);
     SJ_CUDA_CHECK(cudaMemcpyAsync(c->host_result, c->result.p, 64 + sizeof(Stage2Result), cudaMemcpyDeviceToHost, c->stream));
@@ -602,6 +608,7 @@ static int front_half(sj_ctx* c, const uint8_t* d_msg, size_t len, uint32_t flag
             return rc;
         }
         dcap = (size_t)r1->n_idx + 64;  // the index buffer was too small (more than one structural in four bytes): once more
+        exchange_rearm(c);
     }
     return SJ_ERR_CAPACITY;
 }
@@ -639,13 +646,13 @@ extern "C" int sj_parse_nd_sharded_count(sj_ctx* c, const uint8_t* d_msg, size_t
                                          uint64_t* d_totals) {
     if (!c || !totals) return SJ_ERR_ARGUMENT;
     memset(totals, 0, sizeof *totals);
-    if (len == 0) return SJ_ERR_STAGE1;
-    if (len > SJ_MAX_MESSAGE) return SJ_ERR_TOO_LARGE;
-    flags |= SJ_FLAG_NDJSON;
     SJ_CUDA_CHECK(cudaSetDevice(c->device));
+    flags |= SJ_FLAG_NDJSON;
     Stage1Result r1;
     Stage2Result r2{};
-    int rc = front_half(c, d_msg, len, flags, &r1, &r2, d_totals);
+    exchange_begin(c, &d_totals);
+    int rc = len == 0 ? SJ_ERR_STAGE1 : len > SJ_MAX_MESSAGE ? SJ_ERR_TOO_LARGE : front_half(c, d_msg, len, flags, &r1, &r2, d_totals);
+    rc = exchange_end(c, rc);  // (a counting half that failed before its totals existed tells the peers so)
     if (rc) return rc;
     totals->msg_bytes = len;
     totals->tape_words = r2.tape_len;

@@ -10,6 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SJ_B200_LIB") or os.path.join(os.path.dirname(_HERE), "libsimdjson_b200.so")  # override: kernel variants under test
 
+ERR_EXCHANGE, ERR_PEER, EXCHANGE_HANDLE_BYTES = 10, 11, 64
 FLAG_NDJSON = 1
 FLAG_COPY_STRINGS = 2
 OK, ERR_STAGE1, ERR_STAGE2, ERR_NO_DEVICE, ERR_CAPACITY, ERR_TOO_LARGE, ERR_ARGUMENT = range(7)
@@ -17,7 +18,7 @@ OK, ERR_STAGE1, ERR_STAGE2, ERR_NO_DEVICE, ERR_CAPACITY, ERR_TOO_LARGE, ERR_ARGU
 # every symbol include/simdjson_b200.h declares
 EXPORTS = [
     "sj_supported", "sj_device_count", "sj_error_string", "sj_ctx_create", "sj_ctx_destroy", "sj_ctx_set_stage2_impl", "sj_ctx_set_stream", "sj_bind_to_device_numa", "sj_host_alloc",
-    "sj_host_free", "sj_trim_space", "sj_bounds", "sj_parse", "sj_parse_device", "sj_gen_ndjson_device", "sj_parse_nd_sharded_count", "sj_parse_nd_sharded_emit", "sj_find_structural_indices", "sj_stage1_device",
+    "sj_host_free", "sj_trim_space", "sj_bounds", "sj_parse", "sj_parse_device", "sj_gen_ndjson_device", "sj_parse_nd_sharded_count", "sj_parse_nd_sharded_emit", "sj_exchange_create", "sj_exchange_set_gap", "sj_exchange_set_timeout_ms", "sj_exchange_connect", "sj_exchange_connect_ptrs", "sj_exchange_local", "sj_exchange_bases", "sj_exchange_result", "sj_find_structural_indices", "sj_stage1_device",
     "sj_stage1_launch", "sj_ctx_sync", "sj_event_record", "sj_event_elapsed_ms", "sj_kernel_launches",
     "sj_test_block_masks", "sj_test_geometry", "sj_test_finalize", "sj_test_flatten_bits", "sj_test_parse_strings",
     "sj_test_parse_numbers", "sj_count_where_device", "sj_parse_count_where", "sj_stream_create", "sj_stream_destroy",
@@ -81,6 +82,22 @@ def load():
     L.sj_parse_nd_sharded_count.argtypes = [vp, vp, sz, u32, C.POINTER(ShardTotals), vp]
     L.sj_parse_nd_sharded_emit.restype = i32
     L.sj_parse_nd_sharded_emit.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64, vp, vp, sz, vp, sz]
+    L.sj_exchange_create.restype = i32
+    L.sj_exchange_create.argtypes = [vp, i32, i32, C.c_uint64, vp]
+    L.sj_exchange_set_gap.restype = i32
+    L.sj_exchange_set_gap.argtypes = [vp, C.c_uint64]
+    L.sj_exchange_set_timeout_ms.restype = i32
+    L.sj_exchange_set_timeout_ms.argtypes = [vp, u32]
+    L.sj_exchange_connect.restype = i32
+    L.sj_exchange_connect.argtypes = [vp, vp]
+    L.sj_exchange_connect_ptrs.restype = i32
+    L.sj_exchange_connect_ptrs.argtypes = [vp, C.POINTER(vp)]
+    L.sj_exchange_local.restype = vp
+    L.sj_exchange_local.argtypes = [vp]
+    L.sj_exchange_bases.restype = vp
+    L.sj_exchange_bases.argtypes = [vp]
+    L.sj_exchange_result.restype = i32
+    L.sj_exchange_result.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.sj_gen_ndjson_device.restype = i32
     L.sj_gen_ndjson_device.argtypes = [vp, vp, sz, C.c_uint64, C.c_uint64, vp, sz, szp]
     L.sj_bind_to_device_numa.restype = i32

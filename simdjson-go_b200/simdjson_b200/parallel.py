@@ -91,6 +91,7 @@ class ShardedParse:
 
     def __init__(self, ctx, group=None, device=None):
         self.ctx, self.group, self.device = ctx, group, device
+        self.bases_ptr = None  # device pointer to the bases once connect_exchange succeeded
 
     def count(self, d_msg, n, copy_strings=True, d_totals=None):
         """d_totals: optional device pointer that receives the same four integers on the context's stream"""
@@ -109,6 +110,40 @@ class ShardedParse:
     def exchange(self, totals):
         """all-gather of this rank's (msg_bytes, tape_words, string_bytes): (exclusive prefix, every rank's totals)"""
         return exchange_totals(totals[:3], self.group, self.device)
+
+    # ---- the exchange as a kernel over peer memory (exchange.cuh): set up once, then count() is a collective call whose
+    # result -- the bases -- is already in device memory (`bases_ptr`) when it returns ----
+    def connect_exchange(self, rank, world, gap_bytes=1):
+        """One process per GPU: all-gather of the CUDA IPC handles of the ranks' exchange buffers over `group`, then
+        every rank maps its peers' buffers.  Returns the library's return code (0 = ok); anything else means this box
+        cannot share device memory between processes and the caller keeps exchanging through its collective library."""
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        from . import _lib
+        L = self.ctx.L
+        mine = (C.c_uint8 * _lib.EXCHANGE_HANDLE_BYTES)()
+        rc = L.sj_exchange_create(self.ctx.h, rank, world, gap_bytes, mine)
+        t = torch.tensor([rc] + list(bytes(mine)), dtype=torch.int64, device=self.device)
+        allv = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(allv, t, group=self.group)
+        rows = [[int(v) for v in a.tolist()] for a in allv]
+        if any(r[0] != 0 for r in rows):
+            return next(r[0] for r in rows if r[0] != 0)
+        blob = bytes(b for r in rows for b in r[1:])
+        rc = L.sj_exchange_connect(self.ctx.h, blob)
+        ok = torch.tensor([rc], dtype=torch.int64, device=self.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MAX, group=self.group)  # all ranks or none
+        worst = int(ok.item())
+        self.bases_ptr = L.sj_exchange_bases(self.ctx.h) if worst == 0 else None
+        return rc if rc else worst
+
+    def exchange_result(self):
+        """{ msg_base, tape_base, strings_base, records_base, whole x4, status, epoch } of the last count()"""
+        import ctypes as C
+        out = (C.c_uint64 * 10)()
+        rc = self.ctx.L.sj_exchange_result(self.ctx.h, out)
+        return rc, [int(v) for v in out]
 
 
 def reduce_counts(local, group=None, device=None):

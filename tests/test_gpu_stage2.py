@@ -531,6 +531,139 @@ def test_parse_nd_sharded_is_one_parsed_json(oracle_native, copy, world):
         c.close()
 
 
+def _run_ranks(world, fn):
+    """fn(rank, barrier) on `world` host threads (ctypes calls release the GIL): the ranks of one process"""
+    import threading
+    bar = threading.Barrier(world)
+    out, errs = [None] * world, []
+
+    def body(r):
+        try:
+            out[r] = fn(r, bar)
+        except BaseException as e:  # noqa: BLE001 -- reported below; a rank that dies must not leave the others at a barrier
+            errs.append((r, e))
+            bar.abort()
+
+    ts = [threading.Thread(target=body, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
+    return out
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("copy", [True, False])
+@pytest.mark.parametrize("world", [2, 5])
+def test_parse_nd_sharded_exchange_over_peer_memory(oracle_native, copy, world, impl):
+    """the same claim with the exchange done by the library (exchange.cuh): the counting half ends with a kernel that pushes
+    the shard's totals into every peer's buffer, waits for the peers' and leaves the bases in device memory; the emitting
+    half reads them there.  `world` host threads with one context each stand in for the ranks (their buffers are plain
+    device pointers to each other: sj_exchange_connect_ptrs); three parses in a row exercise the epochs' double buffering"""
+    import ctypes as C
+    import torch
+    import simdjson_b200 as sj
+    from simdjson_b200.parallel import ShardedParse, split_at_newlines, trimmed_window
+    pk = load_fixture("parking-citations").strip()
+    stream = b"\n".join([pk] * 5) + b"\n\n" + b'{"esc":"a\\u00e9\\n","n":[1,2.5,-3],"t":true}\n' + pk[:30000].rsplit(b"\n", 1)[0]
+    rc, tape_o, str_o, (off_o, len_o) = oracle_native.parse(stream, ndjson=True, copy_strings=copy)
+    assert rc == 0
+    dev = torch.device("cuda:0")
+    wins = [trimmed_window(stream, a, b) for a, b in split_at_newlines(stream, world)]
+    ctxs = [sj.Context(0) for _ in range(world)]
+    for r, c in enumerate(ctxs):
+        c.set_stage2_impl(impl)
+        assert c.L.sj_exchange_create(c.h, r, world, 1, None) == 0
+    locs = (C.c_void_p * world)(*[c.L.sj_exchange_local(c.h) for c in ctxs])
+
+    def rank(r, bar):
+        c = ctxs[r]
+        a, b = wins[r]
+        assert c.L.sj_exchange_connect_ptrs(c.h, locs) == 0
+        assert c.L.sj_exchange_set_gap(c.h, wins[r + 1][0] - b if r + 1 < world else 0) == 0
+        d_msg = torch.full((b - a + 256,), 0x20, dtype=torch.uint8, device=dev)
+        d_msg[: b - a] = torch.frombuffer(bytearray(stream[a:b]), dtype=torch.uint8).to(dev)
+        torch.cuda.synchronize()
+        sp = ShardedParse(c)
+        res = None
+        for it in range(3):
+            bar.wait()
+            rc, tot = sp.count(d_msg.data_ptr(), b - a, copy)
+            assert rc == 0, rc
+            rc, ex = sp.exchange_result()
+            assert rc == 0 and ex[8] == 0 and ex[9] == it + 1, ex
+            d_tape = torch.empty(tot[1] + 8, dtype=torch.int64, device=dev)
+            d_str = torch.empty(tot[2] + 64, dtype=torch.uint8, device=dev)
+            assert sp.emit(0, 0, 0, d_tape.data_ptr(), d_tape.numel(), d_str.data_ptr(), d_str.numel(), c.L.sj_exchange_bases(c.h)) == 0
+            res = (d_tape[: tot[1]].cpu().numpy().view(np.uint64), d_str[: tot[2]].cpu().numpy().tobytes(), tot, ex)
+        return res
+
+    out = _run_ranks(world, rank)
+    got = np.concatenate([o[0] for o in out])
+    assert len(got) == len(tape_o)
+    assert np.array_equal(got, tape_o), int(np.nonzero(got != tape_o)[0][0])
+    assert b"".join(o[1] for o in out) == str_o
+    for r, o in enumerate(out):
+        ex = o[3]
+        assert ex[0] == wins[r][0] - off_o and ex[1] == sum(q[2][1] for q in out[:r]) and ex[2] == sum(q[2][2] for q in out[:r])
+        assert ex[4] == len_o and ex[5] == len(tape_o) and ex[6] == len(str_o) and ex[7] == sum(q[2][3] for q in out)
+    for c in ctxs:
+        c.close()
+
+
+def test_sharded_exchange_failures_do_not_hang():
+    """a rank whose shard fails (stage 1: unterminated string; stage 2 counting pass: invalid escape; empty shard) still
+    publishes, so its peers return SJ_ERR_PEER instead of waiting; a rank that never calls costs the others the time limit
+    and SJ_ERR_EXCHANGE (the ranks' epochs then differ: the exchange has to be set up again)"""
+    import ctypes as C
+    import time
+    import torch
+    import simdjson_b200 as sj
+    from simdjson_b200 import _lib
+    from simdjson_b200.parallel import ShardedParse
+    dev = torch.device("cuda:0")
+    world = 3
+    good = b'{"a":1}\n{"b":[true,null]}'
+    cases = [(b'{"a":"unterminated}', _lib.ERR_STAGE1), (b'{"a":"bad \\q escape"}', _lib.ERR_STAGE2), (b"", _lib.ERR_STAGE1), (None, None)]
+    ctxs = [sj.Context(0) for _ in range(world)]
+    for r, c in enumerate(ctxs):
+        assert c.L.sj_exchange_create(c.h, r, world, 1, None) == 0
+    locs = (C.c_void_p * world)(*[c.L.sj_exchange_local(c.h) for c in ctxs])
+
+    def rank(r, bar):
+        c = ctxs[r]
+        assert c.L.sj_exchange_connect_ptrs(c.h, locs) == 0
+        sp = ShardedParse(c)
+        got = []
+        for doc, want in cases:
+            mine = doc if r == 1 else good
+            bar.wait()
+            if mine is None:
+                got.append(None)  # this rank skips the call: the others time out, and the epochs no longer agree ...
+                bar.wait()
+                continue
+            d = torch.full((len(mine) + 256,), 0x20, dtype=torch.uint8, device=dev)
+            if mine:
+                d[: len(mine)] = torch.frombuffer(bytearray(mine), dtype=torch.uint8).to(dev)
+            torch.cuda.synchronize()
+            t0 = time.time()
+            rc, tot = sp.count(d.data_ptr(), len(mine), True)
+            got.append((rc, time.time() - t0))
+            if doc is None:
+                bar.wait()
+        return got
+
+    out = _run_ranks(world, rank)
+    for i, (doc, want) in enumerate(cases[:3]):
+        assert out[1][i][0] == want, (i, out[1][i])
+        assert out[0][i][0] == _lib.ERR_PEER and out[2][i][0] == _lib.ERR_PEER, (i, out[0][i], out[2][i])
+        assert max(o[i][1] for o in out) < 1.0
+    assert out[0][3][0] == _lib.ERR_EXCHANGE and out[2][3][0] == _lib.ERR_EXCHANGE and 1.5 < out[0][3][1] < 4.0, out[0][3]
+    for c in ctxs:
+        c.close()
+
+
 def test_numbers_fast_path_shapes(ctx, oracle):
     """the one-pass fast path of K2h ([-]digits[.digits], at most 18 digits, no exponent) and its borders: the hook runs it
     beside the full routine on every item and poisons the tag on a disagreement; the full routine is checked against the oracle"""
