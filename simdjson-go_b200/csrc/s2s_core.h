@@ -194,6 +194,14 @@ SJ_HD uint32_t bitsel(uint32_t m, uint32_t a, uint32_t b) {  // (a & m) | (b & ~
     return (a & m) | (b & ~m);
 #endif
 }
+SJ_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s) {  // lower word of (hi:lo) >> (s & 31)
+#ifdef __CUDA_ARCH__
+    return __funnelshift_r(lo, hi, s);
+#else
+    s &= 31;
+    return s ? (lo >> s) | (hi << (32 - s)) : lo;
+#endif
+}
 SJ_HD uint32_t funnel_l(uint32_t lo, uint32_t hi, uint32_t s) {  // upper word of (hi:lo) << (s & 31)
 #ifdef __CUDA_ARCH__
     return __funnelshift_l(lo, hi, s);
@@ -580,10 +588,15 @@ struct S2sWarpMem {
     const uint8_t* oktab;  // [256] transition_mask(p, c) at [p * 16 + c]
     const uint32_t* cmptab;  // [16] compress_sel(m) | popcount(m) << 16
     const uint8_t* hextab;   // [256] hex_code
-    uint8_t* esc;            // [S2S_ESC_SCRATCH] escape positions + decode results of a step (K2r: the tape staging area, idle then)
+    uint8_t* esc;            // [S2S_ESC_SCRATCH] drop map + list of a step's escapes (K2r: the tape staging area, idle then)
 };
-constexpr uint32_t S2S_ESC_CAP = 256;                        // escapes of a step decoded by the balanced scheme
-constexpr uint32_t S2S_ESC_SCRATCH = S2S_ESC_CAP * (2 + 8);  // u16 position + u64 result each
+// scratch of a step's escapes: the drop map (one bit per image byte + one word behind the step), the record of the escape
+// whose output runs past the end of the step, the list of escape positions (an escape is at least two bytes long)
+constexpr uint32_t S2S_ESC_CAP = S2S_STEP_BYTES / 2;
+constexpr uint32_t S2S_ESC_DMAP_WORDS = S2S_STEP_BYTES / 32 + 1;
+constexpr uint32_t S2S_ESC_REC_OFS = 272, S2S_ESC_LIST_OFS = 288;
+constexpr uint32_t S2S_ESC_SCRATCH = S2S_ESC_LIST_OFS + 2 * S2S_ESC_CAP;  // 2336 bytes
+static_assert(S2S_ESC_DMAP_WORDS * 4 <= S2S_ESC_REC_OFS, "drop map fits in front of the record");
 // digit_to_val_p with the raw quote and every non-digit folded into one "invalid" code (see hex4_at)
 SJ_HDC uint32_t hex_code(uint32_t c) {
     return c == '"' ? 0x80u

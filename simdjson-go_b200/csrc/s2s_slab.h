@@ -70,39 +70,43 @@ SJ_HD void mark_range(uint64_t& m, uint32_t& spill, uint32_t lo, uint32_t hi) {
     }
 }
 
-// (measured on a B200: SLOWER than esc_decode -- twitterescaped 65.7 -> 56.7 GB/s: the kernels are bound by dependent
-// latencies, not by instruction count, and the table look-ups chain two shared-memory loads per digit.  Kept behind
-// SJ_S2S_ESC_FAST = 0 as a measured dead end.)
-#ifndef SJ_S2S_ESC_FAST
-#define SJ_S2S_ESC_FAST 0
+// esc_decode for the common case -- "\\uXXXX" with four proper hex digits, not a surrogate, and nothing that looks like a
+// high surrogate six bytes in front of it -- straight from the step image with word accesses and register arithmetic
+// only: four aligned words cover the twelve bytes [o - 6, o + 6), funnel shifts align them, the hex digits are checked
+// and converted four at a time (SWAR).  No table look-ups: a first version that went through the 256-entry tables was
+// SLOWER than esc_decode (twitterescaped 65.7 -> 56.7 GB/s; two dependent shared-memory loads per digit in a kernel that
+// is bound by dependent latencies).  Returns false when it does not apply; esc_decode (s2s_core.h) is the definition and
+// takes those cases -- including every digit quirk of parse_string_amd64.s:4-69, which is why only proper digits pass here.
+//   o: offset of the backslash in the image; avail: image bytes that are message bytes
+#ifndef SJ_S2S_ESC_UFAST
+#define SJ_S2S_ESC_UFAST 1
 #endif
-// esc_decode for the common case, straight from the step image: the escape's six bytes and the three bytes six in
-// front of it each lie inside one 16-byte chunk of the image (so one swizzled address + immediate offsets reaches
-// them), the escape is not a high surrogate and what precedes it does not look like one.  Returns false when it does
-// not apply -- esc_decode (s2s_core.h) is the definition and takes those.
-SJ_HD bool esc_decode_fast(const uint8_t* img, uint32_t o, uint32_t step_len, const uint8_t* hextab, EscInfo& r) {
-    if ((o & 15u) > 10u || o + 6 > step_len || o < 6 || ((o - 6) & 15u) > 13u) return false;
-    const uint8_t* b = img + swz(o);
-    const uint32_t e = b[1];
-    const uint8_t* y = img + swz(o - 6);
-    if (y[0] == '\\' && y[1] == 'u' && (y[2] | 0x20u) == 'd') return false;  // may be the low half of a pair: the full rules decide
-    r.second = false;
-    r.valid = true;
-    if (e != 'u') {
-        const uint32_t m = escape_map_p(e);
-        r.c = 2, r.n = 1, r.bytes = m, r.valid = m != 0;
-        return true;
-    }
-    const uint32_t h0 = hextab[b[2]], h1 = hextab[b[3]], h2 = hextab[b[4]], h3 = hextab[b[5]];
-    r.c = 6, r.n = 1, r.bytes = 0;
-    if ((h0 | h1 | h2 | h3) & 0x80u) {
-        r.valid = false;
-        return true;
-    }
-    const uint32_t cp = (h0 << 12) | (h1 << 8) | (h2 << 4) | h3;
-    if ((cp & 0xFC00u) == 0xD800u) return false;  // high surrogate: pair logic
+SJ_HD bool esc_u_fast(const uint8_t* img, uint32_t o, uint32_t avail, EscInfo& r) {
+    if (!SJ_S2S_ESC_UFAST || o < 6 || o + 6 > avail) return false;
+    const uint32_t a = (o - 6) & ~3u, sh = 8 * ((o - 6) & 3u);
+    const uint32_t a3 = a + 12 < S2S_STEP_BYTES ? a + 12 : a + 8;  // (the fourth word only matters when sh != 0, and then it is inside)
+    const uint32_t w0 = *reinterpret_cast<const uint32_t*>(img + swz(a)), w1 = *reinterpret_cast<const uint32_t*>(img + swz(a + 4));
+    const uint32_t w2 = *reinterpret_cast<const uint32_t*>(img + swz(a + 8)), w3 = *reinterpret_cast<const uint32_t*>(img + swz(a3));
+    const uint32_t q0 = pi::funnel_r(w0, w1, sh), q1 = pi::funnel_r(w1, w2, sh), x = pi::funnel_r(w2, w3, sh);
+    // q0 = bytes o-6 .. o-3, q1 = o-2 .. o+1, x = o+2 .. o+5 (the digits)
+    if ((q1 >> 24) != 'u') return false;
+    if ((q0 & 0x00DFFFFFu) == 0x0044755Cu) return false;  // "\\uD" / "\\ud" six bytes in front: perhaps the first half of a pair
+    // bytes are proper hex digits: '0'..'9' (tested on x), 'A'..'F' / 'a'..'f' (tested on x | 0x20); every byte < 0x80,
+    // so the per-byte additions do not carry into their neighbours (a byte >= 0x80 fails through ~x)
+    const uint32_t l = x | 0x20202020u;
+    const uint32_t isdig = (x + 0x50505050u) & ~(x + 0x46464646u);
+    const uint32_t isalp = (l + 0x1f1f1f1fu) & ~(l + 0x19191919u);
+    if ((((isdig | isalp) & ~x) & 0x80808080u) != 0x80808080u) return false;
+    const uint32_t v = (x & 0x0f0f0f0fu) + 9u * ((x >> 6) & 0x01010101u);  // digit values, first digit in byte 0
+    const uint32_t rv = pi::byte_perm(v, 0, 0x0123);                        // first digit in byte 3
+    const uint32_t pr = (rv | (rv >> 4)) & 0x00ff00ffu;
+    const uint32_t cp = (pr | (pr >> 8)) & 0xffffu;
+    if ((cp & 0xF800u) == 0xD800u) return false;  // surrogates: the pair rules
+    r.c = 6;
     r.n = cp < 0x80u ? 1u : cp < 0x800u ? 2u : 3u;
     r.bytes = utf8_pack(cp, r.n);
+    r.valid = true;
+    r.second = false;
     return true;
 }
 
@@ -362,109 +366,68 @@ SJ_HD void s2s_slab(W& wp, const S2sParams& p, uint32_t slab, const S2sWarpMem& 
         err |= hd.bad;
         hd_next.drop = 0, hd_next.nhead = 0, hd_next.hpos = 0, hd_next.head = 0, hd_next.bad = 0;
         const bool any_esc = wp.any(Ein != 0);
-        {
-            uint32_t spill = 0;
-            uint32_t st_drop = 0, st_nhead = 0, st_hpos = 0, st_head = 0;  // this lane's escape that runs past the end of the step
-            if (any_esc) {
-                // Escape-heavy text is lumpy (a run of "\\uXXXX\\uXXXX..." puts ten escapes into one block and none into its
-                // neighbours), and a decode is a long dependent chain: with every lane decoding its own escapes the warp
-                // waits for the fullest block.  So the step's escapes are first listed in shared memory and decoded
-                // round-robin by all lanes; each lane then only reads the results of its own.  (More than S2S_ESC_CAP of
-                // them in one step: every lane decodes its own.)
-                const uint32_t e_cnt = pi::popc64(Ein);
-                uint32_t e_inc = e_cnt;
+        if (any_esc) {
+            // Escape-heavy text is lumpy (a run of "\\uXXXX\\uXXXX..." puts eleven escapes into one block and none into its
+            // neighbours), and a decode is a long dependent chain: with every lane decoding its own escapes the warp
+            // waits for the fullest block.  So the step's escapes are listed in shared memory and decoded round-robin
+            // by all lanes.  Whoever decodes an escape also publishes it: the UTF-8 bytes go straight into the image,
+            // over the escape's own LAST bytes (esc_out_pos); its other bytes are marked in the step's DROP MAP (one
+            // bit per image byte, red.shared.or); the one escape whose bytes run past the end of the step leaves a
+            // record for the next step.  The owners then just read their 64 bits of the map -- no second walk.
+            uint32_t* dmap = reinterpret_cast<uint32_t*>(sm.esc);
+            uint32_t* rec = reinterpret_cast<uint32_t*>(sm.esc + S2S_ESC_REC_OFS);  // { nhead, hpos, head }
+            uint16_t* epos = reinterpret_cast<uint16_t*>(sm.esc + S2S_ESC_LIST_OFS);
+            dmap[2 * lane] = 0, dmap[2 * lane + 1] = 0;
+            if (lane == 0) dmap[S2S_ESC_DMAP_WORDS - 1] = 0, rec[0] = 0, rec[1] = 0, rec[2] = 0;
+            const uint32_t e_cnt = pi::popc64(Ein);
+            uint32_t e_inc = e_cnt;
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t t = wp.shfl_up(e_inc, d);
-                    if ((int)lane >= d) e_inc += t;
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = wp.shfl_up(e_inc, d);
+                if ((int)lane >= d) e_inc += t;
+            }
+            const uint32_t e_tot = wp.shfl(e_inc, 31);
+            {
+                uint32_t k = e_inc - e_cnt;
+                for (uint64_t e = Ein; e; e &= e - 1) epos[k++] = (uint16_t)(64 * lane + pi::ctz64(e));
+            }
+            wp.sync();
+            uint8_t* img = const_cast<uint8_t*>(sbase);
+            const uint32_t avail = (uint32_t)(rd.slab_end - rd.slab_start);  // image bytes that are message bytes
+            const ImageReader ird{sbase, (uint32_t)step_start, (uint32_t)(rd.slab_end - rd.slab_start), p.msg, p.len};
+            for (uint32_t i = lane; i < e_tot; i += 32) {
+                const uint32_t o = epos[i];
+                EscInfo ei;
+                if (!esc_u_fast(sbase, o, avail, ei)) ei = esc_decode(ird, g, step_start + o);
+                if (ei.second) continue;
+                if (!ei.valid) {
+                    err = 1;
+                    continue;
                 }
-                const uint32_t e_tot = wp.shfl(e_inc, 31), e_ex = e_inc - e_cnt;
-                const bool shared_decode = e_tot <= S2S_ESC_CAP;  // warp-uniform
-                uint16_t* epos = reinterpret_cast<uint16_t*>(sm.esc + 8 * S2S_ESC_CAP);
-                uint64_t* eres = reinterpret_cast<uint64_t*>(sm.esc);
-                if (shared_decode) {
-                    uint32_t k = e_ex;
-                    for (uint64_t e = Ein; e; e &= e - 1) epos[k++] = (uint16_t)(64 * lane + pi::ctz64(e));
-                    wp.sync();
-                    uint8_t* img = const_cast<uint8_t*>(sbase);
-                    for (uint32_t i = lane; i < e_tot; i += 32) {
-                        const uint32_t o = epos[i];
-                        const EscInfo ei = esc_decode(ImageReader{sbase, (uint32_t)step_start, (uint32_t)(rd.slab_end - rd.slab_start), p.msg, p.len}, g,
-                                                      step_start + o);
-                        eres[i] = (uint64_t)ei.bytes | ((uint64_t)ei.c << 32) | ((uint64_t)ei.n << 36) | ((uint64_t)(ei.valid ? 1 : 0) << 39) |
-                                  ((uint64_t)(ei.second ? 1 : 0) << 40);
-                        if (EMIT && ei.valid && !ei.second) {
-                            // the UTF-8 bytes go straight into the image, over the escape's own LAST bytes (whoever decoded it
-                            // writes them: other lanes may still be decoding -- see high_escape_at for why that is fine)
-                            const uint32_t op = o + ei.c - ei.n;
-                            for (uint32_t j = 0; j < ei.n; j++)
-                                if (op + j < S2S_STEP_BYTES) img[swz(op + j)] = (uint8_t)(ei.bytes >> (8 * j));
-                        }
-                    }
-                    wp.sync();
+                const uint32_t op = o + ei.c - ei.n;  // first output position (image offset; may lie behind the step)
+                // all c source bytes are dropped except the last n, which hold the output
+                const uint32_t m = ((1u << ei.c) - 1u) & ~(((1u << ei.n) - 1u) << (ei.c - ei.n));
+                const uint32_t wd = o >> 5, sh = o & 31u;
+                wp.atomic_or_shared(dmap + wd, m << sh);
+                if (sh > 20 && (m >> (32 - sh))) wp.atomic_or_shared(dmap + wd + 1, m >> (32 - sh));  // (word 64: bytes of the next step)
+                if (EMIT) {
+                    for (uint32_t j = 0; j < ei.n; j++)
+                        if (op + j < S2S_STEP_BYTES) img[swz(op + j)] = (uint8_t)(ei.bytes >> (8 * j));
                 }
-                uint32_t k = e_ex;
-                uint64_t e = Ein;
-                while (e) {
-                    const uint32_t b = pi::ctz64(e);
-                    e &= e - 1;
-                    const uint64_t x = block_pos + b;
-                    EscInfo ei;
-                    if (shared_decode) {
-                        const uint64_t r = eres[k++];
-                        ei.bytes = (uint32_t)r, ei.c = (uint32_t)(r >> 32) & 15u, ei.n = (uint32_t)(r >> 36) & 7u;
-                        ei.valid = ((r >> 39) & 1) != 0, ei.second = ((r >> 40) & 1) != 0;
-                    } else {
-                        ei = esc_decode(rd, g, x);
-                    }
-                    if (ei.second) continue;
-                    if (!ei.valid) {
-                        err = 1;
-                        continue;
-                    }
-                    // all c source bytes are dropped except the last n, which hold the output (esc_out_pos): a short mask
-                    // shifted to the escape's position, the part beyond bit 63 spills into the next lane
-                    {
-                        const uint64_t m = (uint64_t)(((1u << ei.c) - 1u) & ~(((1u << ei.n) - 1u) << (ei.c - ei.n)));
-                        D |= m << b;
-                        if (b > 52) spill |= (uint32_t)(m >> (64 - b));
-                    }
-                    if (x + ei.c > step_end) {  // runs past the end of the step: the same bookkeeping head_info does
-                        const uint32_t over = (uint32_t)(x + ei.c - step_end);
-                        const uint64_t op = x + ei.c - ei.n;
-                        const uint32_t k0 = op < step_end ? (uint32_t)(step_end - op) : 0u;
-                        st_drop = (uint32_t)range64(0, over);
-                        if (k0 < ei.n) {
-                            st_nhead = ei.n - k0;
-                            st_hpos = op < step_end ? 0u : (uint32_t)(op - step_end);
-                            st_head = ei.bytes >> (8 * k0);
-                            st_drop &= ~(uint32_t)range64(st_hpos, st_hpos + st_nhead);
-                        }
-                    }
-                    if (EMIT && !shared_decode) {
-                        uint8_t* img = const_cast<uint8_t*>(sbase);
-                        const uint32_t ob = b + ei.c - ei.n;
-                        for (uint32_t i = 0; i < ei.n; i++)
-                            if (64 * lane + ob + i < S2S_STEP_BYTES) img[swz(64 * lane + ob + i)] = (uint8_t)(ei.bytes >> (8 * i));
-                    }
+                if (op + ei.n > S2S_STEP_BYTES) {  // output bytes behind the end of the step: the next step patches them in
+                    const uint32_t k0 = op < S2S_STEP_BYTES ? S2S_STEP_BYTES - op : 0u;
+                    rec[0] = ei.n - k0;
+                    rec[1] = op < S2S_STEP_BYTES ? 0u : op - S2S_STEP_BYTES;
+                    rec[2] = ei.bytes >> (8 * k0);
                 }
             }
-            if (any_esc || hd.drop) {  // warp-uniform
-                uint32_t spin = wp.shfl_up(spill, 1);
-                if (lane == 0) spin = hd.drop;
-                D |= (uint64_t)spin;
-            }
-            if (any_esc) {  // (at most one escape straddles the end of the step in a valid document)
-                const uint32_t have = wp.ballot(st_drop != 0 || st_nhead != 0);
-                if (have) {
-                    const uint32_t pick = 31 - pi::clz32(have);
-                    hd_next.drop = wp.shfl(st_drop, pick);
-                    hd_next.nhead = wp.shfl(st_nhead, pick);
-                    hd_next.hpos = wp.shfl(st_hpos, pick);
-                    hd_next.head = wp.shfl(st_head, pick);
-                }
-            }
+            wp.sync();
+            D = mk64u(dmap[2 * lane], dmap[2 * lane + 1]);
+            hd_next.drop = dmap[S2S_ESC_DMAP_WORDS - 1];
+            hd_next.nhead = rec[0], hd_next.hpos = rec[1], hd_next.head = rec[2];
+            wp.sync();  // (the scratch is the tape staging area of the rest of the step)
         }
+        if (lane == 0) D |= (uint64_t)hd.drop;
         const uint64_t K = qm & ~qb & ~D;  // bytes of Strings.B, at their source positions
         if (EMIT && (any_esc || hd.nhead)) {  // warp-uniform: the image was patched, the compaction wants the patched words
             if (hd.nhead && lane == 0) {

@@ -275,3 +275,22 @@ extern "C" int s2s_emu_parse(const uint8_t* msg, size_t len, int ndjson, const u
     if (error || grand.depth != 0) return 2;
     return 0;
 }
+
+// esc_u_fast against its definition: `img` holds one step (2048 message bytes, natural order); every backslash position o
+// is decoded both ways.  Returns the number of positions where the fast path applied, or -(o + 1) at the first
+// disagreement.  (The fast path reads the swizzled image, the definition reads the bytes in natural order.)
+extern "C" long s2s_emu_esc_fast_check(const uint8_t* step, uint32_t avail) {
+    alignas(16) static uint8_t img[S2S_STEP_BYTES];
+    for (uint32_t i = 0; i < S2S_STEP_BYTES; i++) img[swz(i)] = step[i];
+    const GlobalReader g{step, avail};
+    long applied = 0;
+    for (uint32_t o = 0; o + 1 < avail; o++) {
+        if (step[o] != '\\') continue;
+        EscInfo f;
+        if (!esc_u_fast(img, o, avail, f)) continue;
+        const EscInfo d = esc_decode(g, g, o);
+        if (d.second || !d.valid || d.c != f.c || d.n != f.n || d.bytes != f.bytes) return -(long)(o + 1);
+        applied++;
+    }
+    return applied;
+}

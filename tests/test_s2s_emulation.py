@@ -151,3 +151,40 @@ def test_lane_order_does_not_matter():
     out = subprocess.run([sys.executable, "-m", "pytest", "tests/test_s2s_emulation.py", "-x", "-q", "-k",
                           "escapes or strings_across or twitterescaped or ndjson or golden"], cwd=root, env=env, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:]
+
+
+def test_escape_fast_path_is_the_definition():
+    """esc_u_fast (word loads + SWAR hex digits) must agree with esc_decode wherever it claims to apply: random steps dense
+    in "\\uXXXX" with proper, improper and quirky digits (bytes below '0', raw quotes, upper / lower case, >= 0x80),
+    surrogates and look-alikes of a high surrogate six bytes in front, at every alignment and at both ends of the step"""
+    import ctypes as C
+    from tests import emu_util
+    L = emu_util.lib()
+    L.s2s_emu_esc_fast_check.restype = C.c_long
+    L.s2s_emu_esc_fast_check.argtypes = [C.c_void_p, C.c_uint32]
+    rng = np.random.default_rng(20260923)
+    digits = b"0123456789abcdefABCDEF"
+    odd = b"gG/:@`\"' \x00\x10\x19\x2f\x3a\x7f\x80\xff\\u"
+    applied = 0
+    for it in range(400):
+        out = bytearray()
+        while len(out) < 2048 + 16:
+            k = int(rng.integers(0, 10))
+            if k < 6:
+                hx = bytes(digits[int(j)] for j in rng.integers(0, len(digits), 4))
+                if rng.integers(0, 5) == 0:
+                    hx = (b"d" if rng.integers(0, 2) else b"D") + bytes([b"89abAB cdefCDEF"[int(rng.integers(0, 15))]]) + hx[2:]
+                if rng.integers(0, 6) == 0:
+                    j = int(rng.integers(0, 4))
+                    hx = hx[:j] + bytes([odd[int(rng.integers(0, len(odd)))]]) + hx[j + 1:]
+                out += b"\\u" + hx
+            elif k < 8:
+                out += bytes(rng.integers(0x20, 0x7f, int(rng.integers(1, 7)), dtype=np.uint8).tolist()).replace(b"\\", b"x")
+            else:
+                out += b"\\" + bytes([b'nrt"/\\bfq'[int(rng.integers(0, 9))]])
+        step = np.frombuffer(bytes(out[:2048]), dtype=np.uint8).copy()
+        avail = 2048 if it % 3 else int(rng.integers(1, 2049))
+        r = L.s2s_emu_esc_fast_check(step.ctypes.data, avail)
+        assert r >= 0, (it, -r - 1, bytes(step[max(0, -r - 8): -r + 8]))
+        applied += r
+    assert applied > 20000
