@@ -61,6 +61,35 @@ SJ_HD bool atom_ok_p(const R& rd, uint64_t pos, uint64_t len, uint32_t type) {
     return structural_or_ws_or_nul_p(rd(pos + n));
 }
 
+// The same test for an atom that lies, with the byte behind it and then some, inside the step image (o + 8 <= avail):
+// three aligned words, two funnel shifts, word compares; the byte behind the literal is looked up in a 128-bit set.
+// Returns false when it does not apply (atom_ok_p is the definition); *ch = the atom's first byte.
+SJ_HD bool atom_ok_fast(const uint8_t* img, uint32_t o, uint32_t avail, uint32_t* ch, bool* ok) {
+    if (o + 8 > avail) return false;
+    const uint32_t a = o & ~3u, sh = 8 * (o & 3u);
+    const uint32_t a2 = a + 8 < S2S_STEP_BYTES ? a + 8 : a + 4;  // (the third word only matters when sh != 0, and then it is inside)
+    const uint32_t w0 = *reinterpret_cast<const uint32_t*>(img + swz(a)), w1 = *reinterpret_cast<const uint32_t*>(img + swz(a + 4));
+    const uint32_t w2 = *reinterpret_cast<const uint32_t*>(img + swz(a2));
+    const uint32_t q0 = pi::funnel_r(w0, w1, sh), q1 = pi::funnel_r(w1, w2, sh);
+    const uint32_t c = q0 & 0xffu;
+    *ch = c;
+    uint32_t follow;
+    bool lit;
+    if (c == 't') {
+        lit = q0 == 0x65757274u, follow = q1 & 0xffu;
+    } else if (c == 'n') {
+        lit = q0 == 0x6c6c756eu, follow = q1 & 0xffu;
+    } else if (c == 'f') {
+        lit = q0 == 0x736c6166u && (q1 & 0xffu) == 'e', follow = (q1 >> 8) & 0xffu;
+    } else {
+        return false;
+    }
+    // NUL \t \n \r | space , : | [ ] | { }   (structural_or_ws_or_nul_p)
+    const uint32_t set = follow < 32 ? 0x00002601u : follow < 64 ? 0x04001001u : follow < 96 ? 0x28000000u : 0x28000000u;
+    *ok = lit && follow < 128 && ((set >> (follow & 31u)) & 1u) != 0;
+    return true;
+}
+
 // mark [lo, hi) (bit numbers relative to a block, hi <= 64 + 32) in a 64-bit mask and in the spill word behind it
 SJ_HD void mark_range(uint64_t& m, uint32_t& spill, uint32_t lo, uint32_t hi) {
     m |= range64(lo, hi < 64 ? hi : 64);
@@ -388,8 +417,17 @@ SJ_HD void s2s_slab(W& wp, const S2sParams& p, uint32_t slab, const S2sWarpMem& 
             }
             const uint32_t e_tot = wp.shfl(e_inc, 31);
             {
-                uint32_t k = e_inc - e_cnt;
-                for (uint64_t e = Ein; e; e &= e - 1) epos[k++] = (uint16_t)(64 * lane + pi::ctz64(e));
+                // the two 32-bit halves side by side (a 64-bit find-first-set is several instructions; two chains, half the trips)
+                uint32_t lo = (uint32_t)Ein, hi = (uint32_t)(Ein >> 32);
+                uint32_t k0 = e_inc - e_cnt, k1 = k0 + pi::popc32(lo);
+                while (lo | hi) {  // branch-free body: an exhausted half writes into a spare slot behind the list
+                    const uint32_t s0 = lo ? k0 : S2S_ESC_CAP, s1 = hi ? k1 : S2S_ESC_CAP;
+                    epos[s0] = (uint16_t)(64 * lane + pi::ctz32(lo | 0x80000000u));
+                    epos[s1] = (uint16_t)(64 * lane + 32 + pi::ctz32(hi | 0x80000000u));
+                    k0 += lo != 0, k1 += hi != 0;
+                    lo &= lo - 1;
+                    hi &= hi - 1;
+                }
             }
             wp.sync();
             uint8_t* img = const_cast<uint8_t*>(sbase);
@@ -411,8 +449,16 @@ SJ_HD void s2s_slab(W& wp, const S2sParams& p, uint32_t slab, const S2sWarpMem& 
                 wp.atomic_or_shared(dmap + wd, m << sh);
                 if (sh > 20 && (m >> (32 - sh))) wp.atomic_or_shared(dmap + wd + 1, m >> (32 - sh));  // (word 64: bytes of the next step)
                 if (EMIT) {
-                    for (uint32_t j = 0; j < ei.n; j++)
-                        if (op + j < S2S_STEP_BYTES) img[swz(op + j)] = (uint8_t)(ei.bytes >> (8 * j));
+                    if ((op & 15u) + ei.n <= 16u && op + ei.n <= S2S_STEP_BYTES) {  // inside one 16-byte chunk of the image: one address
+                        uint8_t* q = img + swz(op);
+                        q[0] = (uint8_t)ei.bytes;
+                        if (ei.n > 1) q[1] = (uint8_t)(ei.bytes >> 8);
+                        if (ei.n > 2) q[2] = (uint8_t)(ei.bytes >> 16);
+                        if (ei.n > 3) q[3] = (uint8_t)(ei.bytes >> 24);
+                    } else {
+                        for (uint32_t j = 0; j < ei.n; j++)
+                            if (op + j < S2S_STEP_BYTES) img[swz(op + j)] = (uint8_t)(ei.bytes >> (8 * j));
+                    }
                 }
                 if (op + ei.n > S2S_STEP_BYTES) {  // output bytes behind the end of the step: the next step patches them in
                     const uint32_t k0 = op < S2S_STEP_BYTES ? S2S_STEP_BYTES - op : 0u;
@@ -726,8 +772,13 @@ SJ_HD void s2s_slab(W& wp, const S2sParams& p, uint32_t slab, const S2sWarpMem& 
                 for (uint32_t mm = atm; mm; mm &= mm - 1) {
                     const uint32_t j = pi::ctz32(mm), bit = 1u << j, lo = bit - 1u;
                     const uint32_t slot = words_b + pi::popc32(w1 & lo) + 2 * (pi::popc32(w2 & lo) + pi::popc32(rs & (lo | bit)));
-                    const uint32_t ch = sbase[swz(64 * lane + 32 * h + j)];
-                    if (!atom_ok_p(rd, half_pos + j, p.len, sm.ctab[ch])) err = 1;
+                    uint32_t ch;
+                    bool ok;
+                    if (!atom_ok_fast(sbase, 64 * lane + 32 * h + j, (uint32_t)(rd.slab_end - rd.slab_start), &ch, &ok)) {
+                        ch = sbase[swz(64 * lane + 32 * h + j)];
+                        ok = atom_ok_p(rd, half_pos + j, p.len, sm.ctab[ch]);
+                    }
+                    if (!ok) err = 1;
                     tout[slot] = (uint64_t)ch << 56;
                 }
                 // totals of the half

@@ -294,3 +294,23 @@ extern "C" long s2s_emu_esc_fast_check(const uint8_t* step, uint32_t avail) {
     }
     return applied;
 }
+
+// atom_ok_fast against atom_ok_p at every position of a step that holds 't', 'f' or 'n' (the bytes are whatever the test
+// put there): the number of positions where the fast path applied, or -(o + 1) at the first disagreement
+extern "C" long s2s_emu_atom_fast_check(const uint8_t* step, uint32_t avail, uint64_t len) {
+    alignas(16) static uint8_t img[S2S_STEP_BYTES];
+    for (uint32_t i = 0; i < S2S_STEP_BYTES; i++) img[swz(i)] = step[i];
+    const GlobalReader g{step, len};
+    long applied = 0;
+    for (uint32_t o = 0; o < avail; o++) {
+        uint32_t ch = 0;
+        bool ok = false;
+        if (!atom_ok_fast(img, o, avail, &ch, &ok)) continue;
+        if (ch != step[o]) return -(long)(o + 1);
+        const uint32_t type = char_type(ch);
+        if (type != T_TRUE && type != T_FALSE && type != T_NULL) return -(long)(o + 1);
+        if (atom_ok_p(g, o, len, type) != ok) return -(long)(o + 1);
+        applied++;
+    }
+    return applied;
+}

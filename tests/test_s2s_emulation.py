@@ -188,3 +188,27 @@ def test_escape_fast_path_is_the_definition():
         assert r >= 0, (it, -r - 1, bytes(step[max(0, -r - 8): -r + 8]))
         applied += r
     assert applied > 20000
+
+
+def test_atom_fast_path_is_the_definition():
+    """atom_ok_fast (word compares on the step image) against atom_ok_p (stage2_build_tape_amd64.go:124-158, 455-476): steps
+    full of true / false / null, near misses and every kind of byte behind them, at every alignment and near the end"""
+    import ctypes as C
+    from tests import emu_util
+    L = emu_util.lib()
+    L.s2s_emu_atom_fast_check.restype = C.c_long
+    L.s2s_emu_atom_fast_check.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64]
+    rng = np.random.default_rng(7)
+    words = [b"true", b"false", b"null", b"tru", b"fals", b"nul", b"trve", b"falsf", b"nulL", b"True", b"t", b"f", b"n", b"truetrue", b"nullfalse"]
+    follow = [bytes([c]) for c in (0, 9, 10, 13, 32, 44, 58, 91, 93, 123, 125, 11, 12, 31, 33, 34, 43, 45, 59, 92, 94, 122, 124, 126, 127, 128, 255, 48, 101)]
+    applied = 0
+    for it in range(300):
+        out = bytearray()
+        while len(out) < 2048 + 16:
+            out += words[int(rng.integers(0, len(words)))] + follow[int(rng.integers(0, len(follow)))] * int(rng.integers(1, 3))
+        step = np.frombuffer(bytes(out[:2048]), dtype=np.uint8).copy()
+        avail = 2048 if it % 3 else int(rng.integers(1, 2049))
+        r = L.s2s_emu_atom_fast_check(step.ctypes.data, avail, avail)
+        assert r >= 0, (it, -r - 1, bytes(step[max(0, -r - 4): -r + 10]))
+        applied += r
+    assert applied > 50000
