@@ -58,4 +58,49 @@ same(b"[" + b"[1," * 3000 + b"1" + b"]" * 3000 + b"]")
 same(b"[" + b",".join(b"%d.%de%d" % (i, i * 7919 % 100000, i % 30 - 15) for i in range(4000)) + b"]")
 same(b'{"a":tru}')
 same(b'["abc\\q"]')
+# the sharded ParseND with the exchange kernel over peer memory (exchange.cuh): two host threads = two ranks on this GPU
+import ctypes as C
+import threading
+
+import torch
+
+from simdjson_b200.parallel import ShardedParse, split_at_newlines, trimmed_window
+
+stream = pk[:60000].rsplit(b"\n", 1)[0] + b'\n{"esc":"a\\u00e9\\n","n":[1,2.5,-3],"t":true}'
+rc_o, tape_o, str_o, (off_o, len_o) = o.parse(stream, ndjson=True, copy_strings=True)
+wins = [trimmed_window(stream, a, b) for a, b in split_at_newlines(stream, 2)]
+cx = [sj.Context(0), sj.Context(0)]
+for r, c in enumerate(cx):
+    assert c.L.sj_exchange_create(c.h, r, 2, 1, None) == 0
+    assert c.L.sj_exchange_set_timeout_ms(c.h, 120000) == 0
+locs = (C.c_void_p * 2)(*[c.L.sj_exchange_local(c.h) for c in cx])
+res = [None, None]
+
+
+def rank(r):
+    c = cx[r]
+    a, b = wins[r]
+    assert c.L.sj_exchange_connect_ptrs(c.h, locs) == 0
+    assert c.L.sj_exchange_set_gap(c.h, wins[1][0] - b if r == 0 else 0) == 0
+    dev = torch.device("cuda:0")
+    d_msg = torch.full((b - a + 256,), 0x20, dtype=torch.uint8, device=dev)
+    d_msg[: b - a] = torch.frombuffer(bytearray(stream[a:b]), dtype=torch.uint8).to(dev)
+    torch.cuda.synchronize()
+    sp = ShardedParse(c)
+    rc, tot = sp.count(d_msg.data_ptr(), b - a, True)
+    assert rc == 0, rc
+    d_tape = torch.empty(tot[1] + 8, dtype=torch.int64, device=dev)
+    d_str = torch.empty(tot[2] + 64, dtype=torch.uint8, device=dev)
+    assert sp.emit(0, 0, 0, d_tape.data_ptr(), d_tape.numel(), d_str.data_ptr(), d_str.numel(), c.L.sj_exchange_bases(c.h)) == 0
+    res[r] = (d_tape[: tot[1]].cpu().numpy().view(np.uint64), d_str[: tot[2]].cpu().numpy().tobytes())
+
+
+ts = [threading.Thread(target=rank, args=(r,)) for r in range(2)]
+for t in ts:
+    t.start()
+for t in ts:
+    t.join()
+assert res[0] is not None and res[1] is not None
+assert np.array_equal(np.concatenate([res[0][0], res[1][0]]), tape_o) and res[0][1] + res[1][1] == str_o
+n += 1
 print("sanitize_run ok: %d documents, %d kernel launches" % (n, ctx.launches()))
