@@ -595,7 +595,7 @@ struct S2sWarpMem {
 constexpr uint32_t S2S_ESC_CAP = S2S_STEP_BYTES / 2;
 constexpr uint32_t S2S_ESC_DMAP_WORDS = S2S_STEP_BYTES / 32 + 1;
 constexpr uint32_t S2S_ESC_REC_OFS = 272, S2S_ESC_LIST_OFS = 288;
-constexpr uint32_t S2S_ESC_SCRATCH = S2S_ESC_LIST_OFS + 2 * S2S_ESC_CAP + 16;  // list + one spare slot, 2352 bytes
+constexpr uint32_t S2S_ESC_SCRATCH = S2S_ESC_LIST_OFS + 2 * (S2S_ESC_CAP + 32);  // list + one spare slot per lane, 2400 bytes
 static_assert(S2S_ESC_DMAP_WORDS * 4 <= S2S_ESC_REC_OFS, "drop map fits in front of the record");
 // digit_to_val_p with the raw quote and every non-digit folded into one "invalid" code (see hex4_at)
 SJ_HDC uint32_t hex_code(uint32_t c) {

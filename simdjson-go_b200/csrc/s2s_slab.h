@@ -420,8 +420,8 @@ SJ_HD void s2s_slab(W& wp, const S2sParams& p, uint32_t slab, const S2sWarpMem& 
                 // the two 32-bit halves side by side (a 64-bit find-first-set is several instructions; two chains, half the trips)
                 uint32_t lo = (uint32_t)Ein, hi = (uint32_t)(Ein >> 32);
                 uint32_t k0 = e_inc - e_cnt, k1 = k0 + pi::popc32(lo);
-                while (lo | hi) {  // branch-free body: an exhausted half writes into a spare slot behind the list
-                    const uint32_t s0 = lo ? k0 : S2S_ESC_CAP, s1 = hi ? k1 : S2S_ESC_CAP;
+                while (lo | hi) {  // branch-free body: an exhausted half writes into the lane's spare slot behind the list
+                    const uint32_t s0 = lo ? k0 : S2S_ESC_CAP + lane, s1 = hi ? k1 : S2S_ESC_CAP + lane;
                     epos[s0] = (uint16_t)(64 * lane + pi::ctz32(lo | 0x80000000u));
                     epos[s1] = (uint16_t)(64 * lane + 32 + pi::ctz32(hi | 0x80000000u));
                     k0 += lo != 0, k1 += hi != 0;
@@ -433,39 +433,53 @@ SJ_HD void s2s_slab(W& wp, const S2sParams& p, uint32_t slab, const S2sWarpMem& 
             uint8_t* img = const_cast<uint8_t*>(sbase);
             const uint32_t avail = (uint32_t)(rd.slab_end - rd.slab_start);  // image bytes that are message bytes
             const ImageReader ird{sbase, (uint32_t)step_start, (uint32_t)(rd.slab_end - rd.slab_start), p.msg, p.len};
-            for (uint32_t i = lane; i < e_tot; i += 32) {
-                const uint32_t o = epos[i];
+            // rounds of 32 escapes; in the emitting pass a round's patches wait until every lane has read what it needs (the
+            // fast path reads whole words of the image, a patch writes bytes inside them), and the next round's reads wait
+            // for the patches
+            for (uint32_t base = 0; base < e_tot; base += 32) {  // warp-uniform trips
+                const uint32_t i = base + lane;
+                uint32_t o = 0;
                 EscInfo ei;
-                if (!esc_u_fast(sbase, o, avail, ei)) ei = esc_decode(ird, g, step_start + o);
-                if (ei.second) continue;
-                if (!ei.valid) {
-                    err = 1;
-                    continue;
-                }
-                const uint32_t op = o + ei.c - ei.n;  // first output position (image offset; may lie behind the step)
-                // all c source bytes are dropped except the last n, which hold the output
-                const uint32_t m = ((1u << ei.c) - 1u) & ~(((1u << ei.n) - 1u) << (ei.c - ei.n));
-                const uint32_t wd = o >> 5, sh = o & 31u;
-                wp.atomic_or_shared(dmap + wd, m << sh);
-                if (sh > 20 && (m >> (32 - sh))) wp.atomic_or_shared(dmap + wd + 1, m >> (32 - sh));  // (word 64: bytes of the next step)
-                if (EMIT) {
-                    if ((op & 15u) + ei.n <= 16u && op + ei.n <= S2S_STEP_BYTES) {  // inside one 16-byte chunk of the image: one address
-                        uint8_t* q = img + swz(op);
-                        q[0] = (uint8_t)ei.bytes;
-                        if (ei.n > 1) q[1] = (uint8_t)(ei.bytes >> 8);
-                        if (ei.n > 2) q[2] = (uint8_t)(ei.bytes >> 16);
-                        if (ei.n > 3) q[3] = (uint8_t)(ei.bytes >> 24);
-                    } else {
-                        for (uint32_t j = 0; j < ei.n; j++)
-                            if (op + j < S2S_STEP_BYTES) img[swz(op + j)] = (uint8_t)(ei.bytes >> (8 * j));
+                ei.c = 0, ei.n = 0, ei.bytes = 0, ei.valid = false, ei.second = false;
+                bool live = false;
+                if (i < e_tot) {
+                    o = epos[i];
+                    if (!esc_u_fast(sbase, o, avail, ei)) ei = esc_decode(ird, g, step_start + o);
+                    if (!ei.second) {
+                        if (!ei.valid)
+                            err = 1;
+                        else
+                            live = true;
                     }
                 }
-                if (op + ei.n > S2S_STEP_BYTES) {  // output bytes behind the end of the step: the next step patches them in
-                    const uint32_t k0 = op < S2S_STEP_BYTES ? S2S_STEP_BYTES - op : 0u;
-                    rec[0] = ei.n - k0;
-                    rec[1] = op < S2S_STEP_BYTES ? 0u : op - S2S_STEP_BYTES;
-                    rec[2] = ei.bytes >> (8 * k0);
+                if (EMIT) wp.sync();
+                if (live) {
+                    const uint32_t op = o + ei.c - ei.n;  // first output position (image offset; may lie behind the step)
+                    // all c source bytes are dropped except the last n, which hold the output
+                    const uint32_t m = ((1u << ei.c) - 1u) & ~(((1u << ei.n) - 1u) << (ei.c - ei.n));
+                    const uint32_t wd = o >> 5, sh = o & 31u;
+                    wp.atomic_or_shared(dmap + wd, m << sh);
+                    if (sh > 20 && (m >> (32 - sh))) wp.atomic_or_shared(dmap + wd + 1, m >> (32 - sh));  // (word 64: bytes of the next step)
+                    if (EMIT) {
+                        if ((op & 15u) + ei.n <= 16u && op + ei.n <= S2S_STEP_BYTES) {  // inside one 16-byte chunk of the image: one address
+                            uint8_t* q = img + swz(op);
+                            q[0] = (uint8_t)ei.bytes;
+                            if (ei.n > 1) q[1] = (uint8_t)(ei.bytes >> 8);
+                            if (ei.n > 2) q[2] = (uint8_t)(ei.bytes >> 16);
+                            if (ei.n > 3) q[3] = (uint8_t)(ei.bytes >> 24);
+                        } else {
+                            for (uint32_t j = 0; j < ei.n; j++)
+                                if (op + j < S2S_STEP_BYTES) img[swz(op + j)] = (uint8_t)(ei.bytes >> (8 * j));
+                        }
+                    }
+                    if (op + ei.n > S2S_STEP_BYTES) {  // output bytes behind the end of the step: the next step patches them in
+                        const uint32_t k0 = op < S2S_STEP_BYTES ? S2S_STEP_BYTES - op : 0u;
+                        rec[0] = ei.n - k0;
+                        rec[1] = op < S2S_STEP_BYTES ? 0u : op - S2S_STEP_BYTES;
+                        rec[2] = ei.bytes >> (8 * k0);
+                    }
                 }
+                if (EMIT) wp.sync();
             }
             wp.sync();
             D = mk64u(dmap[2 * lane], dmap[2 * lane + 1]);
