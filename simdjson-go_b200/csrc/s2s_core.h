@@ -587,7 +587,6 @@ struct S2sWarpMem {
     const uint8_t* ctab;   // [256] char_type
     const uint8_t* oktab;  // [256] transition_mask(p, c) at [p * 16 + c]
     const uint32_t* cmptab;  // [16] compress_sel(m) | popcount(m) << 16
-    const uint8_t* hextab;   // [256] hex_code
     uint8_t* esc;            // [S2S_ESC_SCRATCH] drop map + list of a step's escapes (K2r: the tape staging area, idle then)
 };
 // scratch of a step's escapes: the drop map (one bit per image byte + one word behind the step), the record of the escape
@@ -597,15 +596,6 @@ constexpr uint32_t S2S_ESC_DMAP_WORDS = S2S_STEP_BYTES / 32 + 1;
 constexpr uint32_t S2S_ESC_REC_OFS = 272, S2S_ESC_LIST_OFS = 288;
 constexpr uint32_t S2S_ESC_SCRATCH = S2S_ESC_LIST_OFS + 2 * (S2S_ESC_CAP + 32);  // list + one spare slot per lane, 2400 bytes
 static_assert(S2S_ESC_DMAP_WORDS * 4 <= S2S_ESC_REC_OFS, "drop map fits in front of the record");
-// digit_to_val_p with the raw quote and every non-digit folded into one "invalid" code (see hex4_at)
-SJ_HDC uint32_t hex_code(uint32_t c) {
-    return c == '"' ? 0x80u
-           : c < 0x30 ? 0u
-           : c <= '9' ? c - '0'
-           : ((c | 0x20u) >= 'a' && (c | 0x20u) <= 'f' && c >= 'A' && c < 0x80) ? (c | 0x20u) - 'a' + 10u
-                                                                                 : 0x80u;
-}
-
 // byte offset of message byte `o` of a step inside the swizzled step image: the four 16-byte chunks of block b are
 // stored at chunk slots (j ^ ((b >> 1) & 3)) -- the pattern of a 64-byte TMA swizzle -- so that lane b reading its
 // chunk j (LDS.128) is bank-conflict free for every j in NATURAL order (no mask rotation afterwards)

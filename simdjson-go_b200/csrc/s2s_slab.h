@@ -90,15 +90,6 @@ SJ_HD bool atom_ok_fast(const uint8_t* img, uint32_t o, uint32_t avail, uint32_t
     return true;
 }
 
-// mark [lo, hi) (bit numbers relative to a block, hi <= 64 + 32) in a 64-bit mask and in the spill word behind it
-SJ_HD void mark_range(uint64_t& m, uint32_t& spill, uint32_t lo, uint32_t hi) {
-    m |= range64(lo, hi < 64 ? hi : 64);
-    if (hi > 64) {
-        const uint32_t a = lo > 64 ? lo - 64 : 0, b = hi - 64;
-        spill |= (uint32_t)range64(a, b);
-    }
-}
-
 // esc_decode for the common case -- "\\uXXXX" with four proper hex digits, not a surrogate, and nothing that looks like a
 // high surrogate six bytes in front of it -- straight from the step image with word accesses and register arithmetic
 // only: four aligned words cover the twelve bytes [o - 6, o + 6), funnel shifts align them, the hex digits are checked

@@ -72,14 +72,12 @@ struct S2sTables {
     uint8_t ctab[256];
     uint8_t oktab[256];
     uint32_t cmptab[16];
-    uint8_t hextab[256];
 };
 __device__ __forceinline__ void s2s_fill_tables(S2sTables& t) {
     for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
         t.ctab[i] = (uint8_t)char_type(i);
         const uint32_t p = i >> 4, c = i & 15;
         t.oktab[i] = (p < 15 && c < 15) ? (uint8_t)transition_mask(p, c) : (uint8_t)0;
-        t.hextab[i] = (uint8_t)hex_code(i);
     }
     if (threadIdx.x < 16) t.cmptab[threadIdx.x] = compress_sel(threadIdx.x) | ((uint32_t)__popc(threadIdx.x) << 16);
 }
@@ -98,7 +96,6 @@ __global__ void __launch_bounds__(S2S_THREADS, SJ_S2S_COUNT_MIN_BLOCKS) s2s_coun
     sm.ctab = tabs.ctab;
     sm.oktab = tabs.oktab;
     sm.cmptab = tabs.cmptab;
-    sm.hextab = tabs.hextab;
     DevWarp wp;
     s2s_warp_loop<DevWarp, false>(wp, p, blockIdx.x * S2S_WARPS + warp, gridDim.x * S2S_WARPS, sm);
 }
@@ -118,7 +115,6 @@ __global__ void __launch_bounds__(S2S_THREADS, SJ_S2S_EMIT_MIN_BLOCKS) s2s_emit_
     sm.ctab = tabs.ctab;
     sm.oktab = tabs.oktab;
     sm.cmptab = tabs.cmptab;
-    sm.hextab = tabs.hextab;
     DevWarp wp;
     s2s_warp_loop<DevWarp, true>(wp, p, blockIdx.x * S2S_WARPS + warp, gridDim.x * S2S_WARPS, sm);
 }

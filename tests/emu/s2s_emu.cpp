@@ -125,9 +125,7 @@ struct FiberWarp {
 struct Tables {
     uint8_t ctab[256], oktab[256];
     uint32_t cmptab[16];
-    uint8_t hextab[256];
     Tables() {
-        for (int i = 0; i < 256; i++) hextab[i] = (uint8_t)hex_code((uint32_t)i);
         for (int i = 0; i < 256; i++) ctab[i] = (uint8_t)char_type((uint32_t)i);
         memset(oktab, 0, sizeof oktab);
         for (uint32_t p = 0; p < 15; p++)
@@ -188,7 +186,6 @@ extern "C" int s2s_emu_parse(const uint8_t* msg, size_t len, int ndjson, const u
     sm.ctab = T.ctab;
     sm.oktab = T.oktab;
     sm.cmptab = T.cmptab;
-    sm.hextab = T.hextab;
     FiberWarp W;
     // ---- K2p ----
     // (three "warps" of a stride-3 grid, so that the hand-over of the image pipeline from slab to slab is exercised)
