@@ -655,7 +655,10 @@ SJ_HD void s2s_slab(W& wp, const S2sParams& p, uint32_t slab, const S2sWarpMem& 
         }
 
         // ---------------- the lane's events, in order ----------------
-        const bool staged = w_step <= S2S_TSTAGE_WORDS;  // warp-uniform
+#ifndef SJ_S2S_DIRECT_TAPE
+#define SJ_S2S_DIRECT_TAPE 0  // 1: tape words always go straight to global memory (A/B switch; see profiles/README.md)
+#endif
+        const bool staged = !SJ_S2S_DIRECT_TAPE && w_step <= S2S_TSTAGE_WORDS;  // warp-uniform
         const uint32_t slot0 = 1 + run.w;                // tape slot of the step's first word (slot 0: the first root word)
         uint64_t* tout = staged ? sm.tstage - slot0 : p.tape;
         {

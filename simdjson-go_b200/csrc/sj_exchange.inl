@@ -82,18 +82,37 @@ extern "C" int sj_exchange_set_timeout_ms(sj_ctx* c, uint32_t ms) {
 
 extern "C" void* sj_exchange_local(sj_ctx* c) { return c && xchg_of(c) ? xchg_of(c)->d_local : nullptr; }
 
-extern "C" int sj_exchange_connect_ptrs(sj_ctx* c, void* const* peer_buffers) {
-    SjExchange* x = c ? xchg_of(c) : nullptr;
-    if (!x || !peer_buffers) return SJ_ERR_ARGUMENT;
-    SJ_CUDA_CHECK(cudaSetDevice(c->device));
+// `enable_peer`: the buffers were handed in as plain pointers -- those on another device of this process (one process driving
+// several GPUs, a goroutine / thread per context) need peer access from this context's device; buffers opened through CUDA
+// IPC have it already (cudaIpcMemLazyEnablePeerAccess)
+static int exchange_set_table(sj_ctx* c, void* const* peer_buffers, bool enable_peer) {
+    SjExchange* x = xchg_of(c);
     uint64_t* tab[sj::XCHG_MAX_WORLD] = {};
     for (int r = 0; r < x->world; r++) {
         tab[r] = r == x->rank ? x->d_local : static_cast<uint64_t*>(peer_buffers[r]);
         if (!tab[r]) return SJ_ERR_ARGUMENT;
+        if (enable_peer && r != x->rank) {
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, tab[r]) == cudaSuccess && at.type == cudaMemoryTypeDevice && at.device != c->device) {
+                const cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                    cudaGetLastError();
+                    return -(1000 + (int)e);
+                }
+            }
+            cudaGetLastError();  // (cudaErrorPeerAccessAlreadyEnabled is sticky-free but reported once)
+        }
     }
     SJ_CUDA_CHECK(cudaMemcpy(x->d_peers, tab, sizeof tab, cudaMemcpyHostToDevice));
     x->connected = true;
     return SJ_OK;
+}
+
+extern "C" int sj_exchange_connect_ptrs(sj_ctx* c, void* const* peer_buffers) {
+    SjExchange* x = c ? xchg_of(c) : nullptr;
+    if (!x || !peer_buffers) return SJ_ERR_ARGUMENT;
+    SJ_CUDA_CHECK(cudaSetDevice(c->device));
+    return exchange_set_table(c, peer_buffers, true);
 }
 
 extern "C" int sj_exchange_connect(sj_ctx* c, const void* handles) {
@@ -111,7 +130,7 @@ extern "C" int sj_exchange_connect(sj_ctx* c, const void* handles) {
         if (!x->opened[r]) SJ_CUDA_CHECK(cudaIpcOpenMemHandle(&x->opened[r], h, cudaIpcMemLazyEnablePeerAccess));
         tab[r] = x->opened[r];
     }
-    return sj_exchange_connect_ptrs(c, tab);
+    return exchange_set_table(c, tab, false);
 }
 
 extern "C" const uint64_t* sj_exchange_bases(sj_ctx* c) { return c && xchg_of(c) ? xchg_of(c)->d_out : nullptr; }
