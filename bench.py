@@ -286,7 +286,7 @@ def main():
         rc_x = sp.connect_exchange(rank, world, gap_bytes=1) if not args.nccl_exchange else -1
         if rc_x == 0:
             exchange = "peer"
-            L.sj_exchange_set_timeout_ms(ctx.h, 20000)
+            L.sj_exchange_set_timeout_ms(ctx.h, 60000)
         else:
             exchange = "nccl"
             L.sj_ctx_set_stream(ctx.h, torch.cuda.current_stream().cuda_stream)
@@ -331,6 +331,7 @@ def main():
         return float(t.item())
 
     # ---- value: device resident ----
+    barrier()  # (the ranks leave their set-up seconds apart; the sharded step is a collective call with a time limit)
     for _ in range(args.warmup):
         step_device()
     ms = C.c_float(0)
