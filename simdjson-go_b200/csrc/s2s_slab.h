@@ -656,7 +656,8 @@ SJ_HD void s2s_slab(W& wp, const S2sParams& p, uint32_t slab, const S2sWarpMem& 
 
         // ---------------- the lane's events, in order ----------------
 #ifndef SJ_S2S_DIRECT_TAPE
-#define SJ_S2S_DIRECT_TAPE 0  // 1: tape words always go straight to global memory (A/B switch; see profiles/README.md)
+#define SJ_S2S_DIRECT_TAPE 1  // tape words go straight to global memory (0: staged in shared memory and copied out coalesced --
+                              // measured: twitter 218 -> 224 GB/s, twitterescaped 110 -> 113, gsoc-2018 267 -> 275, parking-citations the same)
 #endif
         const bool staged = !SJ_S2S_DIRECT_TAPE && w_step <= S2S_TSTAGE_WORDS;  // warp-uniform
         const uint32_t slot0 = 1 + run.w;                // tape slot of the step's first word (slot 0: the first root word)
