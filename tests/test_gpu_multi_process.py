@@ -29,7 +29,8 @@ def _worker(rank, world, port, copy, outdir):
     from simdjson_b200.parallel import ShardedParse, split_at_newlines, trimmed_window
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import datetime
+    dist.init_process_group("gloo", rank=rank, world_size=world, timeout=datetime.timedelta(seconds=120))
     try:
         devno = rank % torch.cuda.device_count()
         torch.cuda.set_device(devno)
@@ -66,6 +67,7 @@ def _worker(rank, world, port, copy, outdir):
         dist.destroy_process_group()
 
 
+@pytest.mark.timeout(600)
 @pytest.mark.parametrize("copy", [True, False])
 def test_two_processes_exchange_through_cuda_ipc(tmp_path, oracle_native, copy):
     import torch.multiprocessing as mp
