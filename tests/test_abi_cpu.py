@@ -33,6 +33,39 @@ def test_every_declared_symbol_is_exported(lib):
     assert sorted(_lib.EXPORTS) == names
 
 
+def test_python_mirror_uses_the_headers_numbers(lib):
+    """return codes, flags and the exchange handle size of the ctypes mirror are the header's #defines; sj_error_string knows
+    every code"""
+    from simdjson_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "simdjson_b200.h")).read()
+    defs = {k: int(v.rstrip("u"), 0) for k, v in re.findall(r"#define\s+(SJ_[A-Z0-9_]+)\s+(0x[0-9a-fA-F]+u?|[0-9]+u?)\b", src)}
+    for name, val in (("SJ_OK", _lib.OK), ("SJ_ERR_STAGE1", _lib.ERR_STAGE1), ("SJ_ERR_STAGE2", _lib.ERR_STAGE2),
+                      ("SJ_ERR_NO_DEVICE", _lib.ERR_NO_DEVICE), ("SJ_ERR_CAPACITY", _lib.ERR_CAPACITY),
+                      ("SJ_ERR_TOO_LARGE", _lib.ERR_TOO_LARGE), ("SJ_ERR_ARGUMENT", _lib.ERR_ARGUMENT),
+                      ("SJ_ERR_EXCHANGE", _lib.ERR_EXCHANGE), ("SJ_ERR_PEER", _lib.ERR_PEER),
+                      ("SJ_FLAG_NDJSON", _lib.FLAG_NDJSON), ("SJ_FLAG_COPY_STRINGS", _lib.FLAG_COPY_STRINGS),
+                      ("SJ_EXCHANGE_HANDLE_BYTES", _lib.EXCHANGE_HANDLE_BYTES)):
+        assert defs[name] == val, name
+    lib.sj_error_string.restype = C.c_char_p
+    codes = [v for k, v in defs.items() if k.startswith(("SJ_ERR_", "SJ_STREAM_")) or k == "SJ_OK"]
+    assert len(set(codes)) == len(codes)  # no two codes share a number
+    for v in codes:
+        assert lib.sj_error_string(v) not in (None, b"", b"unknown error"), v
+
+
+def test_exchange_needs_a_context(lib):
+    """the exchange entry points take a context that owns an exchange: without one they refuse (no device here, so no
+    context can exist) instead of touching memory"""
+    assert lib.sj_exchange_create(None, 0, 2, 1, None) != 0
+    assert lib.sj_exchange_connect(None, None) != 0
+    assert lib.sj_exchange_connect_ptrs(None, None) != 0
+    assert lib.sj_exchange_set_gap(None, 1) != 0
+    assert lib.sj_exchange_set_timeout_ms(None, 1000) != 0
+    assert not lib.sj_exchange_local(None) and not lib.sj_exchange_bases(None)
+    out = (C.c_uint64 * 10)()
+    assert lib.sj_exchange_result(None, out) != 0
+
+
 def test_no_device_means_no_service(lib):
     import torch
     if torch.cuda.is_available():
